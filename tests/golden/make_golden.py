@@ -1,0 +1,85 @@
+"""Generate the golden fixtures tests/golden/*.npz.
+
+BUILD-CONTAINER ONLY (needs /root/reference).  For every case of cases.CASES it runs
+the REFERENCE's own Python -- Param, Grid, Fluid2d, Euler/Boussinesq/QG, Timescheme,
+Operators, gmg.Gmg -- with the reference's f2py kernels replaced by the CPU oracle
+(oracle/refshim.py), and freezes:
+
+  state0            full model state handed to the time loop
+  state{k}, t{k}, dt{k}, diag{k}_<name>   after k = 1 and 10 iterations of the loop body
+  mg_nlevs, mg_msk{l}, mg_A{l}            multigrid masks and 5-diagonal matrices
+  mg_shape{l}                             (m, n) interior size per level
+  varnames, grid_msk
+
+Usage:  python tests/golden/make_golden.py [case ...]
+"""
+import io
+import os
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+
+from oracle import refshim  # noqa: E402
+
+
+def reference_api():
+    refshim.install()
+    import types
+    from param import Param
+    from grid import Grid
+    from fluid2d import Fluid2d
+    return types.SimpleNamespace(Param=Param, Grid=Grid, Fluid2d=Fluid2d, name="reference")
+
+
+def generate(names=None):
+    import numpy as np
+    sys.path.insert(0, HERE)
+    import cases
+    api = reference_api()
+    datadir = tempfile.mkdtemp(prefix="f2d_golden_")
+    real_stdout = sys.stdout
+    for name, builder in cases.CASES.items():
+        if names and name not in names:
+            continue
+        sys.stdout = io.StringIO()
+        try:
+            f2d = builder(api, datadir)
+            log = sys.stdout
+        finally:
+            pass
+        sys.stdout = io.StringIO()   # Fluid2d installs a tee Logger; silence it
+        model = f2d.model
+        out = {}
+        out["varnames"] = np.array(model.var.varname_list)
+        out["state0"] = np.array(model.var.state, copy=True)
+        out["grid_msk"] = np.array(f2d.msk if hasattr(f2d, "msk") else model.msk, copy=True)
+        gmg = model.ope.gmg
+        out["mg_nlevs"] = np.array(gmg.nlevs)
+        for lev in range(gmg.nlevs):
+            g = gmg.grid[lev]
+            out["mg_msk%i" % lev] = np.array(g.msk, dtype=np.int8, copy=True)
+            out["mg_A%i" % lev] = np.array(g.A, copy=True)
+            out["mg_shape%i" % lev] = np.array([g.m, g.n])
+        res = cases.run_steps(f2d)
+        for k, (state, t, dt, diags) in res.items():
+            out["state%i" % k] = state
+            out["t%i" % k] = np.array(t)
+            out["dt%i" % k] = np.array(dt)
+            for dn, dv in diags.items():
+                out["diag%i_%s" % (k, dn)] = np.array(dv)
+        sys.stdout = real_stdout
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("%-28s -> %s (%.0f KB)  t10=%.6g  maxspeed=%.6g" % (
+            name, os.path.relpath(path, REPO), os.path.getsize(path)/1024.,
+            float(out["t10"]), float(out["diag10_maxspeed"])))
+    sys.stdout = real_stdout
+
+
+if __name__ == "__main__":
+    if not refshim.available():
+        sys.exit("make_golden.py needs the reference at /root/reference (build container only)")
+    generate(sys.argv[1:])

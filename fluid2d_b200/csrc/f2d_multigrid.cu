@@ -1,0 +1,641 @@
+// Geometric multigrid: gmg/hierarchy.py (Gmg), gmg/level.py (Grid, Gridinfo) and the
+// kernels of gmg/fortran_multigrid.f90, single rank.
+//
+// Device data per level: int8 corner mask, the 5 stored diagonals of the symmetric
+// 9-point matrix as 5 planes A[k][ny][nx] (k = 0..4: SW,S,SE,W,C), fields x,b,r and a
+// scratch t.  Every operator application is followed in the reference by a periodic
+// halo fill (level.py:365,384,493); here the fill is fused into the producing kernel
+// (threads owning rim cells also store the halo images).
+#include <vector>
+#include <map>
+#include <tuple>
+
+#include "f2d_common.cuh"
+
+using namespace f2d;
+
+namespace {
+constexpr int NH = 3;
+
+struct Level {
+  int ny = 0, nx = 0;       // with halos
+  int8_t *msk = nullptr;
+  double *A = nullptr;      // 5 planes
+  double *x = nullptr, *b = nullptr, *r = nullptr, *t = nullptr;
+  int mode = 0;             // 0 stored, 1 constant, 2 constant x mask products
+  size_t n() const { return (size_t)ny * nx; }
+};
+}  // namespace
+
+struct f2d_mg {
+  std::vector<Level> L;
+  double omega = 8. / 9.;
+  int npre = 1, npost = 1, ndeepest = 16, nvcyc = 1;  // hierarchy.py:29-32
+  double *scratch = nullptr;  // reductions
+  double *dscal = nullptr;    // device scalars [4]
+  double *hscal = nullptr;    // pinned host mirror [4]
+  cudaStream_t cap = nullptr; // capture stream for CUDA graphs
+  bool graphs = true;
+  struct G { cudaGraphExec_t exec; long long kernels; };
+  std::map<std::tuple<int, int, const void *, const void *>, G> cache;
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+#define IJ2()                                      \
+  int i = blockIdx.x * blockDim.x + threadIdx.x;   \
+  int j = blockIdx.y * blockDim.y + threadIdx.y;   \
+  if (i >= nx || j >= ny) return;                  \
+  size_t c = (size_t)j * nx + i
+
+inline dim3 grid2d(int ny, int nx, dim3 b) { return dim3(cdiv(nx, b.x), cdiv(ny, b.y)); }
+
+// sum over the 8 off-diagonal neighbours of A*s (fortran_multigrid.f90:68-77)
+__device__ __forceinline__ double offdiag(const double *__restrict__ A, size_t pl, const double *__restrict__ s,
+                                          size_t c, int nx) {
+  const double *A1 = A, *A2 = A + pl, *A3 = A + 2 * pl, *A4 = A + 3 * pl;
+  double acc = A1[c] * s[c - nx - 1];
+  acc = acc + A2[c] * s[c - nx];
+  acc = acc + A3[c] * s[c - nx + 1];
+  acc = acc + A4[c] * s[c - 1];
+  acc = acc + A4[c + 1] * s[c + 1];
+  acc = acc + A3[c + nx - 1] * s[c + nx - 1];
+  acc = acc + A2[c + nx] * s[c + nx];
+  acc = acc + A1[c + nx + 1] * s[c + nx + 1];
+  return acc;
+}
+
+// one damped-Jacobi sweep on [lo, n-1-lo]^2 (fortran_multigrid.f90:62-86 / :96-117);
+// fill != 0: the range is the interior and halo images are stored too
+__global__ void k_jacobi(const int8_t *__restrict__ msk, const double *__restrict__ A, const double *__restrict__ xin,
+                         const double *__restrict__ b, double *__restrict__ xout, double c1, double c2, int ny,
+                         int nx, int lo, int fill) {
+  IJ2();
+  if (j < lo || j > ny - 1 - lo || i < lo || i > nx - 1 - lo) return;
+  size_t pl = (size_t)ny * nx;
+  double val = 0.;
+  if (msk[c] != 0) {
+    double c3 = c1 / fabs(A[4 * pl + c]);
+    val = xin[c] * c2 + c3 * (offdiag(A, pl, xin, c, nx) - b[c]);
+  }
+  xout[c] = val;
+  if (fill) for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { xout[(size_t)jj * nx + ii] = val; });
+}
+
+// residual on the interior + halo images (fortran_multigrid.f90:320-362 + fill)
+__global__ void k_residual(const int8_t *__restrict__ msk, const double *__restrict__ A, const double *__restrict__ x,
+                           const double *__restrict__ b, double *__restrict__ r, int ny, int nx) {
+  IJ2();
+  if (j < NH || j > ny - 1 - NH || i < NH || i > nx - 1 - NH) return;
+  size_t pl = (size_t)ny * nx;
+  double val = 0.;
+  if (msk[c] != 0) {
+    const double *A1 = A, *A2 = A + pl, *A3 = A + 2 * pl, *A4 = A + 3 * pl, *A5 = A + 4 * pl;
+    val = b[c] - A1[c] * x[c - nx - 1];
+    val = val - A2[c] * x[c - nx];
+    val = val - A3[c] * x[c - nx + 1];
+    val = val - A4[c] * x[c - 1];
+    val = val - A5[c] * x[c];
+    val = val - A4[c + 1] * x[c + 1];
+    val = val - A3[c + nx - 1] * x[c + nx - 1];
+    val = val - A2[c + nx] * x[c + nx];
+    val = val - A1[c + nx + 1] * x[c + nx + 1];
+  }
+  r[c] = val;
+  for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { r[(size_t)jj * nx + ii] = val; });
+}
+
+// full-weighting restriction on the coarse interior + halo images
+// (fortran_multigrid.f90:501-546 + fill); msk2 == nullptr means all ones
+__global__ void k_restrict(const int8_t *__restrict__ msk2, const double *__restrict__ x1, double *__restrict__ x2,
+                           int ny, int nx /*coarse*/, int nx1) {
+  IJ2();
+  if (j < NH || j > ny - 1 - NH || i < NH || i > nx - 1 - NH) return;
+  double val = 0.;
+  if (!msk2 || msk2[c] != 0) {
+    // coarse 0-based J2 <-> fine 0-based J1 = 2*J2 - 2
+    size_t f = (size_t)(2 * j - 2) * nx1 + (2 * i - 2);
+    val = 0.25 * x1[f] +
+          0.125 * (((x1[f - 1] + x1[f + 1]) + x1[f - nx1]) + x1[f + nx1]) +
+          0.0625 * (((x1[f - nx1 - 1] + x1[f - nx1 + 1]) + x1[f + nx1 - 1]) + x1[f + nx1 + 1]);
+  }
+  x2[c] = val;
+  for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { x2[(size_t)jj * nx + ii] = val; });
+}
+
+// mask-aware bilinear interpolation over the whole fine array
+// (fortran_multigrid.f90:415-498); add: x1 += I(x2)
+__global__ void k_interpolate(const int8_t *__restrict__ msk1, const int8_t *__restrict__ msk2,
+                              const double *__restrict__ x2, double *__restrict__ x1, int ny, int nx /*fine*/,
+                              int nx2, int add) {
+  IJ2();
+  const double third = (double)0.3333333333333333333333333333f;
+  double val = 0.;
+  if (msk1[c] > 0) {
+    int j2 = (j >> 1) + 1, i2 = (i >> 1) + 1;
+    size_t k = (size_t)j2 * nx2 + i2;
+    int pj = j & 1, pi = i & 1;
+    if (!pj && !pi) {
+      val = x2[k];
+    } else if (!pj) {
+      int s = msk2[k] + msk2[k + 1];
+      double w = s == 2 ? 0.5 : (s == 1 ? 1. : 0.);
+      val = (x2[k] + x2[k + 1]) * w;
+    } else if (!pi) {
+      int s = msk2[k] + msk2[k + nx2];
+      double w = s == 2 ? 0.5 : (s == 1 ? 1. : 0.);
+      val = (x2[k] + x2[k + nx2]) * w;
+    } else {
+      int s = msk2[k] + msk2[k + 1] + msk2[k + nx2] + msk2[k + nx2 + 1];
+      double w = s == 4 ? 0.25 : (s == 3 ? third : (s == 2 ? 0.5 : (s == 1 ? 1. : 0.)));
+      val = w * (((x2[k] + x2[k + 1]) + x2[k + nx2]) + x2[k + nx2 + 1]);
+    }
+  }
+  x1[c] = add ? x1[c] + val : val;
+}
+
+// ---- set-up kernels ---------------------------------------------------------
+__global__ void k_mask_from_double(const double *__restrict__ a, int8_t *__restrict__ m, size_t n) {
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+    m[k] = (int8_t)a[k];
+}
+__global__ void k_mask_to_double(const int8_t *__restrict__ m, double *__restrict__ a, size_t n) {
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+    a[k] = (double)m[k];
+}
+__global__ void k_fill_const(double *__restrict__ a, double v, size_t n) {
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) a[k] = v;
+}
+__global__ void k_threshold_mask(const double *__restrict__ w, int8_t *__restrict__ m, size_t n) {
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+    m[k] = w[k] <= 0.5 ? 0 : 1;
+}
+struct Stencil9 { double v[9]; };
+// level.py:288-298: A_k(J,I) = stencil_k*coef*msk(J+j,I+i)*msk(J,I) on 1..n-2, 0 on the outer ring
+__global__ void k_finest_matrix(const int8_t *__restrict__ msk, double *__restrict__ A9, Stencil9 st, int ny, int nx) {
+  IJ2();
+  size_t pl = (size_t)ny * nx;
+  bool inner = (j >= 1 && j <= ny - 2 && i >= 1 && i <= nx - 2);
+  for (int k = 0; k < 9; k++) {
+    double val = 0.;
+    if (inner) {
+      int di = (k % 3) - 1, dj = (k / 3) - 1;
+      val = (st.v[k] * (double)msk[c + (ptrdiff_t)dj * nx + di]) * (double)msk[c];
+    }
+    A9[k * pl + c] = val;
+  }
+}
+// coarsenmatrix: fortran_multigrid.f90:706-811 on the coarse range nh..m2-nh (1-based)
+__global__ void k_coarsenmatrix(const double *__restrict__ Af, double *__restrict__ Ac, const int8_t *__restrict__ msk1,
+                                const int8_t *__restrict__ msk2, int ny2, int nx2, int ny1, int nx1) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  // 1-based j2 = j+1 in [nh, m2-nh]
+  if (j + 1 < NH || j + 1 > ny2 - NH || i + 1 < NH || i + 1 > nx2 - NH) return;
+  size_t c2 = (size_t)j * nx2 + i;
+  size_t pl1 = (size_t)ny1 * nx1, pl2 = (size_t)ny2 * nx2;
+  if (msk2[c2] != 1) {
+    for (int l = 0; l < 9; l++) Ac[l * pl2 + c2] = 0.;
+    return;
+  }
+  const double coefv[3] = {0.125, 0.25, 0.125};  // coef(ki,kj) = cw(ki)*cw(kj)*... see below
+  // coef table 0.125,0.25,0.125 / 0.25,0.5,0.25 / 0.125,0.25,0.125
+  auto coef = [&](int ki, int kj) -> double {
+    double a = coefv[ki + 1];
+    return kj == 0 ? 2. * a : a;
+  };
+  // fine centre, 0-based: 1-based i1 = 2*(i2-nh)+nh  ->  0-based = 2*(i+1-nh)+nh-1
+  int i1 = 2 * (i + 1 - NH) + NH - 1;
+  int j1 = 2 * (j + 1 - NH) + NH - 1;
+  for (int l = 0; l < 9; l++) {
+    int di2 = l % 3 - 1, dj2 = l / 3 - 1;
+    double z5[5][5];
+    for (int a = 0; a < 5; a++)
+      for (int b2 = 0; b2 < 5; b2++) z5[a][b2] = 0.;
+    for (int kj = -1; kj <= 1; kj++)
+      for (int ki = -1; ki <= 1; ki++) {
+        int ii = 2 * di2 + ki, jj = 2 * dj2 + kj;
+        if (abs(ii) <= 2 && abs(jj) <= 2)
+          if (msk1[(size_t)(j1 + jj) * nx1 + (i1 + ii)] == 1) z5[jj + 2][ii + 2] = 2. * coef(ki, kj);
+      }
+    double w = 0.;
+    for (int jj = -1; jj <= 1; jj++)
+      for (int ii = -1; ii <= 1; ii++) {
+        double z3 = 0.;
+        size_t f = (size_t)(j1 + jj) * nx1 + (i1 + ii);
+        if (msk1[f] == 1)
+          for (int kj = -1; kj <= 1; kj++)
+            for (int ki = -1; ki <= 1; ki++) {
+              int k = (ki + 1) + (kj + 1) * 3;
+              z3 = z3 + Af[k * pl1 + f] * z5[jj + kj + 2][ii + ki + 2];
+            }
+        w = w + (0.5 * coef(ii, jj)) * z3;
+      }
+    Ac[l * pl2 + c2] = w;
+  }
+}
+// hierarchy.py:80-84
+__global__ void k_helmholtz(double *__restrict__ A5, double shift, size_t n) {
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+    if (A5[k] != 0.) A5[k] = A5[k] - shift;
+}
+__global__ void k_add_inplace(double *__restrict__ y, const double *__restrict__ a, size_t n) {
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+    y[k] = y[k] + a[k];
+}
+
+inline int nblocks1d(size_t n) {
+  long long b = (long long)((n + 255) / 256);
+  return (int)(b > 148LL * 16 ? 148LL * 16 : (b < 1 ? 1 : b));
+}
+
+// ---------------------------------------------------------------------------
+// per-level operators
+// ---------------------------------------------------------------------------
+int op_smooth(f2d_mg *mg, int lev, double *x, const double *b, int nite, cudaStream_t s) {
+  Level &l = mg->L[lev];
+  dim3 blk(32, 8), grd = grid2d(l.ny, l.nx, blk);
+  double c1 = mg->omega, c2 = 1. - c1;
+  for (int k = 0; k < nite; k++) {
+    // sweep 1 on [2, n-3] (all that sweep 2 needs), sweep 2 on the interior + halo fill
+    k_jacobi<<<grd, blk, 0, s>>>(l.msk, l.A, x, b, l.t, c1, c2, l.ny, l.nx, 2, 0);
+    F2D_LAUNCHED();
+    k_jacobi<<<grd, blk, 0, s>>>(l.msk, l.A, l.t, b, x, c1, c2, l.ny, l.nx, NH, 1);
+    F2D_LAUNCHED();
+  }
+  return F2D_OK;
+}
+int op_residual(f2d_mg *mg, int lev, const double *x, const double *b, double *r, cudaStream_t s) {
+  Level &l = mg->L[lev];
+  dim3 blk(32, 8);
+  k_residual<<<grid2d(l.ny, l.nx, blk), blk, 0, s>>>(l.msk, l.A, x, b, r, l.ny, l.nx);
+  F2D_LAUNCHED();
+  return F2D_OK;
+}
+int op_restrict(f2d_mg *mg, int lev, const double *xf, double *xc, cudaStream_t s) {
+  Level &c = mg->L[lev + 1];
+  dim3 blk(32, 8);
+  k_restrict<<<grid2d(c.ny, c.nx, blk), blk, 0, s>>>(c.msk, xf, xc, c.ny, c.nx, mg->L[lev].nx);
+  F2D_LAUNCHED();
+  return F2D_OK;
+}
+int op_interpolate(f2d_mg *mg, int lev, const double *xc, double *xf, int add, cudaStream_t s) {
+  Level &f = mg->L[lev];
+  dim3 blk(32, 8);
+  k_interpolate<<<grid2d(f.ny, f.nx, blk), blk, 0, s>>>(f.msk, mg->L[lev + 1].msk, xc, xf, f.ny, f.nx,
+                                                        mg->L[lev + 1].nx, add);
+  F2D_LAUNCHED();
+  return F2D_OK;
+}
+
+#define TRY(call)               \
+  do {                          \
+    int rc__ = (call);          \
+    if (rc__ != F2D_OK) return rc__; \
+  } while (0)
+
+// hierarchy.py:98-127; x0/b0 stand for self.x[lev1], self.b[lev1]
+int vcycle_enqueue(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s) {
+  int last = (int)mg->L.size() - 1;
+  auto X = [&](int lev) { return lev == lev1 ? x0 : mg->L[lev].x; };
+  auto B = [&](int lev) { return lev == lev1 ? b0 : mg->L[lev].b; };
+  for (int lev = lev1; lev < last; lev++) {
+    Level &l = mg->L[lev];
+    if (lev > lev1) F2D_CUDA(cudaMemsetAsync(X(lev), 0, l.n() * sizeof(double), s));
+    TRY(op_smooth(mg, lev, X(lev), B(lev), mg->npre, s));
+    TRY(op_residual(mg, lev, X(lev), B(lev), l.r, s));
+    TRY(op_restrict(mg, lev, l.r, B(lev + 1), s));
+  }
+  if (last > lev1 || true) {
+    Level &l = mg->L[last];
+    F2D_CUDA(cudaMemsetAsync(X(last), 0, l.n() * sizeof(double), s));
+    TRY(op_smooth(mg, last, X(last), B(last), mg->ndeepest, s));
+  }
+  for (int lev = last - 1; lev >= lev1; lev--) {
+    TRY(op_interpolate(mg, lev, X(lev + 1), X(lev), 1, s));
+    TRY(op_smooth(mg, lev, X(lev), B(lev), mg->npost, s));
+  }
+  return F2D_OK;
+}
+
+// hierarchy.py:131-151
+int fcycle_enqueue(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s) {
+  int last = (int)mg->L.size() - 1;
+  auto X = [&](int lev) { return lev == lev1 ? x0 : mg->L[lev].x; };
+  auto B = [&](int lev) { return lev == lev1 ? b0 : mg->L[lev].b; };
+  for (int lev = lev1; lev < last; lev++) TRY(op_restrict(mg, lev, B(lev), B(lev + 1), s));
+  F2D_CUDA(cudaMemsetAsync(X(last), 0, mg->L[last].n() * sizeof(double), s));
+  TRY(op_smooth(mg, last, X(last), B(last), mg->ndeepest, s));
+  for (int lev = last - 1; lev >= lev1; lev--) {
+    TRY(op_interpolate(mg, lev, X(lev + 1), X(lev), 0, s));
+    for (int k = 0; k < mg->nvcyc; k++) TRY(vcycle_enqueue(mg, lev, X(lev), B(lev), s));
+  }
+  return F2D_OK;
+}
+
+// run `kind` (0 two V-cycles from level 0, 1 F-cycle, 2 single V-cycle) through a cached graph
+int run_cycle(f2d_mg *mg, int kind, int lev1, double *x0, double *b0, cudaStream_t s) {
+  auto enqueue = [&](cudaStream_t st) -> int {
+    if (kind == 0) {
+      TRY(vcycle_enqueue(mg, 0, x0, b0, st));
+      return vcycle_enqueue(mg, 0, x0, b0, st);
+    }
+    if (kind == 1) return fcycle_enqueue(mg, lev1, x0, b0, st);
+    return vcycle_enqueue(mg, lev1, x0, b0, st);
+  };
+  if (!mg->graphs) return enqueue(s);
+  auto key = std::make_tuple(kind, lev1, (const void *)x0, (const void *)b0);
+  auto it = mg->cache.find(key);
+  if (it == mg->cache.end()) {
+    long long before = g_launches;
+    F2D_CUDA(cudaStreamBeginCapture(mg->cap, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue(mg->cap);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(mg->cap, &graph);
+    long long nk = g_launches - before;
+    g_launches = before;
+    if (rc != F2D_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
+    f2d_mg::G g;
+    g.kernels = nk;
+    e = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
+    it = mg->cache.emplace(key, g).first;
+  }
+  F2D_CUDA(cudaGraphLaunch(it->second.exec, s));
+  g_launches += it->second.kernels;
+  return F2D_OK;
+}
+
+int read_scalars(f2d_mg *mg, int n, cudaStream_t s) {
+  F2D_CUDA(cudaMemcpyAsync(mg->hscal, mg->dscal, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  F2D_CUDA(cudaStreamSynchronize(s));
+  return F2D_OK;
+}
+
+void free_level(Level &l) {
+  cudaFree(l.msk); cudaFree(l.A); cudaFree(l.x); cudaFree(l.b); cudaFree(l.r); cudaFree(l.t);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" int f2d_mg_create(f2d_mg_t **out, const double *cornermask, int ny, int nx, double dx, double dy,
+                             double omega, double hydroepsilon, double Rd, f2d_stream_t stream) {
+  if (!out || !cornermask) return fail(F2D_ERR_ARG, "mg_create: null pointer");
+  int m = ny - 2 * NH, n = nx - 2 * NH;
+  if (m < 4 || n < 4) return fail(F2D_ERR_ARG, "mg_create: grid too small");
+  if ((m & (m - 1)) || (n & (n - 1))) return fail(F2D_ERR_ARG, "mg_create: nx, ny must be powers of two");
+  if (hydroepsilon * dy / dx <= 0.2)
+    return fail(F2D_ERR_ARG, "mg_create: small aspect ratio needs the tridiagonal relaxation (not built yet)");
+  cudaStream_t s = S(stream);
+  f2d_mg *mg = new f2d_mg();
+  mg->omega = omega;
+  // Gridinfo, single rank (level.py:62-93): halve until n <= 4 or m <= 4
+  {
+    int nn = n, mm = m, lev = 0;
+    while (true) {
+      if (lev > 0) { nn /= 2; mm /= 2; }
+      Level l;
+      l.ny = mm + 2 * NH;
+      l.nx = nn + 2 * NH;
+      mg->L.push_back(l);
+      lev++;
+      if (nn <= 4 || mm <= 4) break;
+      if (lev > 20) { delete mg; return fail(F2D_ERR_ARG, "mg_create: too many levels"); }
+    }
+  }
+#define MGC(call)                                                         \
+  do {                                                                    \
+    cudaError_t e__ = (call);                                             \
+    if (e__ != cudaSuccess) { f2d_mg_destroy(mg); return cuda_fail(e__, #call); } \
+  } while (0)
+  MGC(cudaStreamCreateWithFlags(&mg->cap, cudaStreamNonBlocking));
+  MGC(cudaMalloc(&mg->scratch, f2d_reduce_scratch_len() * sizeof(double)));
+  MGC(cudaMalloc(&mg->dscal, 8 * sizeof(double)));
+  MGC(cudaMallocHost(&mg->hscal, 8 * sizeof(double)));
+  for (auto &l : mg->L) {
+    size_t nb = l.n() * sizeof(double);
+    MGC(cudaMalloc(&l.msk, l.n()));
+    MGC(cudaMalloc(&l.A, 5 * nb));
+    MGC(cudaMalloc(&l.x, nb));
+    MGC(cudaMalloc(&l.b, nb));
+    MGC(cudaMalloc(&l.r, nb));
+    MGC(cudaMalloc(&l.t, nb));
+    MGC(cudaMemsetAsync(l.x, 0, nb, s));
+    MGC(cudaMemsetAsync(l.b, 0, nb, s));
+    MGC(cudaMemsetAsync(l.r, 0, nb, s));
+    MGC(cudaMemsetAsync(l.t, 0, nb, s));
+  }
+  // matrices
+  double *A9prev = nullptr, *A9 = nullptr;
+  dim3 blk(32, 8);
+  for (size_t lev = 0; lev < mg->L.size(); lev++) {
+    Level &l = mg->L[lev];
+    size_t pl = l.n();
+    MGC(cudaMalloc(&A9, 9 * pl * sizeof(double)));
+    if (lev == 0) {
+      k_mask_from_double<<<nblocks1d(pl), 256, 0, s>>>(cornermask, l.msk, pl);
+      ++g_launches;
+      // level.py:261-302
+      double bx = dy / dx * hydroepsilon, by = dx / dy, a = -2 * (bx + by);
+      double st[9] = {0., by, 0., bx, a, bx, 0., by, 0.};
+      if (dx == dy && hydroepsilon == 1.) {
+        double aa = -6. / 2, bb = 1. / 2, cc = 0.5 / 2;
+        double st9[9] = {cc, bb, cc, bb, aa, bb, cc, bb, cc};
+        for (int k = 0; k < 9; k++) st[k] = st9[k];
+      }
+      double coef = 1. / (dx * dy);
+      Stencil9 S9;
+      for (int k = 0; k < 9; k++) S9.v[k] = st[k] * coef;
+      k_finest_matrix<<<grid2d(l.ny, l.nx, blk), blk, 0, s>>>(l.msk, A9, S9, l.ny, l.nx);
+      ++g_launches;
+    } else {
+      Level &p = mg->L[lev - 1];
+      // mask coarsening (level.py:233-236): w = ones; restrict(float(msk_fine)); fill; threshold
+      k_mask_to_double<<<nblocks1d(p.n()), 256, 0, s>>>(p.msk, p.t, p.n());
+      k_fill_const<<<nblocks1d(pl), 256, 0, s>>>(l.t, 1., pl);
+      k_restrict<<<grid2d(l.ny, l.nx, blk), blk, 0, s>>>(nullptr, p.t, l.t, l.ny, l.nx, p.nx);
+      k_threshold_mask<<<nblocks1d(pl), 256, 0, s>>>(l.t, l.msk, pl);
+      k_coarsenmatrix<<<grid2d(l.ny, l.nx, blk), blk, 0, s>>>(A9prev, A9, p.msk, l.msk, l.ny, l.nx, p.ny, p.nx);
+      g_launches += 5;
+    }
+    for (int k = 0; k < 9; k++) {
+      int rc = f2d_fill_halo(A9 + k * pl, NH, l.ny, l.nx, stream);
+      if (rc != F2D_OK) { cudaFree(A9); cudaFree(A9prev); f2d_mg_destroy(mg); return rc; }
+    }
+    MGC(cudaMemcpyAsync(l.A, A9, 5 * pl * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    MGC(cudaStreamSynchronize(s));
+    cudaFree(A9prev);
+    A9prev = A9;
+    A9 = nullptr;
+  }
+  cudaFree(A9prev);
+  if (Rd > 0.) {
+    for (auto &l : mg->L) {
+      k_helmholtz<<<nblocks1d(l.n()), 256, 0, s>>>(l.A + 4 * l.n(), 1. / (Rd * Rd), l.n());
+      ++g_launches;
+    }
+  }
+  MGC(cudaStreamSynchronize(s));
+  MGC(cudaGetLastError());
+#undef MGC
+  *out = mg;
+  return F2D_OK;
+}
+
+extern "C" int f2d_mg_destroy(f2d_mg_t *mg) {
+  if (!mg) return F2D_OK;
+  for (auto &kv : mg->cache) cudaGraphExecDestroy(kv.second.exec);
+  for (auto &l : mg->L) free_level(l);
+  cudaFree(mg->scratch);
+  cudaFree(mg->dscal);
+  if (mg->hscal) cudaFreeHost(mg->hscal);
+  if (mg->cap) cudaStreamDestroy(mg->cap);
+  delete mg;
+  return F2D_OK;
+}
+
+extern "C" int f2d_mg_nlevels(const f2d_mg_t *mg) { return mg ? (int)mg->L.size() : 0; }
+extern "C" int f2d_mg_level_shape(const f2d_mg_t *mg, int lev, int *ny, int *nx) {
+  if (!mg || lev < 0 || lev >= (int)mg->L.size()) return fail(F2D_ERR_ARG, "mg_level_shape: bad level");
+  *ny = mg->L[lev].ny;
+  *nx = mg->L[lev].nx;
+  return F2D_OK;
+}
+extern "C" void *f2d_mg_level_ptr(f2d_mg_t *mg, int lev, int which) {
+  if (!mg || lev < 0 || lev >= (int)mg->L.size()) return nullptr;
+  Level &l = mg->L[lev];
+  switch (which) {
+    case 0: return l.msk;
+    case 1: return l.A;
+    case 2: return l.x;
+    case 3: return l.b;
+    case 4: return l.r;
+  }
+  return nullptr;
+}
+extern "C" int f2d_mg_level_matrix_mode(const f2d_mg_t *mg, int lev) {
+  if (!mg || lev < 0 || lev >= (int)mg->L.size()) return -1;
+  return mg->L[lev].mode;
+}
+extern "C" int f2d_mg_set_graphs(f2d_mg_t *mg, int enable) {
+  if (!mg) return fail(F2D_ERR_ARG, "mg_set_graphs: null");
+  mg->graphs = enable != 0;
+  return F2D_OK;
+}
+
+#define CHECK_LEV(mg, lev, name)                                                       \
+  if (!(mg) || (lev) < 0 || (lev) >= (int)(mg)->L.size()) return fail(F2D_ERR_ARG, name ": bad handle/level")
+
+extern "C" int f2d_mg_smooth(f2d_mg_t *mg, int lev, double *x, const double *b, int nite, f2d_stream_t s) {
+  CHECK_LEV(mg, lev, "mg_smooth");
+  if (!x || !b) return fail(F2D_ERR_ARG, "mg_smooth: null");
+  return op_smooth(mg, lev, x, b, nite, S(s));
+}
+extern "C" int f2d_mg_residual(f2d_mg_t *mg, int lev, const double *x, const double *b, double *r, f2d_stream_t s) {
+  CHECK_LEV(mg, lev, "mg_residual");
+  if (!x || !b || !r) return fail(F2D_ERR_ARG, "mg_residual: null");
+  return op_residual(mg, lev, x, b, r, S(s));
+}
+extern "C" int f2d_mg_restrict(f2d_mg_t *mg, int lev, const double *xf, double *xc, f2d_stream_t s) {
+  CHECK_LEV(mg, lev + 1, "mg_restrict");
+  if (lev < 0 || !xf || !xc) return fail(F2D_ERR_ARG, "mg_restrict: bad args");
+  return op_restrict(mg, lev, xf, xc, S(s));
+}
+extern "C" int f2d_mg_interpolate(f2d_mg_t *mg, int lev, const double *xc, double *xf, int add, f2d_stream_t s) {
+  CHECK_LEV(mg, lev + 1, "mg_interpolate");
+  if (lev < 0 || !xf || !xc) return fail(F2D_ERR_ARG, "mg_interpolate: bad args");
+  return op_interpolate(mg, lev, xc, xf, add, S(s));
+}
+extern "C" int f2d_mg_sumsq(f2d_mg_t *mg, int lev, const double *x, double *out, f2d_stream_t s) {
+  CHECK_LEV(mg, lev, "mg_sumsq");
+  Level &l = mg->L[lev];
+  return f2d_computenorm(l.msk, x, NH, l.ny, l.nx, out, mg->scratch, s);
+}
+extern "C" int f2d_mg_vcycle(f2d_mg_t *mg, int lev1, f2d_stream_t s) {
+  CHECK_LEV(mg, lev1, "mg_vcycle");
+  return run_cycle(mg, 2, lev1, mg->L[lev1].x, mg->L[lev1].b, S(s));
+}
+extern "C" int f2d_mg_fcycle(f2d_mg_t *mg, int lev1, f2d_stream_t s) {
+  CHECK_LEV(mg, lev1, "mg_fcycle");
+  return run_cycle(mg, 1, lev1, mg->L[lev1].x, mg->L[lev1].b, S(s));
+}
+// hierarchy.py:207-218.  The residual computed before each V-cycle (:215) is dead (the
+// V-cycle overwrites r[0] before reading it) and is skipped; psi/rhs are used in place
+// of the copies x[0], b[0].
+extern "C" int f2d_mg_two_vcycle(f2d_mg_t *mg, double *psi, const double *rhs, f2d_stream_t s) {
+  if (!mg || !psi || !rhs) return fail(F2D_ERR_ARG, "mg_two_vcycle: null");
+  return run_cycle(mg, 0, 0, psi, const_cast<double *>(rhs), S(s));
+}
+// hierarchy.py:154-192
+extern "C" int f2d_mg_solve(f2d_mg_t *mg, double *psi, const double *rhs, double tol, int maxite, int *nite_out,
+                            double *res_out, f2d_stream_t stream) {
+  if (!mg || !psi || !rhs) return fail(F2D_ERR_ARG, "mg_solve: null");
+  cudaStream_t s = S(stream);
+  Level &l = mg->L[0];
+  TRY(op_residual(mg, 0, psi, rhs, l.b, s));
+  TRY(f2d_computenorm(l.msk, rhs, NH, l.ny, l.nx, mg->dscal, mg->scratch, stream));
+  TRY(f2d_computenorm(l.msk, l.b, NH, l.ny, l.nx, mg->dscal + 1, mg->scratch, stream));
+  TRY(read_scalars(mg, 2, s));
+  double normb = sqrt(mg->hscal[0]);
+  int nite = 0;
+  double res = 0.;
+  if (normb > 0) {
+    double res0 = sqrt(mg->hscal[1]) / normb;
+    res = res0;
+    int ndiv = 0;
+    while (nite < maxite && res0 > tol) {
+      TRY(run_cycle(mg, 1, 0, l.x, l.b, s));
+      k_add_inplace<<<nblocks1d(l.n()), 256, 0, s>>>(psi, l.x, l.n());
+      F2D_LAUNCHED();
+      TRY(op_residual(mg, 0, psi, rhs, l.b, s));
+      TRY(f2d_computenorm(l.msk, l.b, NH, l.ny, l.nx, mg->dscal + 1, mg->scratch, stream));
+      TRY(read_scalars(mg, 2, s));
+      res = sqrt(mg->hscal[1]) / normb;
+      double conv = res0 / res;
+      res0 = res;
+      nite++;
+      if (conv < 1) ndiv++;
+      if (ndiv > 4) return fail(F2D_ERR_DIVERGE, "solver is not converging");
+    }
+  }
+  if (nite_out) *nite_out = nite;
+  if (res_out) *res_out = res;
+  return F2D_OK;
+}
+
+// operators.py:421-498
+extern "C" int f2d_invert_vorticity(f2d_mg_t *mg, const int8_t *msk, const int8_t *mskp, const double *w,
+                                    double *psi, double *u, double *v, double *work, const double *rhsp,
+                                    const double *psi_island, int full, int perio, double area, double dx,
+                                    double dy, int nh, int *nite, double *res, double *scratch,
+                                    f2d_stream_t stream) {
+  if (!mg || !msk || !mskp || !w || !psi || !u || !v || !work) return fail(F2D_ERR_ARG, "invert_vorticity: null");
+  if (nh != NH) return fail(F2D_ERR_NH, "invert_vorticity: nh must be 3");
+  Level &l = mg->L[0];
+  size_t n = l.n();
+  TRY(f2d_celltocorner(w, work, l.ny, l.nx, stream));
+  if (rhsp) TRY(f2d_add_scaled(work, -1., rhsp, n, stream));
+  if (full) {
+    TRY(f2d_mg_solve(mg, psi, work, 1e-11, 4, nite, res, stream));
+    if (perio) {
+      if (!scratch) return fail(F2D_ERR_ARG, "invert_vorticity: scratch needed");
+      TRY(f2d_domain_sum(psi, NH, l.ny, l.nx, mg->dscal + 2, scratch, stream));
+      TRY(f2d_sub_devscalar(psi, mg->dscal + 2, area, n, stream));
+    }
+  } else {
+    TRY(f2d_mg_two_vcycle(mg, psi, work, stream));
+    if (nite) *nite = 1;
+    if (res) *res = 0.;
+  }
+  TRY(f2d_mul_mask(psi, mskp, n, stream));
+  if (psi_island) TRY(f2d_add_scaled(psi, 1., psi_island, n, stream));
+  return f2d_orthogradient(msk, psi, dx, dy, nh, u, v, l.ny, l.nx, stream);
+}

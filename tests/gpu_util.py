@@ -1,0 +1,48 @@
+"""helpers for the -m gpu tests: device buffers through torch, calls through the C ABI"""
+import ctypes
+
+import numpy as np
+import torch
+
+from fluid2d_b200 import _lib
+
+
+def dev(a):
+    """numpy -> contiguous cuda tensor (float64 / int8 preserved)"""
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def host(t):
+    torch.cuda.synchronize()
+    return t.cpu().numpy()
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def scratch(L):
+    return torch.zeros(L.reduce_scratch_len(), dtype=torch.float64, device="cuda")
+
+
+def rel_l2(a, b):
+    d = np.linalg.norm((a - b).ravel())
+    n = np.linalg.norm(b.ravel())
+    return d / n if n > 0 else d
+
+
+def check(a, b, strict, tol=1e-13, what=""):
+    """bit-exact for the -fmad=false build, relative L2 <= tol for the product build"""
+    if strict:
+        np.testing.assert_array_equal(a, b, err_msg=what)
+    else:
+        e = rel_l2(a, b)
+        assert e <= tol, "%s: rel L2 %.3e > %.1e" % (what, e, tol)
+
+
+def libs():
+    return [("strict", _lib.lib(strict=True), True), ("product", _lib.lib(strict=False), False)]

@@ -15,6 +15,17 @@ extern "C" const char *f2d_last_error(void) { return f2d::g_err; }
 extern "C" long long f2d_launch_count(void) { return f2d::g_launches; }
 extern "C" void f2d_launch_count_reset(void) { f2d::g_launches = 0; }
 
+extern "C" int f2d_copy(void *dst, const void *src, size_t nbytes, f2d_stream_t s) {
+  if (!dst || !src) return fail(F2D_ERR_ARG, "copy: null");
+  F2D_CUDA(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, S(s)));
+  return F2D_OK;
+}
+extern "C" int f2d_zero(void *dst, size_t nbytes, f2d_stream_t s) {
+  if (!dst) return fail(F2D_ERR_ARG, "zero: null");
+  F2D_CUDA(cudaMemsetAsync(dst, 0, nbytes, S(s)));
+  return F2D_OK;
+}
+
 // ---------------------------------------------------------------------------
 // halo fill: one thread per halo cell, pulls from the periodic interior source
 // ---------------------------------------------------------------------------

@@ -49,6 +49,11 @@ const char *f2d_last_error(void);
 long long f2d_launch_count(void);
 void f2d_launch_count_reset(void);
 
+/* plain device-to-device copy / fill of nbytes (numpy slice assignments of the
+ * reference's Python, e.g. hierarchy.py:212-217, euler.py:115) */
+int f2d_copy(void *dst, const void *src, size_t nbytes, f2d_stream_t stream);
+int f2d_zero(void *dst, size_t nbytes, f2d_stream_t stream);
+
 /* ---- gmg/fortran_multigrid.f90:365-412  fillhalo(x,nh)  (Halo.fill, halo.py:136-141)
  * doubly periodic halo fill, corners included */
 int f2d_fill_halo(double *x, int nh, int ny, int nx, f2d_stream_t stream);

@@ -12,6 +12,20 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
+_alive = []
+
+
+def keep(a):
+    """device copy that stays allocated until release() (a bare dev(x).data_ptr() would
+    hand the caching allocator's block straight to the next temporary)"""
+    t = dev(a)
+    _alive.append(t)
+    if len(_alive) > 4096:
+        torch.cuda.synchronize()
+        del _alive[:2048]
+    return t
+
+
 def ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 

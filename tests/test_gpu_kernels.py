@@ -92,7 +92,7 @@ def test_advection(L, shape, mkind, order, method):
             dm = None if mkind == "none" else g.dev(msk)
             fn = lib.adv_upwind if upw else lib.adv_centered
             cst_c = (ctypes.c_double * 5)(*cst)
-            fn(g.ptr(dm), g.ptr(g.dev(q)), g.ptr(dq), g.ptr(g.dev(u)), g.ptr(g.dev(v)),
+            fn(g.ptr(dm), g.ptr(g.keep(q)), g.ptr(dq), g.ptr(g.keep(u)), g.ptr(g.keep(v)),
                g.ptr(dfx), g.ptr(dfy), cst_c, 3, method, order, ny, nx, fill, g.stream())
             g.check(g.host(dq), refh, strict, what="dq")
             if flx:
@@ -113,7 +113,7 @@ def test_advection_umax_zero_and_bad_nh(L):
     K.fortran_advection.adv_upwind(msk, q, ref, u, v, cst, 3, 1, 5)
     dq = g.dev(np.zeros((ny, nx)))
     cst_c = (ctypes.c_double * 5)(*cst)
-    args = [g.ptr(g.dev(msk)), g.ptr(g.dev(q)), g.ptr(dq), g.ptr(g.dev(u)), g.ptr(g.dev(v)), None, None, cst_c]
+    args = [g.ptr(g.keep(msk)), g.ptr(g.keep(q)), g.ptr(dq), g.ptr(g.keep(u)), g.ptr(g.keep(v)), None, None, cst_c]
     lib.adv_upwind(*args, 3, 1, 5, ny, nx, 0, g.stream())
     out = g.host(dq)
     assert np.isfinite(out).all()
@@ -139,17 +139,17 @@ def test_stencil_operators(L, shape):
         b = rng.standard_normal(shape)
         # celltocorner / cornertocell
         ref = b.copy(); fo.celltocorner(a, ref)
-        d = g.dev(b); lib.celltocorner(g.ptr(g.dev(a)), g.ptr(d), ny, nx, s)
+        d = g.dev(b); lib.celltocorner(g.ptr(g.keep(a)), g.ptr(d), ny, nx, s)
         g.check(g.host(d), ref, strict, what="celltocorner")
         ref = b.copy(); fo.cornertocell(a, ref)
-        d = g.dev(b); lib.cornertocell(g.ptr(g.dev(a)), g.ptr(d), ny, nx, s)
+        d = g.dev(b); lib.cornertocell(g.ptr(g.keep(a)), g.ptr(d), ny, nx, s)
         g.check(g.host(d), ref, strict, what="cornertocell")
         # orthogradient
         ur, vr = a.copy(), b.copy()
         psi = rng.standard_normal(shape)
         fo.computeorthogradient(msk, psi, 0.01, 0.02, 3, ur, vr)
         du, dv = g.dev(a), g.dev(b)
-        lib.orthogradient(g.ptr(g.dev(msk)), g.ptr(g.dev(psi)), 0.01, 0.02, 3, g.ptr(du), g.ptr(dv), ny, nx, s)
+        lib.orthogradient(g.ptr(g.keep(msk)), g.ptr(g.keep(psi)), 0.01, 0.02, 3, g.ptr(du), g.ptr(dv), ny, nx, s)
         g.check(g.host(du), ur, strict, what="u")
         g.check(g.host(dv), vr, strict, what="v")
         # diffusion
@@ -158,7 +158,7 @@ def test_stencil_operators(L, shape):
             if fill:
                 K.fortran_multigrid.fillhalo(ref, 3)
             d = g.dev(b)
-            lib.add_diffusion(g.ptr(g.dev(msk)), g.ptr(g.dev(a)), 0.01, 3, 3e-4, g.ptr(d), ny, nx, fill, s)
+            lib.add_diffusion(g.ptr(g.keep(msk)), g.ptr(g.keep(a)), 0.01, 3, 3e-4, g.ptr(d), ny, nx, fill, s)
             g.check(g.host(d), ref, strict, what="diffusion")
         # torque (with the y *= msk of operators.py:311)
         for premask in (0, 1):
@@ -168,12 +168,12 @@ def test_stencil_operators(L, shape):
             fo.add_torque(msk, a, 0.01, 3, 9.81, ref)
             K.fortran_multigrid.fillhalo(ref, 3)
             d = g.dev(b)
-            lib.add_torque(g.ptr(g.dev(msk)), g.ptr(g.dev(a)), 0.01, 3, 9.81, g.ptr(d), ny, nx, premask, 1, s)
+            lib.add_torque(g.ptr(g.keep(msk)), g.ptr(g.keep(a)), 0.01, 3, 9.81, g.ptr(d), ny, nx, premask, 1, s)
             g.check(g.host(d), ref, strict, what="torque")
         # no-slip source (scatter in the Fortran, gather here)
         ref = b.copy(); fo.computenoslipsourceterm(msk, psi, ref, 0.01, 0.02, 3)
         d = g.dev(b)
-        lib.noslip_source(g.ptr(g.dev(msk)), g.ptr(g.dev(psi)), g.ptr(d), 0.01, 0.02, 3, ny, nx, s)
+        lib.noslip_source(g.ptr(g.keep(msk)), g.ptr(g.keep(psi)), g.ptr(d), 0.01, 0.02, 3, ny, nx, s)
         g.check(g.host(d), ref, strict, what="noslip")
 
 
@@ -224,7 +224,7 @@ def test_reductions(L, shape):
         # fused Euler diagnostics
         xr, yr = np.meshgrid(np.arange(nx) * 0.01, np.arange(ny) * 0.02)
         lib.diag_euler(g.ptr(dm), g.ptr(du), g.ptr(dv), g.ptr(dx_), g.ptr(dpsi), g.ptr(dsrc),
-                       g.ptr(g.dev(xr)), g.ptr(g.dev(yr)), 3, ny, nx, g.ptr(out), g.ptr(sc), s)
+                       g.ptr(g.keep(xr)), g.ptr(g.keep(yr)), 3, ny, nx, g.ptr(out), g.ptr(sc), s)
         o = g.host(out)
         ke, maxu = fd.computekemaxu(msk, u, v, 3)
         z, z2 = fd.computesumandnorm(msk, x, 3)
@@ -246,7 +246,7 @@ def test_timescheme_combinations_bitexact(L):
 
     def run(fn, first, *rest):
         t = g.dev(first)
-        fn(g.ptr(t), *[g.ptr(g.dev(r)) if isinstance(r, np.ndarray) else r for r in rest], n, s)
+        fn(g.ptr(t), *[g.ptr(g.keep(r)) if isinstance(r, np.ndarray) else r for r in rest], n, s)
         return g.host(t)
 
     np.testing.assert_array_equal(run(lib.ts_axpy, x, dt, a), x + dt * a)

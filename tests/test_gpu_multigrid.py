@@ -57,7 +57,7 @@ def make(lib, kind, ny, nx, Rd=0.):
     dx, dy = 1. / nx, 1. / nx
     ref = om.MG(cm, nx, ny, dx, dy, Rd=(Rd if Rd > 0 else None))
     h = ctypes.c_void_p()
-    lib.mg_create(ctypes.byref(h), g.ptr(g.dev(cm)), ny + 6, nx + 6, dx, dy, 8. / 9., 1., Rd, g.stream())
+    lib.mg_create(ctypes.byref(h), g.ptr(g.keep(cm)), ny + 6, nx + 6, dx, dy, 8. / 9., 1., Rd, g.stream())
     return ref, h, rng
 
 
@@ -69,9 +69,7 @@ def level_array(lib, h, lev, which, shape, dtype=np.float64):
     p = lib.mg_level_ptr(h, lev, which)
     buf = torch.empty(n, dtype=torch.int8 if dtype == np.int8 else torch.float64, device="cuda")
     nbytes = n * (1 if dtype == np.int8 else 8)
-    torch.cuda.synchronize()
-    rc = torch.cuda.cudart().cudaMemcpy(buf.data_ptr(), p, nbytes, 3)
-    assert int(rc) == 0
+    lib.copy(g.ptr(buf), p, nbytes, g.stream())
     a = buf.cpu().numpy()
     return a.reshape((5, ny, nx)) if which == 1 else a.reshape((ny, nx))
 
@@ -114,25 +112,25 @@ def test_level_operators(L, kind, ny, nx):
             K.fortran_multigrid.fillhalo(b, 3)
             for nite in (1, 3):
                 xr = x.copy(); ref.smooth(lev, xr, b, nite)
-                d = g.dev(x); lib.mg_smooth(h, lev, g.ptr(d), g.ptr(g.dev(b)), nite, s)
+                d = g.dev(x); lib.mg_smooth(h, lev, g.ptr(d), g.ptr(g.keep(b)), nite, s)
                 g.check(g.host(d), xr, strict, what="smooth lev %d" % lev)
             rr = np.zeros(shape); ref.residual(lev, x, b, rr)
-            d = g.dev(np.ones(shape)); lib.mg_residual(h, lev, g.ptr(g.dev(x)), g.ptr(g.dev(b)), g.ptr(d), s)
+            d = g.dev(np.ones(shape)); lib.mg_residual(h, lev, g.ptr(g.keep(x)), g.ptr(g.keep(b)), g.ptr(d), s)
             g.check(g.host(d), rr, strict, what="residual lev %d" % lev)
             import torch
             out = torch.zeros(1, dtype=torch.float64, device="cuda")
-            lib.mg_sumsq(h, lev, g.ptr(g.dev(x)), g.ptr(out), s)
+            lib.mg_sumsq(h, lev, g.ptr(g.keep(x)), g.ptr(out), s)
             np.testing.assert_allclose(np.sqrt(g.host(out)[0]), ref.norm(lev, x), rtol=1e-13)
             if lev < ref.nlevs - 1:
                 cshape = ref.msk[lev + 1].shape
                 xc = np.ones(cshape); ref.down(lev, x, xc)
-                d = g.dev(np.ones(cshape)); lib.mg_restrict(h, lev, g.ptr(g.dev(x)), g.ptr(d), s)
+                d = g.dev(np.ones(cshape)); lib.mg_restrict(h, lev, g.ptr(g.keep(x)), g.ptr(d), s)
                 g.check(g.host(d), xc, strict, what="restrict lev %d" % lev)
                 c = rng.standard_normal(cshape)
                 xf = np.ones(shape); ref.up(lev, c, xf)
-                d = g.dev(np.ones(shape)); lib.mg_interpolate(h, lev, g.ptr(g.dev(c)), g.ptr(d), 0, s)
+                d = g.dev(np.ones(shape)); lib.mg_interpolate(h, lev, g.ptr(g.keep(c)), g.ptr(d), 0, s)
                 g.check(g.host(d), xf, strict, what="interpolate lev %d" % lev)
-                d = g.dev(x); lib.mg_interpolate(h, lev, g.ptr(g.dev(c)), g.ptr(d), 1, s)
+                d = g.dev(x); lib.mg_interpolate(h, lev, g.ptr(g.keep(c)), g.ptr(d), 1, s)
                 g.check(g.host(d), x + xf, strict, what="interpolate+add lev %d" % lev)
     finally:
         lib.mg_destroy(h)
@@ -174,7 +172,7 @@ def test_cycles_and_solve(L, kind, ny, nx, graphs):
         g.check(g.host(d), pr, strict, tol=1e-11, what="solve")
         # zero right-hand side: returns (0, 0.) without touching psi (hierarchy.py:161-164)
         d = g.dev(psi0)
-        lib.mg_solve(h, g.ptr(d), g.ptr(g.dev(np.zeros(shape))), 1e-11, 4, ctypes.byref(nite), ctypes.byref(res), s)
+        lib.mg_solve(h, g.ptr(d), g.ptr(g.keep(np.zeros(shape))), 1e-11, 4, ctypes.byref(nite), ctypes.byref(res), s)
         assert nite.value == 0 and res.value == 0.
         np.testing.assert_array_equal(g.host(d), psi0)
     finally:
@@ -192,7 +190,7 @@ def test_convergence_factor(L):
         rhs = np.sin(xx * 0.1) * np.cos(yy * 0.07) * ref.msk[0]
         d = g.dev(np.zeros(shape))
         nite, res = ctypes.c_int(), ctypes.c_double()
-        lib.mg_solve(h, g.ptr(d), g.ptr(g.dev(rhs)), 1e-11, 4, ctypes.byref(nite), ctypes.byref(res), g.stream())
+        lib.mg_solve(h, g.ptr(d), g.ptr(g.keep(rhs)), 1e-11, 4, ctypes.byref(nite), ctypes.byref(res), g.stream())
         assert res.value < 1e-6
     finally:
         lib.mg_destroy(h)

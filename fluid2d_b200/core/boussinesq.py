@@ -1,0 +1,119 @@
+"""Boussinesq: vorticity + buoyancy, on the device (reference: core/boussinesq.py).
+Same interface: var, ope, tscheme, diags, step, dynamics, add_noslip,
+set_psi_from_vorticity, diagnostics, forc / extrastep hooks."""
+import numpy as np
+from importlib import import_module
+
+from operators import Operators
+from variables import Var
+from timescheme import Timescheme
+from runtime import rt
+import torch
+
+
+class Boussinesq(object):
+    def __init__(self, param, grid):
+        self.list_param = ['forcing', 'noslip', 'timestepping', 'diffusion', 'Kdiff', 'myrank',
+                           'forcing_module', 'gravity', 'isisland', 'customized', 'custom_module',
+                           'additional_tracer']
+        param.copy(self, self.list_param)
+        self.list_param = ['xr', 'yr', 'nh', 'Lx', 'msk', 'area', 'mpitools']
+        grid.copy(self, self.list_param)
+        param.varname_list = ['vorticity', 'psi', 'u', 'v', 'buoyancy', 'banom']
+        param.tracer_list = ['vorticity', 'buoyancy']
+        param.whosetspsi = ('vorticity')
+        if hasattr(self, 'additional_tracer'):
+            for trac in self.additional_tracer:
+                param.varname_list.append(trac)
+                param.tracer_list.append(trac)
+        param.sizevar = [grid.nyl, grid.nxl]
+        self.var = Var(param)
+        r = rt()
+        self.rt = r
+        self.ncell = grid.nyl*grid.nxl
+        # reference buoyancy: the buoyancy field at construction time (zeros)
+        self.bref = self.var.get('buoyancy').copy()
+        self.d_bref = r.to_device(self.bref, dtype=np.float64)
+        self.source = torch.zeros((grid.nyl, grid.nxl), dtype=torch.float64, device=r.device)
+        self.d_yr = r.to_device(self.yr, dtype=np.float64)
+        self.ope = Operators(param, grid)
+        self.tscheme = Timescheme(param, self.var.dstate)
+        self.tscheme.set(self.dynamics, self.timestepping)
+        if self.forcing:
+            if self.forcing_module == 'embedded':
+                self.msg_forcing = ('To make Fluid2d aware of your embedded forcing\n'
+                                    'you need to add in the user script \n'
+                                    'model.forc = Forcing(param, grid)\n'
+                                    'right below the line: model = f2d.model')
+            else:
+                try:
+                    f = import_module(self.forcing_module)
+                except ImportError:
+                    raise ImportError('module %s for forcing cannot be found; make sure file **%s.py** exists'
+                                      % (self.forcing_module, self.forcing_module))
+                self.forc = f.Forcing(param, grid)
+        self.diags = {}
+        if self.customized:
+            f = import_module(self.custom_module)
+            self.extrastep = f.Step(param, grid)
+
+    def step(self, t, dt):
+        r, lib = self.rt, self.rt.lib
+        state = self.var.dstate
+        self.tscheme.forward(state, t, dt)
+        if self.noslip:
+            self.add_noslip(state)
+        if self.customized:
+            self.extrastep.do(self.var, t, dt)
+        ib, ia = self.var.index('buoyancy'), self.var.index('banom')
+        lib.set_sum(state.wptr(ia), state.rptr(ib), -1., r.ptr(self.d_bref), self.ncell, r.stream)
+
+    def dynamics(self, x, t, dxdt):
+        self.ope.rhs_adv(x, t, dxdt)
+        # db/dx is a source of vorticity
+        self.ope.rhs_torque(x, t, dxdt)
+        if self.tscheme.kstage == self.tscheme.kforcing:
+            coef = self.tscheme.dtcoef
+            if self.forcing:
+                assert hasattr(self, 'forc'), self.msg_forcing
+                self.forc.add_forcing(x, t, dxdt, coef=coef)
+            if self.diffusion:
+                self.ope.rhs_diffusion(x, t, dxdt, coef=coef)
+        self.ope.invert_vorticity(dxdt, flag='fast')
+
+    def add_noslip(self, x):
+        self.ope.rhs_noslip(x, self.source)
+        self.ope.invert_vorticity(x, flag='fast', island=self.isisland)
+
+    def set_psi_from_vorticity(self):
+        self.ope.invert_vorticity(self.var.dstate, island=self.isisland)
+
+    def diagnostics(self, var, t):
+        r, lib = self.rt, self.rt.lib
+        s = var.dstate
+        ix = var.index
+        nh, ny, nx = self.nh, s.ny, s.nx
+        msk = r.ptr(self.ope.d_msk)
+        sc = r.ptr(r.scratch)
+
+        def slot(k):
+            import ctypes
+            return ctypes.c_void_p(r.out.data_ptr()+8*k)
+
+        lib.computekemaxu(msk, s.rptr(ix('u')), s.rptr(ix('v')), nh, ny, nx, slot(0), sc, r.stream)
+        lib.computesumandnorm(msk, s.rptr(ix('vorticity')), nh, ny, nx, slot(2), sc, r.stream)
+        lib.computesumandnorm(msk, s.rptr(ix('buoyancy')), nh, ny, nx, slot(4), sc, r.stream)
+        # potential energy: - g * sum(b * y)   (buoyancy is minus density)
+        lib.computedotprod(msk, s.rptr(ix('buoyancy')), r.ptr(self.d_yr), nh, ny, nx, slot(6), sc, r.stream)
+        ke, maxu, z, z2, b, b2, by = r.read_out(7)
+        pe = - self.gravity * by
+        cst = self.mpitools.local_to_global([(maxu, 'max'), (ke, 'sum'), (z, 'sum'), (z2, 'sum'),
+                                             (pe, 'sum'), (b, 'sum'), (b2, 'sum')])
+        self.diags['maxspeed'] = cst[0]
+        self.diags['ke'] = cst[1] / self.area
+        self.diags['pe'] = cst[4] / self.area
+        self.diags['energy'] = (cst[1]+cst[4]) / self.area
+        self.diags['vorticity'] = cst[2] / self.area
+        self.diags['enstrophy'] = 0.5*cst[3] / self.area
+        self.diags['buoyancy'] = cst[5] / self.area
+        self.diags['brms'] = np.sqrt(cst[6] / self.area-(cst[5]/self.area)**2)

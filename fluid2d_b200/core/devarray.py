@@ -1,0 +1,207 @@
+"""Device-resident model state with a lazily synchronised host mirror.
+
+The reference keeps the model state in one numpy array [nvar, ny, nx] that user
+scripts mutate in place through the views returned by Var.get() (variables.py:27-30,
+docs/howto.rst).  Here the authoritative copy lives in HBM; the host sees it through a
+pinned mirror:
+
+  * DeviceState.host_view(k) / state[k] hand out TrackedArray views of the mirror.
+    A TrackedArray tells its DeviceState when it is written (slice assignment, in-place
+    operators, ufuncs with out=) so that the field is uploaded before the next kernel
+    reads it, and refreshes itself from the device before it is read through numpy
+    indexing or ufuncs when the device copy is newer.
+  * kernels get raw device pointers through rptr()/wptr(); wptr() marks the host
+    mirror of that field stale.
+
+Nothing here computes: it only moves bytes (cudaMemcpy through torch).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+
+class TrackedArray(np.ndarray):
+    """numpy view of the pinned mirror that reports writes to / pulls reads from HBM"""
+
+    _own = None   # (DeviceState, field index or None for all)
+
+    def __array_finalize__(self, obj):
+        if obj is not None:
+            self._own = getattr(obj, '_own', None)
+
+    # -- coherence hooks ---------------------------------------------------
+    def _before_read(self):
+        if self._own is not None:
+            self._own[0]._refresh_host(self._own[1])
+
+    def _after_write(self):
+        if self._own is not None:
+            self._own[0]._host_written(self._own[1])
+
+    def __getitem__(self, key):
+        self._before_read()
+        return np.ndarray.__getitem__(self, key)
+
+    def __setitem__(self, key, value):
+        self._before_read()          # partial writes must land on fresh data
+        if isinstance(value, TrackedArray):
+            value._before_read()
+        np.ndarray.__setitem__(self, key, value)
+        self._after_write()
+
+    def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kwargs):
+        plain = []
+        for x in inputs:
+            if isinstance(x, TrackedArray):
+                x._before_read()
+                plain.append(x.view(np.ndarray))
+            else:
+                plain.append(x)
+        written = []
+        if out is not None:
+            pout = []
+            for o in out:
+                if isinstance(o, TrackedArray):
+                    o._before_read()
+                    written.append(o)
+                    pout.append(o.view(np.ndarray))
+                else:
+                    pout.append(o)
+            kwargs['out'] = tuple(pout)
+        res = getattr(ufunc, method)(*plain, **kwargs)
+        for o in written:
+            o._after_write()
+        if out is not None:
+            return out[0] if len(out) == 1 else out
+        return res
+
+    def fill(self, value):
+        np.ndarray.fill(self, value)
+        self._after_write()
+
+    def copy(self, order='C'):
+        self._before_read()
+        return np.array(self.view(np.ndarray), order=order, copy=True)
+
+
+class DeviceState(object):
+    """[nvar, ny, nx] float64 in HBM (torch owns the allocation) + pinned host mirror"""
+
+    def __init__(self, nvar, ny, nx, device=None):
+        self.nvar, self.ny, self.nx = nvar, ny, nx
+        self.device = device if device is not None else torch.device('cuda', torch.cuda.current_device())
+        self.dev = torch.zeros((nvar, ny, nx), dtype=torch.float64, device=self.device)
+        self._host_t = None        # pinned torch tensor, allocated on first host access
+        self._host = None          # numpy view of it
+        self.host_fresh = [True]*nvar
+        self.dev_fresh = [True]*nvar
+        self.fieldbytes = ny*nx*8
+        self.shape = (nvar, ny, nx)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    # -- host side -----------------------------------------------------------
+    def _ensure_host(self):
+        if self._host is None:
+            self._host_t = torch.zeros((self.nvar, self.ny, self.nx), dtype=torch.float64)
+            if self.device.type == 'cuda':
+                self._host_t = self._host_t.pin_memory()
+            self._host = self._host_t.numpy()
+            # the mirror starts as zeros; anything already on the device is newer
+            self.host_fresh = [False]*self.nvar
+
+    def _fields(self, k):
+        return range(self.nvar) if k is None else (k,)
+
+    def _refresh_host(self, k=None):
+        self._ensure_host()
+        todo = [f for f in self._fields(k) if not self.host_fresh[f]]
+        if not todo:
+            return
+        for f in todo:
+            if not self.dev_fresh[f]:
+                raise RuntimeError('DeviceState: field %d stale on both sides' % f)
+            self._host_t[f].copy_(self.dev[f], non_blocking=True)
+            self.host_fresh[f] = True
+            self.d2h_bytes += self.fieldbytes
+        if self.device.type == 'cuda':
+            torch.cuda.current_stream().synchronize()
+
+    def _host_written(self, k=None):
+        for f in self._fields(k):
+            self.host_fresh[f] = True
+            self.dev_fresh[f] = False
+
+    def host_view(self, k=None):
+        """TrackedArray on field k (or on the whole state), fresh from the device"""
+        self._refresh_host(k)
+        base = self._host if k is None else self._host[k]
+        v = base.view(TrackedArray)
+        v._own = (self, k)
+        return v
+
+    def __getitem__(self, k):
+        if isinstance(k, (int, np.integer)):
+            return self.host_view(int(k))
+        return self.host_view(None)[k]
+
+    def __setitem__(self, k, value):
+        if isinstance(k, (int, np.integer)):
+            v = self.host_view(int(k))
+            if not (isinstance(value, np.ndarray) and np.shares_memory(value, v)):
+                np.ndarray.__setitem__(v, slice(None), np.asarray(value))
+            self._host_written(int(k))
+        else:
+            v = self.host_view(None)
+            v[k] = value
+
+    # -- device side ---------------------------------------------------------
+    def to_device(self, k=None):
+        for f in self._fields(k):
+            if not self.dev_fresh[f]:
+                self.dev[f].copy_(self._host_t[f], non_blocking=True)
+                self.dev_fresh[f] = True
+                self.h2d_bytes += self.fieldbytes
+
+    def rptr(self, k):
+        """device address of field k for reading"""
+        self.to_device(k)
+        return ctypes.c_void_p(self.dev[k].data_ptr())
+
+    def wptr(self, k):
+        """device address of field k for (partial) writing: mirror becomes stale"""
+        self.to_device(k)
+        self.host_fresh[k] = False
+        return ctypes.c_void_p(self.dev[k].data_ptr())
+
+    def all_ptr(self, write=False):
+        """device address of the whole [nvar,ny,nx] block"""
+        self.to_device(None)
+        if write:
+            self.host_fresh = [False]*self.nvar
+        return ctypes.c_void_p(self.dev.data_ptr())
+
+    @property
+    def size(self):
+        return self.nvar*self.ny*self.nx
+
+    def zero_(self):
+        self.dev.zero_()
+        self.dev_fresh = [True]*self.nvar
+        self.host_fresh = [False]*self.nvar if self._host is not None else [True]*self.nvar
+        if self._host is None:
+            self.host_fresh = [True]*self.nvar   # mirror not yet materialised (zeros anyway)
+
+    def upload_all_from(self, array):
+        """replace the whole state by a host array (restart, tests)"""
+        self._ensure_host()
+        self._host[...] = array
+        self.host_fresh = [True]*self.nvar
+        self.dev_fresh = [False]*self.nvar
+        self.to_device(None)
+
+    def numpy(self):
+        """fresh plain-numpy copy of the whole state"""
+        self._refresh_host(None)
+        return np.array(self._host, copy=True)

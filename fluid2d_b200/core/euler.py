@@ -1,0 +1,160 @@
+"""Euler: 2-D incompressible Euler / Navier-Stokes in vorticity form, on the device.
+
+Same interface as the reference's core/euler.py -- var, ope, tscheme, timers, diags,
+step(t, dt), dynamics(x, t, dxdt), add_noslip(x), set_psi_from_vorticity(),
+diagnostics(var, t), forc / extrastep hooks, sponge layer, dye / age tracers.  The
+state and the tendency buffers are DeviceState objects; user hooks see them through
+host views (devarray.py).
+"""
+import numpy as np
+from importlib import import_module
+
+from operators import Operators
+from variables import Var
+from timescheme import Timescheme
+from timers import Timers
+from runtime import rt
+
+
+class Euler(object):
+    def __init__(self, param, grid):
+        self.list_param = ['forcing', 'noslip', 'timestepping', 'diffusion', 'Kdiff', 'forcing_module',
+                           'additional_tracer', 'enforce_momentum', 'var_to_save', 'customized',
+                           'custom_module', 'spongelayer']
+        param.copy(self, self.list_param)
+        self.list_param = ['yr', 'nh', 'msk', 'area', 'mpitools', 'dx', 'xr', 'yr', 'r2', 'x0', 'y0', 'x2',
+                           'y2', 'isisland', 'Lx', 'ny']
+        grid.copy(self, self.list_param)
+
+        param.varname_list = ['vorticity', 'psi', 'u', 'v', 'source']
+        param.tracer_list = ['vorticity']
+        param.whosetspsi = ('vorticity')
+        if 'tauw' in self.var_to_save:
+            param.varname_list.append('tauw')
+        if 'wshear' in self.var_to_save:
+            param.varname_list.append('wshear')
+        if hasattr(self, 'additional_tracer'):
+            for trac in self.additional_tracer:
+                param.varname_list.append(trac)
+                param.tracer_list.append(trac)
+        param.sizevar = [grid.nyl, grid.nxl]
+        self.var = Var(param)
+        self.timers = Timers(param)
+        self.ope = Operators(param, grid)
+        self.tscheme = Timescheme(param, self.var.dstate)
+        self.tscheme.set(self.dynamics, self.timestepping)
+        r = rt()
+        self.rt = r
+        self.d_xr = r.to_device(self.xr, dtype=np.float64)
+        self.d_yr = r.to_device(self.yr, dtype=np.float64)
+        self.ncell = grid.nyl*grid.nxl
+
+        if self.forcing:
+            if self.forcing_module == 'embedded':
+                print('Warning: check that you have indeed added the forcing to the model')
+                print('Right below the line    : model = f2d.model')
+                print('you should have the line: model.forc = Forcing(param, grid)')
+            else:
+                try:
+                    f = import_module(self.forcing_module)
+                except ImportError:
+                    raise ImportError('module %s for forcing cannot be found; make sure file **%s.py** exists'
+                                      % (self.forcing_module, self.forcing_module))
+                self.forc = f.Forcing(param, grid)
+        if self.spongelayer:
+            # [0 = full sponge, 1 = no sponge]
+            self.spongemsk = (1-(1+np.tanh((self.xr - self.Lx)/0.1))*0.5)
+            self.d_spongemsk = r.to_device(self.spongemsk, dtype=np.float64)
+        self.diags = {}
+        if self.customized:
+            try:
+                f = import_module(self.custom_module)
+            except ImportError:
+                raise ImportError('module %s cannot be found; make sure file **%s.py** exists'
+                                  % (self.custom_module, self.custom_module))
+            self.extrastep = f.Step(param, grid)
+
+    def step(self, t, dt):
+        r, lib = self.rt, self.rt.lib
+        state = self.var.dstate
+        # 1/ dynamics
+        self.tscheme.forward(state, t, dt)
+        # 2/ no-slip source
+        if self.noslip:
+            self.add_noslip(state)
+            isrc = self.var.index('source')
+            lib.div_scalar(state.wptr(isrc), dt, self.ncell, r.stream)
+            if 'tauw' in self.var_to_save:
+                itau = self.var.index('tauw')
+                lib.copy(state.wptr(itau), state.rptr(isrc), self.ncell*8, r.stream)
+                lib.scale(state.wptr(itau), self.dx, self.ncell, r.stream)
+                lib.scale(state.wptr(itau), self.dx, self.ncell, r.stream)
+        if self.customized:
+            self.extrastep.do(self.var, t, dt)
+        # 3/ dye and age tracers (host views: a few points per step)
+        if 'dye' in self.var.varname_list:
+            i, jp, jm = 1, self.ny//2+3, self.ny//2-3
+            dye = self.var.get('dye')
+            dye[jp+self.nh, i] = 1
+            dye[jm+self.nh, i] = -1
+        if 'age' in self.var.varname_list:
+            age = self.var.get('age')
+            age += dt*self.msk
+            age[:, self.nh] = 0.
+        # 4/ sponge layer
+        if self.spongelayer:
+            lib.mul_field(state.wptr(self.var.index('vorticity')), r.ptr(self.d_spongemsk), self.ncell, r.stream)
+            for name in ('dye', 'age'):
+                if name in self.var.varname_list:
+                    lib.mul_field(state.wptr(self.var.index(name)), r.ptr(self.d_spongemsk), self.ncell, r.stream)
+        self.set_psi_from_vorticity()
+
+    def dynamics(self, x, t, dxdt):
+        """tendencies of the tracers + the streamfunction / velocity they imply"""
+        self.timers.tic('rhs_adv')
+        self.ope.rhs_adv(x, t, dxdt)
+        self.timers.toc('rhs_adv')
+        if self.tscheme.kstage == self.tscheme.kforcing:
+            if self.forcing:
+                self.forc.add_forcing(x, t, dxdt)
+            if self.diffusion:
+                self.ope.rhs_diffusion(x, t, dxdt)
+            if self.diffusion or self.forcing:
+                self.ope.invert_vorticity(dxdt, flag='fast')
+        else:
+            self.timers.tic('invert')
+            self.ope.invert_vorticity(dxdt, flag='fast')
+            self.timers.toc('invert')
+
+    def add_noslip(self, x):
+        self.timers.tic('noslip')
+        self.ope.rhs_noslip(x, (self.var.dstate, self.var.index('source')))
+        self.timers.toc('noslip')
+        self.timers.tic('invert')
+        self.ope.invert_vorticity(x, flag='fast', island=self.isisland)
+        self.timers.toc('invert')
+
+    def set_psi_from_vorticity(self):
+        self.ope.invert_vorticity(self.var.dstate, island=self.isisland)
+
+    def diagnostics(self, var, t):
+        """integral diagnostics; 'maxspeed' feeds the cfl criterion (one fused pass)"""
+        self.timers.tic('diag')
+        r, lib = self.rt, self.rt.lib
+        s = var.dstate
+        ix = var.index
+        lib.diag_euler(r.ptr(self.ope.d_msk), s.rptr(ix('u')), s.rptr(ix('v')), s.rptr(ix('vorticity')),
+                       s.rptr(ix('psi')), s.rptr(ix('source')), r.ptr(self.d_xr), r.ptr(self.d_yr),
+                       self.nh, s.ny, s.nx, r.ptr(r.out), r.ptr(r.scratch), r.stream)
+        maxu, ke, z, z2, px, py, angmom, sce = r.read_out(8)
+        cst = self.mpitools.local_to_global([(maxu, 'max'), (ke, 'sum'), (z, 'sum'), (z2, 'sum'),
+                                             (px, 'sum'), (py, 'sum'), (angmom, 'sum'), (sce, 'sum')])
+        self.diags['maxspeed'] = cst[0]
+        self.diags['ke'] = cst[1] / self.area
+        self.diags['vorticity'] = cst[2] / self.area
+        self.diags['enstrophy'] = 0.5*cst[3] / self.area
+        self.diags['px'] = cst[4] / self.area
+        self.diags['py'] = cst[5] / self.area
+        self.diags['angmom'] = cst[6] / self.area
+        self.diags['source'] = cst[7] / self.area
+        self.timers.toc('diag')

@@ -1,0 +1,257 @@
+"""Fluid2d: builds the model named by param.modelname and runs the time loop.
+
+Same interface as the reference's core/fluid2d.py -- Fluid2d(param, grid), .model,
+.loop(), .set_dt(kt), .enforce_zero_momentum(), .t, .kt, .dt, the stdout tee into
+expdir/output.txt, the copy of the launch script, the blow-up stop, the end-of-run
+performance summary (with the reference's "rescaled time") -- on top of the device
+models.  During the loop the state never leaves HBM: per iteration the host reads back
+eight diagnostics scalars (maxspeed sets the next dt) and the residual norms of the
+end-of-step solve; fields cross only when Output stores a snapshot or a user hook asks.
+"""
+from __future__ import print_function
+import os
+import signal
+import sys
+from importlib import import_module
+from subprocess import call
+from time import time as clock
+
+import numpy as np
+
+from output import Output
+
+
+class Fluid2d(object):
+    def __init__(self, param, grid):
+        param.checkall()
+        launchscript = sys.argv[0]
+        param.datadir = param.datadir.replace('~', os.getenv("HOME", '.'))
+        param.expdir = '%s/%s' % (param.datadir, param.expname)
+        if param.myrank == 0:
+            if not os.path.isdir(param.expdir):
+                os.makedirs(param.expdir)
+            savedscript = '%s/%s.py' % (param.expdir, param.expname)
+            outfile = '%s/output.txt' % param.expdir
+            if os.path.exists(outfile):
+                print('Warning: this experiment has already been ran, output.txt already exists')
+                print('dummy.txt will be used instead')
+                outfile = '%s/dummy.txt' % param.expdir
+            if getattr(param, 'tee_stdout', True):
+                sys.stdout = Logger(outfile)
+            if os.path.exists(savedscript):
+                print('Warning: the python script already exists in %s' % param.expdir)
+            elif os.path.isfile(launchscript):
+                self.savedscript = savedscript
+                call(['cp', launchscript, savedscript])
+
+        self.list_param = ['modelname', 'tend', 'adaptable_dt', 'dt', 'cfl', 'dtmax', 'myrank', 'nprint',
+                           'exacthistime', 'rescaledtime', 'noslip', 'geometry', 'diag_fluxes', 'print_param',
+                           'enforce_momentum', 'forcing', 'decay', 'plotting_module', 'freq_save',
+                           'freq_plot', 'plot_interactive', 'nbproc', 'isisland', 'npx', 'npy', 'nx', 'ny']
+        param.copy(self, self.list_param)
+        self.dt0 = self.dt
+        grid.finalize_msk()
+        self.list_grid = ['dx', 'dy', 'nh', 'msk', 'xr0', 'yr0', 'x2', 'y2']
+        grid.copy(self, self.list_grid)
+        self.grid = grid
+
+        if param.modelname == 'euler':
+            if self.geometry not in ['closed', 'disc']:
+                self.enforce_momentum = False
+            from euler import Euler
+            self.model = Euler(param, grid)
+        else:
+            self.enforce_momentum = False
+        if param.modelname == 'advection':
+            from advection import Advection
+            self.model = Advection(param, grid)
+        if param.modelname == 'boussinesq':
+            from boussinesq import Boussinesq
+            self.model = Boussinesq(param, grid)
+        if param.modelname == 'quasigeostrophic':
+            from quasigeostrophic import QG
+            self.model = QG(param, grid)
+        if param.modelname in ('boussinesqTS', 'sqg', 'thermalwind'):
+            raise NotImplementedError('model %s is outside the device hot path (see DESIGN.md)' % param.modelname)
+
+        self.enstrophyname = 'pv2' if self.modelname in ('quasigeostrophic', 'sqg') else 'enstrophy'
+
+        if self.isisland:
+            grid.island.finalize(self.model.ope.mskp)
+            self.model.ope.rhsp = grid.island.rhsp
+            self.model.ope.psi = grid.island.psi
+        if self.diag_fluxes:
+            raise NotImplementedError('diag_fluxes: the flux kernels exist (f2d_adv_* with xflx/yflx) but the '
+                                      'Fluxes driver is not built yet')
+        flxlist = None
+        if self.plot_interactive:
+            p = import_module(self.plotting_module)
+            self.plotting = p.Plotting(param, grid, self.model.var, self.model.diags)
+        self.tracer_list = param.tracer_list
+        self.t = 0.
+        self.kt = 0
+        self.output = Output(param, grid, self.model.diags, flxlist=flxlist)
+        self.print_config(param, start=True)
+
+    @property
+    def state(self):
+        return self.model.var.state
+
+    def print_config(self, param, start=True):
+        if self.myrank != 0:
+            return
+        if start:
+            print('-'*50)
+            print(' Fluid2d summary (B200 device build):')
+            print('-'*50)
+            print('  - model equations: %s' % self.modelname)
+            print('  - grid size: %i x %i' % (self.nx, self.ny))
+            print('  - integration time: %.2f' % self.tend)
+            print('  - advection schemes applied to:')
+            for trac in self.tracer_list:
+                print('    - %s' % trac)
+            if self.print_param:
+                param.printvalues()
+        else:
+            print(' Output files:')
+            print('-'*50)
+            for f in [self.output.hisfile, self.output.diagfile] + \
+                    ([self.savedscript] if hasattr(self, 'savedscript') else []):
+                print('  - %s' % f)
+            print('-'*50)
+
+    def loop(self, joinhis=True, keepplotalive=False, nsteps=None):
+        """time loop (fluid2d.py:188-349); nsteps (extension) stops after that many iterations"""
+        if self.myrank == 0:
+            print('-'*50)
+            print(' Starting the time loop')
+            print('-'*50)
+        model = self.model
+        model.diagnostics(model.var, self.t)
+        model.diags['dkedt'] = 0.
+        model.diags['dvdt'] = 0.
+        data = {'his': model.var, 'diag': model.diags}
+        self.output.do(data, self.t, self.kt)
+        if self.plot_interactive and not hasattr(self.plotting, 'fig'):
+            self.plotting.create_fig(self.t)
+
+        def signal_handler(sig, frame):
+            if self.myrank == 0:
+                print('\n hit ctrl-C, stopping', end='')
+            self.stop = True
+        try:
+            signal.signal(signal.SIGINT, signal_handler)
+        except ValueError:
+            pass   # not in the main thread
+        self.stop = False
+        kt0 = self.kt
+        t0 = clock()
+        reduce = 0
+        while (self.t < self.tend and not(self.stop)):
+            self.set_dt(self.kt)
+            # land exactly on the next history time, adjusting dt 8 steps ahead
+            if self.exacthistime and self.adaptable_dt:
+                if (self.t+8*self.dt > self.output.tnexthis) and (reduce == 0):
+                    reduce = 8
+                if (reduce > 0):
+                    self.dt = (self.output.tnexthis-self.t)/(reduce*0.95)
+                    reduce -= 1
+                if (self.t+self.dt > self.output.tnexthis):
+                    reduce = 0
+                    self.dt = self.output.tnexthis-self.t
+            model.step(self.t, self.dt)
+            if self.rescaledtime == 'enstrophy':
+                self.t += self.dt * np.sqrt(model.diags['enstrophy'])
+            else:
+                self.t += self.dt
+            self.kt += 1
+            ke_old = model.diags['ke']
+            ens_old = model.diags[self.enstrophyname]
+            model.diagnostics(model.var, self.t)
+            if self.enforce_momentum:
+                self.enforce_zero_momentum()
+                model.diagnostics(model.var, self.t)
+            ke = model.diags['ke']
+            ens = model.diags[self.enstrophyname]
+            model.diags['dkedt'] = (ke-ke_old)/self.dt
+            model.diags['dvdt'] = (ens-ens_old)/self.dt
+            if ((ke > ke_old) and (self.myrank == 0) and (self.decay) and (self.modelname == 'euler')):
+                print('\rkt=%-4i \033[0;32;40mWARNING dlog(ke)\033[0m = %.2g' %
+                      (self.kt, float(np.ravel((ke-ke_old)/ke)[0])), end='')
+            self.output.do(data, self.t, self.kt)
+            flag = '*' if self.dt == self.dtmax else ''
+            if (self.myrank == 0) and (self.kt % self.nprint == 0) or (self.t >= self.tend):
+                print('\rkt=%-4i / t=%-7.3f %s / dt=%-7.3f ' % (self.kt, self.t, flag, self.dt), end='')
+            if self.plot_interactive and (self.kt % self.freq_plot == 0):
+                self.plotting.update_fig(self.t, self.dt, self.kt)
+            if model.diags['maxspeed'] > 1e3:
+                self.stop = True
+                if self.myrank == 0:
+                    print()
+                    print('max|u| > 1000, blow-up detected, stopping')
+            if nsteps is not None and self.kt-kt0 >= nsteps:
+                break
+
+        if self.myrank == 0:
+            print('\ndone')
+        if self.plot_interactive and not(keepplotalive):
+            self.plotting.finalize()
+        if self.myrank == 0:
+            import torch
+            torch.cuda.synchronize()
+            wall = clock()-t0
+            nkt = max(self.kt-kt0, 1)
+            if hasattr(model, 'timers'):
+                print('-'*50)
+                print(' A few model performances metrics')
+                print('-'*50)
+                model.timers._print()
+            print()
+            print('  - Wall  time      : %f s' % wall)
+            print('  - Nb of iterations: %i' % nkt)
+            print('  - Time per ite    : %5.3f s' % (wall/nkt))
+            print('  - Rescaled time   : %5.3e s (per ite, per dof)' % (wall*self.npx*self.npy/(nkt*self.nx*self.ny)))
+            print('  - Cell updates/s  : %5.3e' % (nkt*self.nx*self.ny/wall))
+            print('-'*50)
+        if (self.myrank == 0) and joinhis:
+            self.output.dump_diag()
+            self.output.join()
+        self.print_config(None, start=False)
+
+    def enforce_zero_momentum(self):
+        if self.enforce_momentum:
+            model = self.model
+            r = model.rt
+            s = model.var.dstate
+            px = float(np.ravel(model.diags['px']/self.x2)[0])
+            py = float(np.ravel(model.diags['py']/self.y2)[0])
+            r.lib.sub_lin2(s.wptr(model.var.index('vorticity')), px, r.ptr(model.ope.d_xr0), py,
+                           r.ptr(model.ope.d_yr0), s.ny*s.nx, r.stream)
+            model.ope.invert_vorticity(s, flag='fast')
+
+    def set_dt(self, kt):
+        maxspeed = self.model.diags['maxspeed']
+        if ((self.adaptable_dt) & (maxspeed != 0)):
+            dt = self.cfl * min(self.dx, self.dy) / maxspeed
+            self.dt = dt
+            if self.dt > self.dtmax:
+                self.dt = self.dtmax
+        else:
+            self.dt = self.dt0
+        # the advection scheme needs max|u| for the parabolic flux splitting
+        self.model.ope.cst[3] = maxspeed
+
+
+class Logger(object):
+    """tee of stdout into expdir/output.txt"""
+
+    def __init__(self, logfile):
+        self.terminal = sys.stdout if not isinstance(sys.stdout, Logger) else sys.stdout.terminal
+        self.log = open(logfile, "w")
+
+    def write(self, message):
+        self.terminal.write(message)
+        self.log.write(message)
+
+    def flush(self):
+        self.terminal.flush()

@@ -1,0 +1,111 @@
+"""QG: quasi-geostrophic model, prognostic full PV (reference: core/quasigeostrophic.py).
+The elliptic operator is the Helmholtz operator (Laplacian - 1/Rd^2), built by the
+device multigrid when param.qgoperator is set (hierarchy.py:80-84)."""
+import numpy as np
+from importlib import import_module
+import torch
+
+from operators import Operators
+from variables import Var
+from timescheme import Timescheme
+from runtime import rt
+
+
+class QG(object):
+    def __init__(self, param, grid):
+        self.list_param = ['forcing', 'diffusion', 'Kdiff', 'noslip', 'timestepping', 'beta', 'Rd',
+                           'ageostrophic', 'bottom_torque', 'forcing_module']
+        param.copy(self, self.list_param)
+        self.list_param = ['yr', 'nh', 'msk', 'area', 'mpitools', 'isisland']
+        grid.copy(self, self.list_param)
+        if param.bottom_torque or param.ageostrophic:
+            raise NotImplementedError('QG: bottom_torque / ageostrophic diagnostics are not built yet')
+        param.varname_list = ['pv', 'psi', 'u', 'v', 'pvanom', 'vorticity']
+        param.sizevar = [grid.nyl, grid.nxl]
+        self.var = Var(param)
+        r = rt()
+        self.rt = r
+        self.ncell = grid.nyl*grid.nxl
+        self.source = torch.zeros((grid.nyl, grid.nxl), dtype=torch.float64, device=r.device)
+        self.ipva = self.var.index('pvanom')
+        self.ipv = self.var.index('pv')
+        self.ivor = self.var.index('vorticity')
+        self.ipsi = self.var.index('psi')
+        self.pvback = self.beta*(grid.yr-grid.Ly*.5)*grid.msk
+        self.d_pvback = r.to_device(self.pvback, dtype=np.float64)
+        param.tracer_list = ['pv']
+        param.whosetspsi = ('pvanom')
+        param.qgoperator = True
+        self.ope = Operators(param, grid)
+        self.tscheme = Timescheme(param, self.var.dstate)
+        self.dx0 = self.tscheme.dx0
+        self.kt = 0
+        if self.forcing:
+            if self.forcing_module != 'embedded':
+                f = import_module(self.forcing_module)
+                self.forc = f.Forcing(param, grid)
+        self.diags = {}
+        self.tscheme.set(self.dynamics, self.timestepping)
+
+    def step(self, t, dt):
+        r, lib = self.rt, self.rt.lib
+        s = self.var.dstate
+        self.dt = dt
+        self.tscheme.forward(s, t, dt)
+        if self.noslip:
+            self.add_noslip(s)
+        self.set_psi_from_pv()
+        lib.set_sum(s.wptr(self.ipva), s.rptr(self.ipv), -1., r.ptr(self.d_pvback), self.ncell, r.stream)
+        lib.set_sum(s.wptr(self.ivor), s.rptr(self.ipva), -(self.Rd**-2), s.rptr(self.ipsi), self.ncell, r.stream)
+
+    def dynamics(self, x, t, dxdt):
+        r, lib = self.rt, self.rt.lib
+        lib.zero(dxdt.all_ptr(True), dxdt.size*8, r.stream)
+        self.ope.rhs_adv(x, t, dxdt)
+        if self.tscheme.kstage == self.tscheme.kforcing:
+            if self.forcing:
+                self.forc.add_forcing(x, t, dxdt)
+            if self.diffusion:
+                self.ope.rhs_diffusion(x, t, dxdt)
+        else:
+            lib.copy(dxdt.wptr(self.ipva), dxdt.rptr(self.ipv), self.ncell*8, r.stream)
+            self.ope.invert_vorticity(dxdt, flag='fast', island=self.isisland)
+
+    def add_noslip(self, x):
+        self.ope.rhs_noslip(x, self.source)
+        self.ope.invert_vorticity(x, flag='fast', island=self.isisland)
+
+    def add_backgroundpv(self):
+        r, lib = self.rt, self.rt.lib
+        s = self.var.dstate
+        lib.add_scaled(s.wptr(self.ipv), 1., r.ptr(self.d_pvback), self.ncell, r.stream)
+
+    def set_psi_from_pv(self):
+        r, lib = self.rt, self.rt.lib
+        s = self.var.dstate
+        lib.set_sum(s.wptr(self.ipva), s.rptr(self.ipv), -1., r.ptr(self.d_pvback), self.ncell, r.stream)
+        self.ope.invert_vorticity(s, flag='full', island=self.isisland)
+
+    def diagnostics(self, var, t):
+        import ctypes
+        r, lib = self.rt, self.rt.lib
+        s = var.dstate
+        nh, ny, nx = self.nh, s.ny, s.nx
+        msk, sc = r.ptr(self.ope.d_msk), r.ptr(r.scratch)
+
+        def slot(k):
+            return ctypes.c_void_p(r.out.data_ptr()+8*k)
+
+        lib.cornertocell(s.rptr(self.ipsi), r.ptr(self.ope.work), ny, nx, r.stream)
+        lib.computesumandnorm(msk, r.ptr(self.ope.work), nh, ny, nx, slot(0), sc, r.stream)
+        lib.computekemaxu(msk, s.rptr(var.index('u')), s.rptr(var.index('v')), nh, ny, nx, slot(2), sc, r.stream)
+        lib.computesumandnorm(msk, s.rptr(self.ipv), nh, ny, nx, slot(4), sc, r.stream)
+        psim, psi2, ke, maxu, z, z2 = r.read_out(6)
+        ape = 0.5 * psi2 / self.Rd**2
+        cst = self.mpitools.local_to_global([(maxu, 'max'), (ke, 'sum'), (z, 'sum'), (z2, 'sum'), (ape, 'sum')])
+        self.diags['maxspeed'] = cst[0]
+        self.diags['ke'] = cst[1] / self.area
+        self.diags['pv'] = cst[2] / self.area
+        self.diags['pv2'] = 0.5*cst[3] / self.area
+        self.diags['ape'] = cst[4] / self.area
+        self.diags['energy'] = (cst[1]+cst[4]) / self.area

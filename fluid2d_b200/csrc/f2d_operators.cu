@@ -323,6 +323,21 @@ extern "C" int f2d_add_scaled_mask(double *y, double alpha, const int8_t *a, siz
 extern "C" int f2d_set_sum(double *y, const double *a, double alpha, const double *b, size_t n, f2d_stream_t s) {
   return elementwise(n, S(s), [=] __device__(size_t k) { y[k] = add_rn(a[k], mul_rn(alpha, b[k])); });
 }
+extern "C" int f2d_div_scalar(double *y, double d, size_t n, f2d_stream_t s) {
+  return elementwise(n, S(s), [=] __device__(size_t k) { y[k] = __ddiv_rn(y[k], d); });
+}
+extern "C" int f2d_sub_lin2_mask(double *y, double pa, const double *a, double pb, const double *b,
+                                 const int8_t *mask, size_t n, f2d_stream_t s) {
+  return elementwise(n, S(s), [=] __device__(size_t k) {
+    y[k] = add_rn(y[k], -mul_rn(add_rn(mul_rn(pa, a[k]), mul_rn(pb, b[k])), (double)mask[k]));
+  });
+}
+extern "C" int f2d_sub_lin2(double *y, double pa, const double *a, double pb, const double *b, size_t n,
+                            f2d_stream_t s) {
+  return elementwise(n, S(s), [=] __device__(size_t k) {
+    y[k] = add_rn(y[k], -add_rn(mul_rn(a[k], pa), mul_rn(b[k], pb)));
+  });
+}
 extern "C" int f2d_sub_devscalar(double *y, const double *dev_scalar, double denom, size_t n, f2d_stream_t s) {
   return elementwise(n, S(s), [=] __device__(size_t k) { y[k] = add_rn(y[k], -__ddiv_rn(dev_scalar[0], denom)); });
 }

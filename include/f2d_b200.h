@@ -184,6 +184,14 @@ int f2d_add_scaled_mask(double *y, double alpha, const int8_t *a, size_t n,
                         f2d_stream_t stream);
 int f2d_set_sum(double *y, const double *a, double alpha, const double *b, size_t n,
                 f2d_stream_t stream);
+/* y = y / d  (euler.py:112 source /= dt: a true division) */
+int f2d_div_scalar(double *y, double d, size_t n, f2d_stream_t stream);
+/* y -= (pa*a + pb*b)*mask  (operators.py:287, zero-momentum correction of the source) */
+int f2d_sub_lin2_mask(double *y, double pa, const double *a, double pb, const double *b,
+                      const int8_t *mask, size_t n, f2d_stream_t stream);
+/* y -= (pa*a + pb*b)       (fluid2d.py:356 enforce_zero_momentum) */
+int f2d_sub_lin2(double *y, double pa, const double *a, double pb, const double *b, size_t n,
+                 f2d_stream_t stream);
 int f2d_sub_devscalar(double *y, const double *dev_scalar, double denom, size_t n,
                       f2d_stream_t stream);
 int f2d_sub_devscalar_mask(double *y, const double *dev_scalar, double denom,

@@ -28,6 +28,7 @@ def _common(param, expname, datadir):
     param.tend = 1e30
     param.npx = 1
     param.npy = 1
+    param.tee_stdout = False   # (fluid2d_b200 extension: do not tee stdout into expdir)
 
 
 def freedecay(api, datadir, n=64, order=5, tracer=True, timestepping='RK3_SSP'):

@@ -6,11 +6,13 @@
 // scratch t.  Every operator application is followed in the reference by a periodic
 // halo fill (level.py:365,384,493); here the fill is fused into the producing kernel
 // (threads owning rim cells also store the halo images).
+#include <stdlib.h>
 #include <vector>
 #include <map>
 #include <tuple>
 
 #include "f2d_common.cuh"
+#include "f2d_mg_fused.cuh"
 
 using namespace f2d;
 
@@ -23,6 +25,7 @@ struct Level {
   double *A = nullptr;      // 5 planes
   double *x = nullptr, *b = nullptr, *r = nullptr, *t = nullptr;
   int mode = 0;             // 0 stored, 1 constant, 2 constant x mask products
+  double cst[5] = {0, 0, 0, 0, 0};  // SW,S,SE,W,C of the constant classes
   size_t n() const { return (size_t)ny * nx; }
 };
 }  // namespace
@@ -255,17 +258,78 @@ inline int nblocks1d(size_t n) {
 // ---------------------------------------------------------------------------
 // per-level operators
 // ---------------------------------------------------------------------------
+fused::LevelK level_k(f2d_mg *mg, int lev) {
+  Level &l = mg->L[lev];
+  fused::LevelK k;
+  k.ny = l.ny; k.nx = l.nx; k.msk = l.msk; k.A = l.A;
+  for (int q = 0; q < 5; q++) k.c[q] = l.cst[q];
+  k.c1 = mg->omega;
+  k.c2 = 1. - mg->omega;
+  k.c3 = l.cst[4] != 0. ? mg->omega / fabs(l.cst[4]) : 0.;
+  return k;
+}
+
+// fused double sweep: xout = S2(input), input = xin | 0 | I(xc) | xin + I(xc)
+template <int INPUT>
+int launch_smooth2(f2d_mg *mg, int lev, const double *xin, const double *b, double *xout, const double *xc,
+                   cudaStream_t s) {
+  Level &l = mg->L[lev];
+  fused::LevelK k = level_k(mg, lev);
+  dim3 grid(cdiv(l.nx - 2 * NH, fused::TX), cdiv(l.ny - 2 * NH, fused::TY));
+  size_t sm = sizeof(fused::Smooth2Smem);
+  const int8_t *mskc = nullptr;
+  int nxc = 0, nyc = 0;
+  if (INPUT >= 2) {
+    Level &c = mg->L[lev + 1];
+    mskc = c.msk; nxc = c.nx; nyc = c.ny;
+  }
+  switch (l.mode) {
+    case 1: fused::k_smooth2<false, false, INPUT><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc); break;
+    case 2: fused::k_smooth2<true, false, INPUT><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc); break;
+    default: fused::k_smooth2<true, true, INPUT><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc); break;
+  }
+  F2D_LAUNCHED();
+  return F2D_OK;
+}
+int smooth2(f2d_mg *mg, int lev, int input, const double *xin, const double *b, double *xout, const double *xc,
+            cudaStream_t s) {
+  switch (input) {
+    case 0: return launch_smooth2<0>(mg, lev, xin, b, xout, xc, s);
+    case 1: return launch_smooth2<1>(mg, lev, xin, b, xout, xc, s);
+    case 2: return launch_smooth2<2>(mg, lev, xin, b, xout, xc, s);
+    default: return launch_smooth2<3>(mg, lev, xin, b, xout, xc, s);
+  }
+}
+template <bool M, bool St, int I>
+cudaError_t set_smem_one() {
+  return cudaFuncSetAttribute(fused::k_smooth2<M, St, I>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)sizeof(fused::Smooth2Smem));
+}
+template <int I>
+cudaError_t set_smem_input() {
+  cudaError_t e = set_smem_one<false, false, I>();
+  if (e == cudaSuccess) e = set_smem_one<true, false, I>();
+  if (e == cudaSuccess) e = set_smem_one<true, true, I>();
+  return e;
+}
+cudaError_t set_smem_all() {
+  cudaError_t e = set_smem_input<0>();
+  if (e == cudaSuccess) e = set_smem_input<1>();
+  if (e == cudaSuccess) e = set_smem_input<2>();
+  if (e == cudaSuccess) e = set_smem_input<3>();
+  return e;
+}
+
+// Grid.smooth: nite x (double sweep + fill); ping-pong through the level scratch t
 int op_smooth(f2d_mg *mg, int lev, double *x, const double *b, int nite, cudaStream_t s) {
   Level &l = mg->L[lev];
-  dim3 blk(32, 8), grd = grid2d(l.ny, l.nx, blk);
-  double c1 = mg->omega, c2 = 1. - c1;
+  double *cur = x, *other = l.t;
   for (int k = 0; k < nite; k++) {
-    // sweep 1 on [2, n-3] (all that sweep 2 needs), sweep 2 on the interior + halo fill
-    k_jacobi<<<grd, blk, 0, s>>>(l.msk, l.A, x, b, l.t, c1, c2, l.ny, l.nx, 2, 0);
-    F2D_LAUNCHED();
-    k_jacobi<<<grd, blk, 0, s>>>(l.msk, l.A, l.t, b, x, c1, c2, l.ny, l.nx, NH, 1);
-    F2D_LAUNCHED();
+    int rc = smooth2(mg, lev, 0, cur, b, other, nullptr, s);
+    if (rc != F2D_OK) return rc;
+    double *tmp = cur; cur = other; other = tmp;
   }
+  if (cur != x) F2D_CUDA(cudaMemcpyAsync(x, cur, l.n() * sizeof(double), cudaMemcpyDeviceToDevice, s));
   return F2D_OK;
 }
 int op_residual(f2d_mg *mg, int lev, const double *x, const double *b, double *r, cudaStream_t s) {
@@ -279,6 +343,20 @@ int op_restrict(f2d_mg *mg, int lev, const double *xf, double *xc, cudaStream_t 
   Level &c = mg->L[lev + 1];
   dim3 blk(32, 8);
   k_restrict<<<grid2d(c.ny, c.nx, blk), blk, 0, s>>>(c.msk, xf, xc, c.ny, c.nx, mg->L[lev].nx);
+  F2D_LAUNCHED();
+  return F2D_OK;
+}
+// residual + restriction fused: bc = R(b - A x), the fine residual stays on chip
+int op_resid_restrict(f2d_mg *mg, int lev, const double *x, const double *b, double *bc, cudaStream_t s) {
+  Level &l = mg->L[lev];
+  Level &c = mg->L[lev + 1];
+  fused::LevelK k = level_k(mg, lev);
+  dim3 grid(cdiv(c.nx - 2 * NH, fused::RTX), cdiv(c.ny - 2 * NH, fused::RTY));
+  switch (l.mode) {
+    case 1: fused::k_resid_restrict<false, false><<<grid, fused::NT, 0, s>>>(k, x, b, bc, c.msk, c.ny, c.nx); break;
+    case 2: fused::k_resid_restrict<true, false><<<grid, fused::NT, 0, s>>>(k, x, b, bc, c.msk, c.ny, c.nx); break;
+    default: fused::k_resid_restrict<true, true><<<grid, fused::NT, 0, s>>>(k, x, b, bc, c.msk, c.ny, c.nx); break;
+  }
   F2D_LAUNCHED();
   return F2D_OK;
 }
@@ -297,27 +375,39 @@ int op_interpolate(f2d_mg *mg, int lev, const double *xc, double *xf, int add, c
     if (rc__ != F2D_OK) return rc__; \
   } while (0)
 
-// hierarchy.py:98-127; x0/b0 stand for self.x[lev1], self.b[lev1]
-int vcycle_enqueue(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s) {
+// deepest level: x = 0, then ndeepest double sweeps (hierarchy.py:114-116); the first
+// sweep takes the zero input implicitly, the result ends in X (ndeepest is even)
+int coarsest_enqueue(f2d_mg *mg, double *X, const double *B, cudaStream_t s) {
+  int last = (int)mg->L.size() - 1;
+  Level &l = mg->L[last];
+  double *cur = X, *other = l.t;
+  for (int k = 0; k < mg->ndeepest; k++) {
+    TRY(smooth2(mg, last, k == 0 ? 1 : 0, cur, B, other, nullptr, s));
+    double *tmp = cur; cur = other; other = tmp;
+  }
+  if (cur != X) F2D_CUDA(cudaMemcpyAsync(X, cur, l.n() * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  return F2D_OK;
+}
+
+// hierarchy.py:98-127 with npre = npost = 1; x0/b0 stand for self.x[lev1], self.b[lev1].
+// Going down, the pre-smoothed field of a level lives in its scratch t; coming up,
+// interpolation, correction and post-smoothing are one kernel that writes x again.
+// first_input: 0 = start from x0 as it is; 2 = x0 := I(x[lev1+1]) first (the F-cycle's
+// coarsetofine, hierarchy.py:145-146, fused into the pre-smoothing).
+int vcycle_enqueue(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s, int first_input = 0) {
   int last = (int)mg->L.size() - 1;
   auto X = [&](int lev) { return lev == lev1 ? x0 : mg->L[lev].x; };
   auto B = [&](int lev) { return lev == lev1 ? b0 : mg->L[lev].b; };
+  if (lev1 == last) return coarsest_enqueue(mg, X(last), B(last), s);
   for (int lev = lev1; lev < last; lev++) {
     Level &l = mg->L[lev];
-    if (lev > lev1) F2D_CUDA(cudaMemsetAsync(X(lev), 0, l.n() * sizeof(double), s));
-    TRY(op_smooth(mg, lev, X(lev), B(lev), mg->npre, s));
-    TRY(op_residual(mg, lev, X(lev), B(lev), l.r, s));
-    TRY(op_restrict(mg, lev, l.r, B(lev + 1), s));
+    int input = lev > lev1 ? 1 : first_input;
+    TRY(smooth2(mg, lev, input, X(lev), B(lev), l.t, input == 2 ? X(lev + 1) : nullptr, s));
+    TRY(op_resid_restrict(mg, lev, l.t, B(lev), B(lev + 1), s));
   }
-  if (last > lev1 || true) {
-    Level &l = mg->L[last];
-    F2D_CUDA(cudaMemsetAsync(X(last), 0, l.n() * sizeof(double), s));
-    TRY(op_smooth(mg, last, X(last), B(last), mg->ndeepest, s));
-  }
-  for (int lev = last - 1; lev >= lev1; lev--) {
-    TRY(op_interpolate(mg, lev, X(lev + 1), X(lev), 1, s));
-    TRY(op_smooth(mg, lev, X(lev), B(lev), mg->npost, s));
-  }
+  TRY(coarsest_enqueue(mg, X(last), B(last), s));
+  for (int lev = last - 1; lev >= lev1; lev--)
+    TRY(smooth2(mg, lev, 3, mg->L[lev].t, B(lev), X(lev), X(lev + 1), s));
   return F2D_OK;
 }
 
@@ -327,12 +417,9 @@ int fcycle_enqueue(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s)
   auto X = [&](int lev) { return lev == lev1 ? x0 : mg->L[lev].x; };
   auto B = [&](int lev) { return lev == lev1 ? b0 : mg->L[lev].b; };
   for (int lev = lev1; lev < last; lev++) TRY(op_restrict(mg, lev, B(lev), B(lev + 1), s));
-  F2D_CUDA(cudaMemsetAsync(X(last), 0, mg->L[last].n() * sizeof(double), s));
-  TRY(op_smooth(mg, last, X(last), B(last), mg->ndeepest, s));
-  for (int lev = last - 1; lev >= lev1; lev--) {
-    TRY(op_interpolate(mg, lev, X(lev + 1), X(lev), 0, s));
-    for (int k = 0; k < mg->nvcyc; k++) TRY(vcycle_enqueue(mg, lev, X(lev), B(lev), s));
-  }
+  TRY(coarsest_enqueue(mg, X(last), B(last), s));
+  for (int lev = last - 1; lev >= lev1; lev--)
+    for (int k = 0; k < mg->nvcyc; k++) TRY(vcycle_enqueue(mg, lev, X(lev), B(lev), s, k == 0 ? 2 : 0));
   return F2D_OK;
 }
 
@@ -483,6 +570,41 @@ extern "C" int f2d_mg_create(f2d_mg_t **out, const double *cornermask, int ny, i
       ++g_launches;
     }
   }
+  // coefficient class per level: read the stencil at the first cell whose 3x3
+  // neighbourhood is fluid, then verify entry by entry that "constant stencil x mask
+  // products" reproduces the stored matrix (f2d_mg_fused.cuh)
+  MGC(set_smem_all());
+  {
+    int *dflag = nullptr;
+    unsigned long long *didx = nullptr;
+    MGC(cudaMalloc(&dflag, 2 * sizeof(int)));
+    MGC(cudaMalloc(&didx, sizeof(unsigned long long)));
+    for (size_t lev = 0; lev < mg->L.size(); lev++) {
+      Level &l = mg->L[lev];
+      l.mode = 0;
+      unsigned long long none = ~0ull, idx = none;
+      MGC(cudaMemcpyAsync(didx, &none, sizeof none, cudaMemcpyHostToDevice, s));
+      fused::k_find_interior<<<grid2d(l.ny, l.nx, blk), blk, 0, s>>>(l.msk, l.ny, l.nx, didx);
+      MGC(cudaMemcpyAsync(&idx, didx, sizeof idx, cudaMemcpyDeviceToHost, s));
+      MGC(cudaStreamSynchronize(s));
+      if (idx == none) continue;
+      for (int k = 0; k < 5; k++)
+        MGC(cudaMemcpyAsync(&l.cst[k], l.A + k * l.n() + idx, sizeof(double), cudaMemcpyDeviceToHost, s));
+      int flags[2] = {1, 1};
+      MGC(cudaMemcpyAsync(dflag, flags, sizeof flags, cudaMemcpyHostToDevice, s));
+      MGC(cudaStreamSynchronize(s));
+      fused::k_check_const<<<grid2d(l.ny, l.nx, blk), blk, 0, s>>>(level_k(mg, (int)lev), dflag);
+      MGC(cudaMemcpyAsync(flags, dflag, sizeof flags, cudaMemcpyDeviceToHost, s));
+      MGC(cudaStreamSynchronize(s));
+      g_launches += 2;
+      if (flags[0]) l.mode = flags[1] ? 1 : 2;
+    }
+    cudaFree(dflag);
+    cudaFree(didx);
+  }
+  if (const char *force = getenv("F2D_MG_FORCE_STORED"))
+    if (force[0] == '1')
+      for (auto &l : mg->L) l.mode = 0;
   MGC(cudaStreamSynchronize(s));
   MGC(cudaGetLastError());
 #undef MGC

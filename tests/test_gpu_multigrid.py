@@ -49,8 +49,10 @@ def L(request):
     return _lib.lib(strict=request.param == "strict"), request.param == "strict"
 
 
-def make(lib, kind, ny, nx, Rd=0.):
+def make(lib, kind, ny, nx, Rd=0., force_stored=False):
+    import os
     import gpu_util as g
+    os.environ["F2D_MG_FORCE_STORED"] = "1" if force_stored else "0"
     rng = np.random.default_rng(ny + nx)
     msk = cell_mask(kind, ny, nx, rng)
     cm = corner_mask(msk)
@@ -136,12 +138,28 @@ def test_level_operators(L, kind, ny, nx):
         lib.mg_destroy(h)
 
 
+def test_matrix_classes(L):
+    """doubly periodic: every level is a constant stencil; walls: the finest level is
+    stencil x mask products, Galerkin levels next to walls keep stored coefficients"""
+    lib, strict = L
+    ref, h, rng = make(lib, "perio", 64, 64)
+    assert [lib.mg_level_matrix_mode(h, l) for l in range(ref.nlevs)] == [1]*ref.nlevs
+    lib.mg_destroy(h)
+    ref, h, rng = make(lib, "obstacle", 64, 128)
+    modes = [lib.mg_level_matrix_mode(h, l) for l in range(ref.nlevs)]
+    assert modes[0] == 2 and set(modes[1:]) <= {0, 2}
+    lib.mg_destroy(h)
+    ref, h, rng = make(lib, "perio", 64, 64, force_stored=True)
+    assert [lib.mg_level_matrix_mode(h, l) for l in range(ref.nlevs)] == [0]*ref.nlevs
+    lib.mg_destroy(h)
+
+
 @pytest.mark.parametrize("kind,ny,nx", CASES)
-@pytest.mark.parametrize("graphs", [0, 1])
-def test_cycles_and_solve(L, kind, ny, nx, graphs):
+@pytest.mark.parametrize("graphs,force_stored", [(0, False), (1, False), (1, True)])
+def test_cycles_and_solve(L, kind, ny, nx, graphs, force_stored):
     import gpu_util as g
     lib, strict = L
-    ref, h, rng = make(lib, kind, ny, nx)
+    ref, h, rng = make(lib, kind, ny, nx, force_stored=force_stored)
     s = g.stream()
     lib.mg_set_graphs(h, graphs)
     tol_cycle = 1e-12

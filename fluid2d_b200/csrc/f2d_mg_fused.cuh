@@ -338,20 +338,23 @@ k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restric
 
 // ---------------------------------------------------------------------------
 // k_check_const: does "constant stencil x mask products" reproduce the stored matrix
-// on every entry the kernels can read?  flag[0] is cleared on the first mismatch;
-// flag[1] is cleared when some cell of the level is solid.
+// on every entry the kernels read (cells [2, n-3] compute; they read coefficients and
+// masks of [1, n-2])?  flag[0] is cleared on the first mismatch; flag[1] is cleared when
+// some cell of [1, n-2] is solid.
 // ---------------------------------------------------------------------------
 __global__ void k_check_const(LevelK L, int *flag) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int j = blockIdx.y * blockDim.y + threadIdx.y;
   int ny = L.ny, nx = L.nx;
-  if (i >= nx || j >= ny) return;
+  // masks are consulted on [1, n-2] (gates on [2, n-3] + their neighbours); the outer
+  // ring never enters a value that survives the halo fill
+  if (j < 1 || j > ny - 2 || i < 1 || i > nx - 2) return;
   size_t g = (size_t)j * nx + i;
   if (L.msk[g] == 0) {
     flag[1] = 0;
     return;
   }
-  if (j < 1 || j > ny - 2 || i < 1 || i > nx - 2) return;
+  if (j < 2 || j > ny - 3 || i < 2 || i > nx - 3) return;
   Coefs<true, true> st;
   st.load(L, g, nullptr, 0);
   Coefs<true, false> cm;

@@ -601,6 +601,10 @@ extern "C" int f2d_mg_create(f2d_mg_t **out, const double *cornermask, int ny, i
     }
     cudaFree(dflag);
     cudaFree(didx);
+    // the mask-free kernels also skip the coarse-mask tests of the transfers they fuse:
+    // a level stays in class 1 only if the next coarser level is all fluid as well
+    for (size_t lev = mg->L.size() - 1; lev-- > 0;)
+      if (mg->L[lev].mode == 1 && mg->L[lev + 1].mode != 1) mg->L[lev].mode = 2;
   }
   if (const char *force = getenv("F2D_MG_FORCE_STORED"))
     if (force[0] == '1')

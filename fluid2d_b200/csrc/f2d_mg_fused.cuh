@@ -116,6 +116,16 @@ struct Smooth2Smem {
   int8_t cm[CH][CW];
 };
 
+// 8-byte asynchronous global->shared copy (LDGSTS); !pred zero-fills the destination
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem, bool pred) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = pred ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
 // INPUT: 0 xin, 1 zero, 2 I(xc), 3 xin + I(xc)
 template <bool MASKED, bool STORED, int INPUT>
 __global__ void __launch_bounds__(NT)
@@ -124,68 +134,89 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smooth2Smem &S = *reinterpret_cast<Smooth2Smem *>(smem_raw);
   const int ny = L.ny, nx = L.nx;
-  const int t = threadIdx.x;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int i0 = NH + blockIdx.x * TX, j0 = NH + blockIdx.y * TY;
   constexpr bool INTERP = INPUT >= 2;
-  // ---- stage the coarse tile (fused interpolation)
+  constexpr bool HAVE_X = (INPUT == 0 || INPUT == 3);
   const int cj0 = ((j0 - 2) >> 1) + 1, ci0 = ((i0 - 2) >> 1) + 1;
-  if (INTERP) {
-    for (int p = t; p < CH * CW; p += NT) {
-      int r = p / CW, q = p % CW;
-      int j = cj0 + r, i = ci0 + q;
-      bool in = j < nyc && i < nxc;
-      S.cs[r][q] = in ? xc[(size_t)j * nxc + i] : 0.;
-      if (MASKED) S.cm[r][q] = in ? mskc[(size_t)j * nxc + i] : (int8_t)0;
+  // ---- stage everything with asynchronous copies: one tile row per warp and pass
+  if (HAVE_X) {
+    for (int r = warp; r < XH; r += NT / 32) {
+      int j = j0 - 2 + r;
+      const double *row = xin + (size_t)j * nx + (i0 - 2);
+#pragma unroll
+      for (int q = lane; q < XW; q += 32) {
+        bool in = j < ny && (i0 - 2 + q) < nx;
+        cp_async8(&S.xs[r][q], in ? row + q : xin, in);
+      }
     }
-    __syncthreads();
   }
-  // ---- stage x (halo 2), mask, and b (halo 1)
-  for (int p = t; p < XH * XW; p += NT) {
-    int r = p / XW, q = p % XW;
-    int j = j0 - 2 + r, i = i0 - 2 + q;
-    bool in = j < ny && i < nx;
-    size_t g = (size_t)j * nx + i;
-    int m = 1;
-    if (MASKED) {
-      m = in ? L.msk[g] : 0;
-      S.ms[r][q] = (int8_t)m;
+  for (int r = warp; r < YH; r += NT / 32) {
+    int j = j0 - 1 + r;
+    const double *row = b + (size_t)j * nx + (i0 - 1);
+#pragma unroll
+    for (int q = lane; q < YW; q += 32) {
+      bool in = j < ny && (i0 - 1 + q) < nx;
+      cp_async8(&S.bs[r][q], in ? row + q : b, in);
     }
-    double v = 0.;
-    if (in) {
-      if (INPUT == 0 || INPUT == 3) v = xin[g];
-      if (INTERP) {
+  }
+  if (INTERP) {
+    for (int r = warp; r < CH; r += NT / 32) {
+      int j = cj0 + r;
+      const double *row = xc + (size_t)j * nxc + ci0;
+      for (int q = lane; q < CW; q += 32) {
+        bool in = j < nyc && (ci0 + q) < nxc;
+        cp_async8(&S.cs[r][q], in ? row + q : xc, in);
+        if (MASKED) S.cm[r][q] = in ? mskc[(size_t)j * nxc + ci0 + q] : (int8_t)0;
+      }
+    }
+  }
+  if (MASKED) {
+    for (int r = warp; r < XH; r += NT / 32) {
+      int j = j0 - 2 + r;
+      for (int q = lane; q < XW; q += 32) {
+        int i = i0 - 2 + q;
+        S.ms[r][q] = (j < ny && i < nx) ? L.msk[(size_t)j * nx + i] : (int8_t)0;
+      }
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  // ---- fused interpolation: xs = [xin +] I(xc)  (fortran_multigrid.f90:415-498)
+  if (INTERP) {
+    for (int r = warp; r < XH; r += NT / 32) {
+      int j = j0 - 2 + r;
+      int lj = (j >> 1) + 1 - cj0, pj = j & 1;
+      for (int q = lane; q < XW; q += 32) {
+        int i = i0 - 2 + q;
         double iv = 0.;
-        if (m > 0) {
-          int lj = (j >> 1) + 1 - cj0, li = (i >> 1) + 1 - ci0;
-          int pj = j & 1, pi = i & 1;
+        if (j < ny && i < nx && (!MASKED || S.ms[r][q] > 0)) {
+          int li = (i >> 1) + 1 - ci0, pi = i & 1;
           if (!pj && !pi) {
             iv = S.cs[lj][li];
           } else if (!pj) {
-            int s = MASKED ? S.cm[lj][li] + S.cm[lj][li + 1] : 2;
-            iv = (S.cs[lj][li] + S.cs[lj][li + 1]) * interp_w2(s);
+            int sm = MASKED ? S.cm[lj][li] + S.cm[lj][li + 1] : 2;
+            iv = (S.cs[lj][li] + S.cs[lj][li + 1]) * interp_w2(sm);
           } else if (!pi) {
-            int s = MASKED ? S.cm[lj][li] + S.cm[lj + 1][li] : 2;
-            iv = (S.cs[lj][li] + S.cs[lj + 1][li]) * interp_w2(s);
+            int sm = MASKED ? S.cm[lj][li] + S.cm[lj + 1][li] : 2;
+            iv = (S.cs[lj][li] + S.cs[lj + 1][li]) * interp_w2(sm);
           } else {
-            int s = MASKED ? S.cm[lj][li] + S.cm[lj][li + 1] + S.cm[lj + 1][li] + S.cm[lj + 1][li + 1] : 4;
-            iv = interp_w4(s) * (((S.cs[lj][li] + S.cs[lj][li + 1]) + S.cs[lj + 1][li]) + S.cs[lj + 1][li + 1]);
+            int sm = MASKED ? S.cm[lj][li] + S.cm[lj][li + 1] + S.cm[lj + 1][li] + S.cm[lj + 1][li + 1] : 4;
+            iv = interp_w4(sm) * (((S.cs[lj][li] + S.cs[lj][li + 1]) + S.cs[lj + 1][li]) + S.cs[lj + 1][li + 1]);
           }
         }
-        v = (INPUT == 3) ? v + iv : iv;
+        S.xs[r][q] = (INPUT == 3) ? S.xs[r][q] + iv : iv;
       }
     }
-    S.xs[r][q] = v;
+    __syncthreads();
   }
-  for (int p = t; p < YH * YW; p += NT) {
-    int r = p / YW, q = p % YW;
-    int j = j0 - 1 + r, i = i0 - 1 + q;
-    S.bs[r][q] = (j < ny && i < nx) ? b[(size_t)j * nx + i] : 0.;
-  }
-  __syncthreads();
-  // ---- sweep 1 on the tile + ring 1, restricted to [2, n-3] (all that sweep 2 reads)
-  // strips: thread (tx, tg) takes column tx of the y1 tile and a run of rows; the two
-  // extra columns are done point-wise afterwards
+  // ---- sweep 1 on the tile + ring 1, restricted to [2, n-3] (all that sweep 2 reads).
+  // Thread (tx, tg) takes column tx of the y1 tile and a run of rows, carrying the 3x3
+  // window in registers (3 shared-memory loads per point); the two extra columns of
+  // the ring are done point-wise afterwards.
   const int tx = t & (TX - 1), tg = t >> 6;  // TX == 64
+  Coefs<MASKED, STORED> kc;
+  if (!MASKED && !STORED) kc.load(L, 0, nullptr, 0);
   auto sweep1_point = [&](int r, int q) {   // r,q index the y1 tile
     int j = j0 - 1 + r, i = i0 - 1 + q;
     double val = 0.;
@@ -193,47 +224,56 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
       int xr = r + 1, xq = q + 1;  // same point in the x tile
       if (!MASKED || S.ms[xr][xq] != 0) {
         Coefs<MASKED, STORED> k;
-        k.load(L, (size_t)j * nx + i, MASKED ? &S.ms[xr][xq] : nullptr, XW);
-        val = jacobi_val<MASKED, STORED>(L, k, S.xs[xr - 1][xq - 1], S.xs[xr - 1][xq], S.xs[xr - 1][xq + 1],
-                                         S.xs[xr][xq - 1], S.xs[xr][xq], S.xs[xr][xq + 1], S.xs[xr + 1][xq - 1],
-                                         S.xs[xr + 1][xq], S.xs[xr + 1][xq + 1], S.bs[r][q]);
+        if (MASKED || STORED) k.load(L, (size_t)j * nx + i, MASKED ? &S.ms[xr][xq] : nullptr, XW); else k = kc;
+        double x00 = 0., x01 = 0., x02 = 0., x10 = 0., x11 = 0., x12 = 0., x20 = 0., x21 = 0., x22 = 0.;
+        if (INPUT != 1) {
+          x00 = S.xs[xr - 1][xq - 1]; x01 = S.xs[xr - 1][xq]; x02 = S.xs[xr - 1][xq + 1];
+          x10 = S.xs[xr][xq - 1];     x11 = S.xs[xr][xq];     x12 = S.xs[xr][xq + 1];
+          x20 = S.xs[xr + 1][xq - 1]; x21 = S.xs[xr + 1][xq]; x22 = S.xs[xr + 1][xq + 1];
+        }
+        val = jacobi_val<MASKED, STORED>(L, k, x00, x01, x02, x10, x11, x12, x20, x21, x22, S.bs[r][q]);
       }
     }
     S.y1[r][q] = val;
   };
   {
-    // rows of the y1 tile split 9,9,8,8 between the four row groups; the 3x3 window is
-    // carried in registers down the column (3 shared-memory loads per point)
     const int r0 = tg * 8 + (tg < 2 ? tg : 2), nr = tg < 2 ? 9 : 8;
     const int q = tx, xq = q + 1;
     const int i = i0 - 1 + q;
     const bool colok = (i >= 2 && i <= nx - 3);
-    double a0 = S.xs[r0][xq - 1], a1 = S.xs[r0][xq], a2 = S.xs[r0][xq + 1];
-    double m0 = S.xs[r0 + 1][xq - 1], m1 = S.xs[r0 + 1][xq], m2 = S.xs[r0 + 1][xq + 1];
+    double a0 = 0., a1 = 0., a2 = 0., m0 = 0., m1 = 0., m2 = 0.;
+    if (INPUT != 1) {
+      a0 = S.xs[r0][xq - 1]; a1 = S.xs[r0][xq]; a2 = S.xs[r0][xq + 1];
+      m0 = S.xs[r0 + 1][xq - 1]; m1 = S.xs[r0 + 1][xq]; m2 = S.xs[r0 + 1][xq + 1];
+    }
+#pragma unroll 3
     for (int r = r0; r < r0 + nr; r++) {
-      double h0 = S.xs[r + 2][xq - 1], h1 = S.xs[r + 2][xq], h2 = S.xs[r + 2][xq + 1];
+      double h0 = 0., h1 = 0., h2 = 0.;
+      if (INPUT != 1) { h0 = S.xs[r + 2][xq - 1]; h1 = S.xs[r + 2][xq]; h2 = S.xs[r + 2][xq + 1]; }
       int j = j0 - 1 + r;
       double val = 0.;
       if (colok && j >= 2 && j <= ny - 3 && (!MASKED || S.ms[r + 1][xq] != 0)) {
         Coefs<MASKED, STORED> k;
-        k.load(L, (size_t)j * nx + i, MASKED ? &S.ms[r + 1][xq] : nullptr, XW);
+        if (MASKED || STORED) k.load(L, (size_t)j * nx + i, MASKED ? &S.ms[r + 1][xq] : nullptr, XW); else k = kc;
         val = jacobi_val<MASKED, STORED>(L, k, a0, a1, a2, m0, m1, m2, h0, h1, h2, S.bs[r][q]);
       }
       S.y1[r][q] = val;
       a0 = m0; a1 = m1; a2 = m2;
       m0 = h0; m1 = h1; m2 = h2;
     }
-    for (int p = t; p < YH * 2; p += NT) sweep1_point(p >> 1, TX + (p & 1));
+    if (t < YH * 2) sweep1_point(t >> 1, TX + (t & 1));
   }
   __syncthreads();
-  // ---- sweep 2 on the tile interior, halo images stored too
+  // ---- sweep 2 on the tile interior; tiles that touch the rim also store halo images
   {
+    const bool rim = (j0 < 2 * NH) || (i0 < 2 * NH) || (j0 + TY > ny - 2 * NH) || (i0 + TX > nx - 2 * NH);
     const int r0 = tg * 8;
     const int i = i0 + tx;
     const int yq = tx + 1;
     if (i <= nx - 1 - NH) {
       double a0 = S.y1[r0][yq - 1], a1 = S.y1[r0][yq], a2 = S.y1[r0][yq + 1];
       double m0 = S.y1[r0 + 1][yq - 1], m1 = S.y1[r0 + 1][yq], m2 = S.y1[r0 + 1][yq + 1];
+#pragma unroll 4
       for (int r = r0; r < r0 + 8; r++) {
         int j = j0 + r;
         if (j > ny - 1 - NH) break;
@@ -241,11 +281,12 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
         double val = 0.;
         if (!MASKED || S.ms[r + 2][tx + 2] != 0) {
           Coefs<MASKED, STORED> k;
-          k.load(L, (size_t)j * nx + i, MASKED ? &S.ms[r + 2][tx + 2] : nullptr, XW);
+          if (MASKED || STORED) k.load(L, (size_t)j * nx + i, MASKED ? &S.ms[r + 2][tx + 2] : nullptr, XW); else k = kc;
           val = jacobi_val<MASKED, STORED>(L, k, a0, a1, a2, m0, m1, m2, h0, h1, h2, S.bs[r + 1][yq]);
         }
         xout[(size_t)j * nx + i] = val;
-        f2d::for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { xout[(size_t)jj * nx + ii] = val; });
+        if (rim)
+          f2d::for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { xout[(size_t)jj * nx + ii] = val; });
         a0 = m0; a1 = m1; a2 = m2;
         m0 = h0; m1 = h1; m2 = h2;
       }
@@ -275,27 +316,50 @@ __device__ double resid_global(const LevelK &L, const double *__restrict__ x, co
                                    x[g + nx - 1], x[g + nx], x[g + nx + 1], b[g]);
 }
 
+struct ResidSmem {
+  double xs[RXH][RXW];
+  double rs[RH][RW];
+  double bs[RH][RW];
+  int8_t ms[RXH][RXW];
+};
+
 template <bool MASKED, bool STORED>
 __global__ void __launch_bounds__(NT)
 k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ bc,
                  const int8_t *__restrict__ mskc, int nyc, int nxc) {
-  __shared__ double xs[RXH][RXW];
-  __shared__ double rs[RH][RW];
-  __shared__ int8_t ms[MASKED ? RXH : 1][MASKED ? RXW : 1];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ResidSmem &S = *reinterpret_cast<ResidSmem *>(smem_raw);
   const int ny = L.ny, nx = L.nx;
-  const int t = threadIdx.x;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int ci0 = NH + blockIdx.x * RTX, cj0 = NH + blockIdx.y * RTY;  // first coarse output
   const int fi0 = 2 * ci0 - 3, fj0 = 2 * cj0 - 3;                      // first fine residual point
-  for (int p = t; p < RXH * RXW; p += NT) {
-    int r = p / RXW, q = p % RXW;
-    int j = fj0 - 1 + r, i = fi0 - 1 + q;
-    bool in = j < ny && i < nx;
-    xs[r][q] = in ? x[(size_t)j * nx + i] : 0.;
-    if (MASKED) ms[r][q] = in ? L.msk[(size_t)j * nx + i] : (int8_t)0;
+  for (int r = warp; r < RXH; r += NT / 32) {
+    int j = fj0 - 1 + r;
+    const double *row = x + (size_t)j * nx + (fi0 - 1);
+#pragma unroll
+    for (int q = lane; q < RXW; q += 32) {
+      bool in = j < ny && (fi0 - 1 + q) < nx;
+      cp_async8(&S.xs[r][q], in ? row + q : x, in);
+      if (MASKED) S.ms[r][q] = in ? L.msk[(size_t)j * nx + fi0 - 1 + q] : (int8_t)0;
+    }
   }
+  for (int r = warp; r < RH; r += NT / 32) {
+    int j = fj0 + r;
+    const double *row = b + (size_t)j * nx + fi0;
+#pragma unroll
+    for (int q = lane; q < RW; q += 32) {
+      bool in = j < ny && (fi0 + q) < nx;
+      cp_async8(&S.bs[r][q], in ? row + q : b, in);
+    }
+  }
+  cp_async_wait_all();
   __syncthreads();
-  for (int p = t; p < RH * RW; p += NT) {
-    int r = p / RW, q = p % RW;
+  // ---- fine residual on the (2RTX+1) x (2RTY+1) tile: column strips with the 3x3 window
+  // in registers; column 2RTX point-wise
+  Coefs<MASKED, STORED> kc;
+  if (!MASKED && !STORED) kc.load(L, 0, nullptr, 0);
+  auto resid_point = [&](int r, int q, double x00, double x01, double x02, double x10, double x11, double x12,
+                         double x20, double x21, double x22) -> double {
     int j = fj0 + r, i = fi0 + q;
     double val = 0.;
     if (j <= ny - NH && i <= nx - NH) {
@@ -303,22 +367,40 @@ k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restric
         // first halo ring on the high side: the reference reads the halo-filled residual
         // there, i.e. the residual of the periodic source cell
         val = resid_global<MASKED, STORED>(L, x, b, f2d::wrap_src(j, ny, NH), f2d::wrap_src(i, nx, NH));
-      } else {
-        int xr = r + 1, xq = q + 1;
-        if (!MASKED || ms[xr][xq] != 0) {
-          size_t g = (size_t)j * nx + i;
-          Coefs<MASKED, STORED> k;
-          k.load(L, g, MASKED ? &ms[xr][xq] : nullptr, RXW);
-          double cdiag = STORED ? L.A[4 * (size_t)ny * nx + g] : L.c[4];
-          val = resid_val<MASKED, STORED>(L, k, cdiag, xs[xr - 1][xq - 1], xs[xr - 1][xq], xs[xr - 1][xq + 1],
-                                          xs[xr][xq - 1], xs[xr][xq], xs[xr][xq + 1], xs[xr + 1][xq - 1],
-                                          xs[xr + 1][xq], xs[xr + 1][xq + 1], b[g]);
-        }
+      } else if (!MASKED || S.ms[r + 1][q + 1] != 0) {
+        size_t g = (size_t)j * nx + i;
+        Coefs<MASKED, STORED> k;
+        if (MASKED || STORED) k.load(L, g, MASKED ? &S.ms[r + 1][q + 1] : nullptr, RXW); else k = kc;
+        double cdiag = STORED ? L.A[4 * (size_t)ny * nx + g] : L.c[4];
+        val = resid_val<MASKED, STORED>(L, k, cdiag, x00, x01, x02, x10, x11, x12, x20, x21, x22, S.bs[r][q]);
       }
     }
-    rs[r][q] = val;
+    return val;
+  };
+  {
+    const int tx = t & 63, tg = t >> 6;
+    const int r0 = tg * 8 + (tg < 1 ? 0 : 1), nr = tg < 1 ? 9 : 8;   // 9,8,8,8 = 33 rows
+    const int xq = tx + 1;
+    double a0 = S.xs[r0][xq - 1], a1 = S.xs[r0][xq], a2 = S.xs[r0][xq + 1];
+    double m0 = S.xs[r0 + 1][xq - 1], m1 = S.xs[r0 + 1][xq], m2 = S.xs[r0 + 1][xq + 1];
+#pragma unroll 3
+    for (int r = r0; r < r0 + nr; r++) {
+      double h0 = S.xs[r + 2][xq - 1], h1 = S.xs[r + 2][xq], h2 = S.xs[r + 2][xq + 1];
+      S.rs[r][tx] = resid_point(r, tx, a0, a1, a2, m0, m1, m2, h0, h1, h2);
+      a0 = m0; a1 = m1; a2 = m2;
+      m0 = h0; m1 = h1; m2 = h2;
+    }
+    if (t < RH) {
+      int r = t, q = RW - 1, xr = r + 1, xq2 = q + 1;
+      S.rs[r][q] = resid_point(r, q, S.xs[xr - 1][xq2 - 1], S.xs[xr - 1][xq2], S.xs[xr - 1][xq2 + 1],
+                               S.xs[xr][xq2 - 1], S.xs[xr][xq2], S.xs[xr][xq2 + 1], S.xs[xr + 1][xq2 - 1],
+                               S.xs[xr + 1][xq2], S.xs[xr + 1][xq2 + 1]);
+    }
   }
   __syncthreads();
+  // ---- full-weighting restriction of the residual tile, halo images stored on rim tiles
+  const bool rim = (cj0 < 2 * NH) || (ci0 < 2 * NH) || (cj0 + RTY > nyc - 2 * NH) || (ci0 + RTX > nxc - 2 * NH);
+#pragma unroll
   for (int p = t; p < RTY * RTX; p += NT) {
     int r = p / RTX, q = p % RTX;
     int j = cj0 + r, i = ci0 + q;
@@ -327,12 +409,13 @@ k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restric
     double val = 0.;
     if (!MASKED || mskc[g] != 0) {
       int fr = 2 * r + 1, fq = 2 * q + 1;  // centre in the residual tile
-      val = 0.25 * rs[fr][fq] +
-            0.125 * (((rs[fr][fq - 1] + rs[fr][fq + 1]) + rs[fr - 1][fq]) + rs[fr + 1][fq]) +
-            0.0625 * (((rs[fr - 1][fq - 1] + rs[fr - 1][fq + 1]) + rs[fr + 1][fq - 1]) + rs[fr + 1][fq + 1]);
+      val = 0.25 * S.rs[fr][fq] +
+            0.125 * (((S.rs[fr][fq - 1] + S.rs[fr][fq + 1]) + S.rs[fr - 1][fq]) + S.rs[fr + 1][fq]) +
+            0.0625 * (((S.rs[fr - 1][fq - 1] + S.rs[fr - 1][fq + 1]) + S.rs[fr + 1][fq - 1]) + S.rs[fr + 1][fq + 1]);
     }
     bc[g] = val;
-    f2d::for_each_halo_image(j, i, nyc, nxc, NH, [&](int jj, int ii) { bc[(size_t)jj * nxc + ii] = val; });
+    if (rim)
+      f2d::for_each_halo_image(j, i, nyc, nxc, NH, [&](int jj, int ii) { bc[(size_t)jj * nxc + ii] = val; });
   }
 }
 

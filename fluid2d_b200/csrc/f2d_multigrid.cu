@@ -312,8 +312,16 @@ cudaError_t set_smem_input() {
   if (e == cudaSuccess) e = set_smem_one<true, true, I>();
   return e;
 }
+template <bool M, bool St>
+cudaError_t set_smem_resid() {
+  return cudaFuncSetAttribute(fused::k_resid_restrict<M, St>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)sizeof(fused::ResidSmem));
+}
 cudaError_t set_smem_all() {
   cudaError_t e = set_smem_input<0>();
+  if (e == cudaSuccess) e = set_smem_resid<false, false>();
+  if (e == cudaSuccess) e = set_smem_resid<true, false>();
+  if (e == cudaSuccess) e = set_smem_resid<true, true>();
   if (e == cudaSuccess) e = set_smem_input<1>();
   if (e == cudaSuccess) e = set_smem_input<2>();
   if (e == cudaSuccess) e = set_smem_input<3>();
@@ -352,10 +360,11 @@ int op_resid_restrict(f2d_mg *mg, int lev, const double *x, const double *b, dou
   Level &c = mg->L[lev + 1];
   fused::LevelK k = level_k(mg, lev);
   dim3 grid(cdiv(c.nx - 2 * NH, fused::RTX), cdiv(c.ny - 2 * NH, fused::RTY));
+  size_t sm = sizeof(fused::ResidSmem);
   switch (l.mode) {
-    case 1: fused::k_resid_restrict<false, false><<<grid, fused::NT, 0, s>>>(k, x, b, bc, c.msk, c.ny, c.nx); break;
-    case 2: fused::k_resid_restrict<true, false><<<grid, fused::NT, 0, s>>>(k, x, b, bc, c.msk, c.ny, c.nx); break;
-    default: fused::k_resid_restrict<true, true><<<grid, fused::NT, 0, s>>>(k, x, b, bc, c.msk, c.ny, c.nx); break;
+    case 1: fused::k_resid_restrict<false, false><<<grid, fused::NT, sm, s>>>(k, x, b, bc, c.msk, c.ny, c.nx); break;
+    case 2: fused::k_resid_restrict<true, false><<<grid, fused::NT, sm, s>>>(k, x, b, bc, c.msk, c.ny, c.nx); break;
+    default: fused::k_resid_restrict<true, true><<<grid, fused::NT, sm, s>>>(k, x, b, bc, c.msk, c.ny, c.nx); break;
   }
   F2D_LAUNCHED();
   return F2D_OK;

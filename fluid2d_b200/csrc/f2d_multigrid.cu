@@ -13,6 +13,7 @@
 
 #include "f2d_common.cuh"
 #include "f2d_mg_fused.cuh"
+#include "f2d_mg_tail.cuh"
 
 using namespace f2d;
 
@@ -39,6 +40,9 @@ struct f2d_mg {
   double *hscal = nullptr;    // pinned host mirror [4]
   cudaStream_t cap = nullptr; // capture stream for CUDA graphs
   bool graphs = true;
+  int tail0 = -1;             // first level of the shared-memory tail (-1: no tail kernel)
+  bool tail_const = false;    // every tail level is in the constant-stencil class
+  size_t tail_smem = 0;
   struct G { cudaGraphExec_t exec; long long kernels; };
   std::map<std::tuple<int, int, const void *, const void *>, G> cache;
 };
@@ -398,24 +402,57 @@ int coarsest_enqueue(f2d_mg *mg, double *X, const double *B, cudaStream_t s) {
   return F2D_OK;
 }
 
+// one launch of the shared-memory tail: program 0/1 = V-cycle (x = 0 / x = x_in first),
+// 2 = F-cycle of the levels tail0..last; rhs b_in, result x_out (both of level tail0)
+int tail_launch(f2d_mg *mg, int program, const double *b_in, const double *x_in, double *x_out, cudaStream_t s) {
+  tail::Params P;
+  int n = (int)mg->L.size() - mg->tail0;
+  P.nlev = n;
+  int off = 0;
+  for (int k = 0; k < n; k++) {
+    P.lv[k] = level_k(mg, mg->tail0 + k);
+    P.off[k] = off;
+    off += mg->L[mg->tail0 + k].ny * mg->L[mg->tail0 + k].nx;
+  }
+  P.total = off;
+  P.ndeepest = mg->ndeepest;
+  P.b_in = b_in;
+  P.x_in = x_in;
+  P.x_out = x_out;
+  if (mg->tail_const)
+    tail::k_mg_tail<false, false><<<1, tail::NT, mg->tail_smem, s>>>(P, program);
+  else
+    tail::k_mg_tail<true, true><<<1, tail::NT, mg->tail_smem, s>>>(P, program);
+  F2D_LAUNCHED();
+  return F2D_OK;
+}
+
 // hierarchy.py:98-127 with npre = npost = 1; x0/b0 stand for self.x[lev1], self.b[lev1].
 // Going down, the pre-smoothed field of a level lives in its scratch t; coming up,
 // interpolation, correction and post-smoothing are one kernel that writes x again.
+// Levels >= tail0 are done by one launch of the shared-memory tail kernel.
 // first_input: 0 = start from x0 as it is; 2 = x0 := I(x[lev1+1]) first (the F-cycle's
 // coarsetofine, hierarchy.py:145-146, fused into the pre-smoothing).
 int vcycle_enqueue(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s, int first_input = 0) {
   int last = (int)mg->L.size() - 1;
   auto X = [&](int lev) { return lev == lev1 ? x0 : mg->L[lev].x; };
   auto B = [&](int lev) { return lev == lev1 ? b0 : mg->L[lev].b; };
+  const int t0 = mg->tail0;
+  if (t0 >= 0 && lev1 == t0 && first_input == 0) return tail_launch(mg, 1, b0, x0, x0, s);
+  const bool use_tail = t0 >= 0 && lev1 < t0;
+  const int bottom = use_tail ? t0 : last;   // first level NOT handled by the big kernels
   if (lev1 == last) return coarsest_enqueue(mg, X(last), B(last), s);
-  for (int lev = lev1; lev < last; lev++) {
+  for (int lev = lev1; lev < bottom; lev++) {
     Level &l = mg->L[lev];
     int input = lev > lev1 ? 1 : first_input;
     TRY(smooth2(mg, lev, input, X(lev), B(lev), l.t, input == 2 ? X(lev + 1) : nullptr, s));
     TRY(op_resid_restrict(mg, lev, l.t, B(lev), B(lev + 1), s));
   }
-  TRY(coarsest_enqueue(mg, X(last), B(last), s));
-  for (int lev = last - 1; lev >= lev1; lev--)
+  if (use_tail)
+    TRY(tail_launch(mg, 0, B(t0), nullptr, X(t0), s));
+  else
+    TRY(coarsest_enqueue(mg, X(last), B(last), s));
+  for (int lev = bottom - 1; lev >= lev1; lev--)
     TRY(smooth2(mg, lev, 3, mg->L[lev].t, B(lev), X(lev), X(lev + 1), s));
   return F2D_OK;
 }
@@ -425,6 +462,14 @@ int fcycle_enqueue(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s)
   int last = (int)mg->L.size() - 1;
   auto X = [&](int lev) { return lev == lev1 ? x0 : mg->L[lev].x; };
   auto B = [&](int lev) { return lev == lev1 ? b0 : mg->L[lev].b; };
+  const int t0 = mg->tail0;
+  if (t0 >= 0 && lev1 <= t0) {
+    for (int lev = lev1; lev < t0; lev++) TRY(op_restrict(mg, lev, B(lev), B(lev + 1), s));
+    TRY(tail_launch(mg, 2, B(t0), nullptr, X(t0), s));
+    for (int lev = t0 - 1; lev >= lev1; lev--)
+      for (int k = 0; k < mg->nvcyc; k++) TRY(vcycle_enqueue(mg, lev, X(lev), B(lev), s, k == 0 ? 2 : 0));
+    return F2D_OK;
+  }
   for (int lev = lev1; lev < last; lev++) TRY(op_restrict(mg, lev, B(lev), B(lev + 1), s));
   TRY(coarsest_enqueue(mg, X(last), B(last), s));
   for (int lev = last - 1; lev >= lev1; lev--)
@@ -618,6 +663,31 @@ extern "C" int f2d_mg_create(f2d_mg_t **out, const double *cornermask, int ny, i
   if (const char *force = getenv("F2D_MG_FORCE_STORED"))
     if (force[0] == '1')
       for (auto &l : mg->L) l.mode = 0;
+  // shared-memory tail: the deepest levels whose interior is at most 64 wide
+  {
+    int t0 = (int)mg->L.size();
+    size_t cells = 0;
+    while (t0 > 0) {
+      Level &l = mg->L[t0 - 1];
+      if (l.ny - 2 * NH > tail::MAXN || l.nx - 2 * NH > tail::MAXN) break;
+      if ((int)mg->L.size() - (t0 - 1) > tail::MAXL) break;
+      if (3 * (cells + l.n()) * sizeof(double) > 220 * 1024) break;
+      cells += l.n();
+      t0--;
+    }
+    const char *notail = getenv("F2D_MG_NO_TAIL");
+    if (t0 < (int)mg->L.size() && !(notail && notail[0] == '1')) {
+      mg->tail0 = t0;
+      mg->tail_smem = 3 * cells * sizeof(double);
+      mg->tail_const = true;
+      for (size_t lev = t0; lev < mg->L.size(); lev++)
+        if (mg->L[lev].mode != 1) mg->tail_const = false;
+      MGC(cudaFuncSetAttribute(tail::k_mg_tail<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)mg->tail_smem));
+      MGC(cudaFuncSetAttribute(tail::k_mg_tail<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)mg->tail_smem));
+    }
+  }
   MGC(cudaStreamSynchronize(s));
   MGC(cudaGetLastError());
 #undef MGC

@@ -43,6 +43,17 @@ class Euler(object):
         self.ope = Operators(param, grid)
         self.tscheme = Timescheme(param, self.var.dstate)
         self.tscheme.set(self.dynamics, self.timestepping)
+        if not (self.forcing or self.customized):
+            # Fields whose Runge-Kutta combination can be skipped without changing anything:
+            #  - 'source' (and tauw/wshear) have identically zero tendencies;
+            #  - the intermediate psi is never read (dynamics reads the tracers, u and v);
+            #  - the final u, v are overwritten by the inversions that end the step
+            #    (their outermost ring, which computeorthogradient leaves alone, has zero
+            #    tendencies); the final psi is kept: it is the first guess of the full solve.
+            ix = self.var.index
+            tr = [ix(trac) for trac in param.tracer_list]
+            self.tscheme.fields_stage = tr+[ix('u'), ix('v')]
+            self.tscheme.fields_final = tr+[ix('psi')]
         r = rt()
         self.rt = r
         self.d_xr = r.to_device(self.xr, dtype=np.float64)

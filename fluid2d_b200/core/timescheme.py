@@ -35,6 +35,13 @@ class Timescheme(object):
         self.first = True
         self.second = True
         self.n = x.size
+        self.fieldsize = ny*nx
+        # optional: the fields a model needs combined at the intermediate stages / at the
+        # final update of RK3_SSP (None = the whole state, as the reference does).  A model
+        # may only list fewer fields when skipping the others cannot change any value it
+        # reads later (see Euler.__init__).
+        self.fields_stage = None
+        self.fields_final = None
         self.kstage = 0
         self.kforcing = 0
         self.forward = self._unset
@@ -61,6 +68,30 @@ class Timescheme(object):
     @staticmethod
     def _w(s):
         return s.all_ptr(True)
+
+    def _runs(self, fields):
+        """contiguous runs [(first field, number of fields)] of a sorted list of indices"""
+        runs = []
+        for k in sorted(set(fields)):
+            if runs and runs[-1][0]+runs[-1][1] == k:
+                runs[-1][1] += 1
+            else:
+                runs.append([k, 1])
+        return runs
+
+    @staticmethod
+    def _rk(s, k0, cnt):
+        p = s.rptr(k0)
+        for k in range(k0+1, k0+cnt):
+            s.rptr(k)
+        return p
+
+    @staticmethod
+    def _wk(s, k0, cnt):
+        p = s.wptr(k0)
+        for k in range(k0+1, k0+cnt):
+            s.wptr(k)
+        return p
 
     def _copy(self, dst, src):
         r = rt()
@@ -150,17 +181,25 @@ class Timescheme(object):
 
     def RK3_SSP(self, x, t, dt, **kwargs):
         r = rt()
+        lib = r.lib
+        nf = x.nvar
+        stage = self._runs(self.fields_stage if self.fields_stage is not None else range(nf))
+        final = self._runs(self.fields_final if self.fields_final is not None else range(nf))
+        fs = self.fieldsize
         self.kstage = 0
         self.rhs(x, t, self.dx0)
-        r.lib.ts_xpay(self._w(self.x), self._r(x), dt, self._r(self.dx0), self.n, r.stream)
+        for k0, c in stage:
+            lib.ts_xpay(self._wk(self.x, k0, c), self._rk(x, k0, c), dt, self._rk(self.dx0, k0, c), c*fs, r.stream)
         self.kstage = 1
         self.rhs(self.x, t+dt, self.dx1)
-        r.lib.ts_xpay2(self._w(self.x), self._r(x), 0.25*dt, self._r(self.dx0), self._r(self.dx1),
-                       self.n, r.stream)
+        for k0, c in stage:
+            lib.ts_xpay2(self._wk(self.x, k0, c), self._rk(x, k0, c), 0.25*dt, self._rk(self.dx0, k0, c),
+                         self._rk(self.dx1, k0, c), c*fs, r.stream)
         self.kstage = 2
         self.rhs(self.x, t+0.5*dt, self.dx2)
-        r.lib.ts_rk3ssp_final(self._w(x), dt/6., self._r(self.dx0), self._r(self.dx1), self._r(self.dx2),
-                              self.n, r.stream)
+        for k0, c in final:
+            lib.ts_rk3ssp_final(self._wk(x, k0, c), dt/6., self._rk(self.dx0, k0, c), self._rk(self.dx1, k0, c),
+                                self._rk(self.dx2, k0, c), c*fs, r.stream)
 
     def RK4_LS(self, x, t, dt, **kwargs):
         r = rt()

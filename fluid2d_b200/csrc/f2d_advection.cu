@@ -1,10 +1,11 @@
 // Flux-form advection: core/fortran_advection.f90 (adv_upwind :2-165, adv_centered
 // :169-284) and the flux-storing variants of core/fortran_fluxes.f90.
 //
-// One CTA computes a TX x TY tile of dq = -div(U q).  The q tile (halo 3) and the mask
-// tile are staged in shared memory; every east-face flux of the tile is computed once
-// and shared through shared memory, the north-face flux is carried in a register
-// while the thread marches up its column (the Fortran's fym).  The periodic halo fill
+// One CTA computes a TX x TY tile of dq = -div(U q).  The q tile (halo 3) and the u, v
+// tiles are staged in shared memory with asynchronous copies (LDGSTS); every east-face
+// flux of the tile is computed once (in place over the u tile) and shared through
+// shared memory, the north-face flux is carried in a register while a thread marches
+// up its strip of rows (the Fortran's fym).  The periodic halo fill
 // that Operators.rhs_adv performs next (operators.py:231) is fused: a thread that
 // owns a rim cell also stores its halo images.
 //
@@ -17,8 +18,9 @@ using namespace f2d;
 namespace {
 
 constexpr int NH = 3;
-constexpr int TX = 128;
-constexpr int TY = 16;
+constexpr int TX = 64;    // outputs per tile in x
+constexpr int TY = 32;    // outputs per tile in y
+constexpr int NT = 256;   // threads per CTA
 constexpr int SW = TX + 2 * NH;  // shared tile width
 constexpr int SH = TY + 2 * NH;
 
@@ -99,90 +101,138 @@ __device__ __forceinline__ double face_flux(const AdvC &k, double vel, const dou
                                    m0, mp1, mp2, mp3);
 }
 
-template <bool UPW, int ORDER, bool MASKED, bool FLX>
-__global__ void __launch_bounds__(TX)
+// 8-byte asynchronous global->shared copy (LDGSTS); !pred zero-fills the destination
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem, bool pred) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = pred ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+struct AdvSmem {
+  double q[SH][SW];       // tracer tile, halo 3
+  double u[TY][TX + 1];   // u on the east faces i0-1 .. i0+TX-1; overwritten by the x fluxes
+  double v[TY + 1][TX];   // v on the north faces of rows j0-1 .. j0+TY-1
+  int8_t m[SH][SW];       // mask tile (MASKED only)
+};
+
+template <bool UPW, int ORDER, bool MASKED>
+__global__ void __launch_bounds__(NT)
 k_adv(const int8_t *__restrict__ msk, const double *__restrict__ q, double *__restrict__ dq,
       const double *__restrict__ u, const double *__restrict__ v, double *__restrict__ xflx,
       double *__restrict__ yflx, AdvC k, int ny, int nx, int fill) {
-  __shared__ double sq[SH][SW];
-  __shared__ double sfx[TY][TX + 1];
-  __shared__ int8_t sm[MASKED ? SH : 1][MASKED ? SW : 1];
-  const int tx = threadIdx.x;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  AdvSmem &S = *reinterpret_cast<AdvSmem *>(smem_raw);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int i0 = NH + blockIdx.x * TX;  // first output column of the tile
   const int j0 = NH + blockIdx.y * TY;
-  // stage q (and msk) rows j0-3 .. j0+TY+2, cols i0-3 .. i0+TX+2
-  for (int r = 0; r < SH; r++) {
+  // ---- stage q (halo 3), u, v with asynchronous copies: one tile row per warp and pass
+  for (int r = warp; r < SH; r += NT / 32) {
     int j = j0 - NH + r;
-    for (int cidx = tx; cidx < SW; cidx += TX) {
-      int i = i0 - NH + cidx;
-      bool in = (j < ny) && (i < nx);
-      sq[r][cidx] = in ? q[(size_t)j * nx + i] : 0.;
-      if (MASKED) sm[r][cidx] = in ? msk[(size_t)j * nx + i] : (int8_t)0;
+    const double *row = q + (size_t)j * nx + (i0 - NH);
+#pragma unroll
+    for (int c = lane; c < SW; c += 32) {
+      bool in = j < ny && (i0 - NH + c) < nx;
+      cp_async8(&S.q[r][c], in ? row + c : q, in);
+      if (MASKED) S.m[r][c] = in ? msk[(size_t)j * nx + i0 - NH + c] : (int8_t)0;
     }
   }
+  for (int r = warp; r < TY; r += NT / 32) {
+    int j = j0 + r;
+    const double *row = u + (size_t)j * nx + (i0 - 1);
+#pragma unroll
+    for (int c = lane; c < TX + 1; c += 32) {
+      bool in = j < ny && (i0 - 1 + c) < nx;
+      cp_async8(&S.u[r][c], in ? row + c : u, in);
+    }
+  }
+  for (int r = warp; r < TY + 1; r += NT / 32) {
+    int j = j0 - 1 + r;
+    const double *row = v + (size_t)j * nx + i0;
+#pragma unroll
+    for (int c = lane; c < TX; c += 32) {
+      bool in = j < ny && (i0 + c) < nx;
+      cp_async8(&S.v[r][c], in ? row + c : v, in);
+    }
+  }
+  cp_async_wait_all();
   __syncthreads();
+  const int tx = t & (TX - 1), tg = t >> 6;   // column, row group (TX == 64)
+  const int r0 = tg * (TY / 4);
   const int i = i0 + tx;
   const bool col_ok = i < nx - NH;
-  // east-face fluxes: thread tx -> face of column i (all rows); threads 0..TY-1 also
-  // compute the west face of the tile (column i0-1) for row tx
-  for (int r = 0; r < TY; r++) {
+  const bool flx = xflx != nullptr;
+  // ---- east-face fluxes, in place over the u tile: thread (tx,tg) -> face of column i for
+  // its rows; threads 0..TY-1 also take the west face of the tile (column i0-1) of row t
+#pragma unroll 2
+  for (int r = r0; r < r0 + TY / 4; r++) {
     int j = j0 + r;
     double f = 0.;
     if (col_ok && j < ny - NH)
-      f = face_flux<UPW, ORDER, MASKED>(k, u[(size_t)j * nx + i], &sq[r + NH][tx + NH], 1,
-                                        MASKED ? &sm[r + NH][tx + NH] : nullptr, 1);
-    sfx[r][tx + 1] = f;
+      f = face_flux<UPW, ORDER, MASKED>(k, S.u[r][tx + 1], &S.q[r + NH][tx + NH], 1,
+                                        MASKED ? &S.m[r + NH][tx + NH] : nullptr, 1);
+    S.u[r][tx + 1] = f;
   }
-  if (tx < TY) {
-    int j = j0 + tx;
+  if (t < TY) {
+    int j = j0 + t;
     double f = 0.;
     if (j < ny - NH)
-      f = face_flux<UPW, ORDER, MASKED>(k, u[(size_t)j * nx + (i0 - 1)], &sq[tx + NH][NH - 1], 1,
-                                        MASKED ? &sm[tx + NH][NH - 1] : nullptr, 1);
-    sfx[tx][0] = f;
-    if (FLX && blockIdx.x == 0 && j < ny - NH) xflx[(size_t)j * nx + (i0 - 1)] = f;
+      f = face_flux<UPW, ORDER, MASKED>(k, S.u[t][0], &S.q[t + NH][NH - 1], 1,
+                                        MASKED ? &S.m[t + NH][NH - 1] : nullptr, 1);
+    S.u[t][0] = f;
+    if (flx && blockIdx.x == 0 && j < ny - NH) xflx[(size_t)j * nx + (i0 - 1)] = f;
   }
   __syncthreads();
   if (!col_ok) return;
-  // north-face flux of the row below the tile, then march up
-  double fym = face_flux<UPW, ORDER, MASKED>(k, v[(size_t)(j0 - 1) * nx + i], &sq[NH - 1][tx + NH], SW,
-                                             MASKED ? &sm[NH - 1][tx + NH] : nullptr, SW);
-  if (FLX && blockIdx.y == 0) yflx[(size_t)(j0 - 1) * nx + i] = fym;
-#pragma unroll 4
-  for (int r = 0; r < TY; r++) {
+  // ---- north-face fluxes marching up the strip (the Fortran's fym), divergence, stores
+  const bool rim = fill && ((j0 < 2 * NH) || (i0 < 2 * NH) || (j0 + TY > ny - 2 * NH) || (i0 + TX > nx - 2 * NH));
+  if (j0 + r0 >= ny - NH) return;
+  double fym = face_flux<UPW, ORDER, MASKED>(k, S.v[r0][tx], &S.q[r0 + NH - 1][tx + NH], SW,
+                                             MASKED ? &S.m[r0 + NH - 1][tx + NH] : nullptr, SW);
+  if (flx && blockIdx.y == 0 && r0 == 0) yflx[(size_t)(j0 - 1) * nx + i] = fym;
+#pragma unroll 2
+  for (int r = r0; r < r0 + TY / 4; r++) {
     int j = j0 + r;
     if (j >= ny - NH) break;
     size_t c = (size_t)j * nx + i;
-    double fy = face_flux<UPW, ORDER, MASKED>(k, v[c], &sq[r + NH][tx + NH], SW,
-                                              MASKED ? &sm[r + NH][tx + NH] : nullptr, SW);
-    double fxe = sfx[r][tx + 1], fxw = sfx[r][tx];
+    double fy = face_flux<UPW, ORDER, MASKED>(k, S.v[r + 1][tx], &S.q[r + NH][tx + NH], SW,
+                                              MASKED ? &S.m[r + NH][tx + NH] : nullptr, SW);
+    double fxe = S.u[r][tx + 1], fxw = S.u[r][tx];
     double y = -k.zdx * (fxe - fxw) - k.zdy * (fy - fym);
     dq[c] = y;
-    if (FLX) {
+    if (flx) {
       xflx[c] = fxe;
       yflx[c] = fy;
     }
-    if (fill)
+    if (rim)
       for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { dq[(size_t)jj * nx + ii] = y; });
     fym = fy;
   }
+}
+
+template <bool UPW, int ORDER, bool MASKED>
+int launch_adv_m(const int8_t *msk, const double *q, double *dq, const double *u, const double *v,
+                 double *xflx, double *yflx, const AdvC &k, int ny, int nx, int fill, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    F2D_CUDA(cudaFuncSetAttribute(k_adv<UPW, ORDER, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(AdvSmem)));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(nx - 2 * NH, TX), cdiv(ny - 2 * NH, TY));
+  k_adv<UPW, ORDER, MASKED><<<grid, NT, sizeof(AdvSmem), s>>>(msk, q, dq, u, v, xflx, yflx, k, ny, nx, fill);
+  F2D_LAUNCHED();
+  return F2D_OK;
 }
 
 template <bool UPW, int ORDER>
 int launch_adv(const int8_t *msk, const double *q, double *dq, const double *u, const double *v,
                double *xflx, double *yflx, const AdvC &k, int ny, int nx, int fill, bool masked,
                cudaStream_t s) {
-  dim3 grid(cdiv(nx - 2 * NH, TX), cdiv(ny - 2 * NH, TY));
-  bool flx = xflx != nullptr;
-#define GO(M, F) k_adv<UPW, ORDER, M, F><<<grid, TX, 0, s>>>(msk, q, dq, u, v, xflx, yflx, k, ny, nx, fill)
-  if (masked) {
-    if (flx) GO(true, true); else GO(true, false);
-  } else {
-    if (flx) GO(false, true); else GO(false, false);
-  }
-#undef GO
-  F2D_LAUNCHED();
-  return F2D_OK;
+  if (masked) return launch_adv_m<UPW, ORDER, true>(msk, q, dq, u, v, xflx, yflx, k, ny, nx, fill, s);
+  return launch_adv_m<UPW, ORDER, false>(msk, q, dq, u, v, xflx, yflx, k, ny, nx, fill, s);
 }
 
 int adv_common(bool upw, const int8_t *msk, const double *q, double *dq, const double *u, const double *v,

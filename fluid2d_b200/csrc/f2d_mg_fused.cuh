@@ -130,7 +130,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
 template <bool MASKED, bool STORED, int INPUT>
 __global__ void __launch_bounds__(NT)
 k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b, double *__restrict__ xout,
-          const double *__restrict__ xc, const int8_t *__restrict__ mskc, int nxc, int nyc) {
+          const double *__restrict__ xc, const int8_t *__restrict__ mskc, int nxc, int nyc, double *acc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smooth2Smem &S = *reinterpret_cast<Smooth2Smem *>(smem_raw);
   const int ny = L.ny, nx = L.nx;
@@ -284,9 +284,19 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
           if (MASKED || STORED) k.load(L, (size_t)j * nx + i, MASKED ? &S.ms[r + 2][tx + 2] : nullptr, XW); else k = kc;
           val = jacobi_val<MASKED, STORED>(L, k, a0, a1, a2, m0, m1, m2, h0, h1, h2, S.bs[r + 1][yq]);
         }
-        xout[(size_t)j * nx + i] = val;
-        if (rim)
-          f2d::for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { xout[(size_t)jj * nx + ii] = val; });
+        if (acc) {
+          // solve(): `x += self.x[0]` (hierarchy.py:171) fused into the last kernel of the
+          // F-cycle: the correction is added to psi instead of being stored
+          acc[(size_t)j * nx + i] = acc[(size_t)j * nx + i] + val;
+          if (rim)
+            f2d::for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) {
+              acc[(size_t)jj * nx + ii] = acc[(size_t)jj * nx + ii] + val;
+            });
+        } else {
+          xout[(size_t)j * nx + i] = val;
+          if (rim)
+            f2d::for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { xout[(size_t)jj * nx + ii] = val; });
+        }
         a0 = m0; a1 = m1; a2 = m2;
         m0 = h0; m1 = h1; m2 = h2;
       }

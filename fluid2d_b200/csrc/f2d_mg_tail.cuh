@@ -30,6 +30,7 @@ struct Params {
   const double *b_in;         // global rhs of the finest tail level
   const double *x_in;         // global first guess (V program, xmode 0) or nullptr
   double *x_out;              // global result of the finest tail level
+  double *acc;                // if set: acc += result instead of storing it (solve(), hierarchy.py:171)
 };
 
 struct Ctx {
@@ -208,7 +209,10 @@ __global__ void __launch_bounds__(NT, 1) k_mg_tail(const __grid_constant__ Param
   } else {
     vcycle<MASKED, STORED>(P, X, B, T, 0);
   }
-  for (int p = threadIdx.x; p < n0; p += NT) P.x_out[p] = X[p];
+  if (P.acc)
+    for (int p = threadIdx.x; p < n0; p += NT) P.acc[p] = P.acc[p] + X[p];
+  else
+    for (int p = threadIdx.x; p < n0; p += NT) P.x_out[p] = X[p];
 }
 
 }  // namespace tail

@@ -44,7 +44,7 @@ struct f2d_mg {
   bool tail_const = false;    // every tail level is in the constant-stencil class
   size_t tail_smem = 0;
   struct G { cudaGraphExec_t exec; long long kernels; };
-  std::map<std::tuple<int, int, const void *, const void *>, G> cache;
+  std::map<std::tuple<int, int, const void *, const void *, const void *>, G> cache;
 };
 
 namespace {
@@ -254,6 +254,61 @@ __global__ void k_add_inplace(double *__restrict__ y, const double *__restrict__
     y[k] = y[k] + a[k];
 }
 
+// solve(): residual of the finest level + its squared norm in one pass
+// (hierarchy.py:159-162,172-174: g.residual(x, b, self.b[0]); g.norm(self.b[0])).
+// Block b sweeps rows b, b+RSB, ...; r = b - A x on the interior with its halo images;
+// the per-block sums of r^2 go to `partial` and are folded by k_fold_partials
+// (deterministic two-stage sum; r is 0 on solid corners, so the unmasked sum of r^2
+// equals computenorm's masked one).
+constexpr int RSB = 148 * 4, RST = 256;
+
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double sh[RST / 32];
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int k = 1; k < RST / 32; k++) v += sh[k];
+  return v;
+}
+
+template <bool MASKED, bool STORED>
+__global__ void __launch_bounds__(RST)
+k_resid_sumsq(fused::LevelK L, const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ r,
+              double *__restrict__ partial) {
+  const int ny = L.ny, nx = L.nx;
+  fused::Coefs<MASKED, STORED> kc;
+  if (!MASKED && !STORED) kc.load(L, 0, nullptr, 0);
+  double acc = 0.;
+  for (int j = NH + blockIdx.x; j <= ny - 1 - NH; j += gridDim.x) {
+    const bool rimrow = j < 2 * NH || j >= ny - 2 * NH;
+    for (int i = NH + threadIdx.x; i <= nx - 1 - NH; i += RST) {
+      size_t g = (size_t)j * nx + i;
+      double val = 0.;
+      if (!MASKED || L.msk[g] != 0) {
+        fused::Coefs<MASKED, STORED> k;
+        if (MASKED || STORED) k.load(L, g, MASKED ? L.msk + g : nullptr, nx); else k = kc;
+        double cdiag = STORED ? L.A[4 * (size_t)ny * nx + g] : L.c[4];
+        const double *p = x + g;
+        val = fused::resid_val<MASKED, STORED>(L, k, cdiag, p[-nx - 1], p[-nx], p[-nx + 1], p[-1], p[0], p[1],
+                                               p[nx - 1], p[nx], p[nx + 1], b[g]);
+      }
+      r[g] = val;
+      if (rimrow || i < 2 * NH || i >= nx - 2 * NH)
+        for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { r[(size_t)jj * nx + ii] = val; });
+      acc += val * val;
+    }
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+__global__ void __launch_bounds__(RST) k_fold_partials(const double *__restrict__ partial, int n, double *out) {
+  double acc = 0.;
+  for (int k = threadIdx.x; k < n; k += RST) acc += partial[k];
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) out[0] = acc;
+}
+
 inline int nblocks1d(size_t n) {
   long long b = (long long)((n + 255) / 256);
   return (int)(b > 148LL * 16 ? 148LL * 16 : (b < 1 ? 1 : b));
@@ -276,7 +331,7 @@ fused::LevelK level_k(f2d_mg *mg, int lev) {
 // fused double sweep: xout = S2(input), input = xin | 0 | I(xc) | xin + I(xc)
 template <int INPUT>
 int launch_smooth2(f2d_mg *mg, int lev, const double *xin, const double *b, double *xout, const double *xc,
-                   cudaStream_t s) {
+                   cudaStream_t s, double *acc) {
   Level &l = mg->L[lev];
   fused::LevelK k = level_k(mg, lev);
   dim3 grid(cdiv(l.nx - 2 * NH, fused::TX), cdiv(l.ny - 2 * NH, fused::TY));
@@ -288,20 +343,20 @@ int launch_smooth2(f2d_mg *mg, int lev, const double *xin, const double *b, doub
     mskc = c.msk; nxc = c.nx; nyc = c.ny;
   }
   switch (l.mode) {
-    case 1: fused::k_smooth2<false, false, INPUT><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc); break;
-    case 2: fused::k_smooth2<true, false, INPUT><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc); break;
-    default: fused::k_smooth2<true, true, INPUT><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc); break;
+    case 1: fused::k_smooth2<false, false, INPUT><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc, acc); break;
+    case 2: fused::k_smooth2<true, false, INPUT><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc, acc); break;
+    default: fused::k_smooth2<true, true, INPUT><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc, acc); break;
   }
   F2D_LAUNCHED();
   return F2D_OK;
 }
 int smooth2(f2d_mg *mg, int lev, int input, const double *xin, const double *b, double *xout, const double *xc,
-            cudaStream_t s) {
+            cudaStream_t s, double *acc = nullptr) {
   switch (input) {
-    case 0: return launch_smooth2<0>(mg, lev, xin, b, xout, xc, s);
-    case 1: return launch_smooth2<1>(mg, lev, xin, b, xout, xc, s);
-    case 2: return launch_smooth2<2>(mg, lev, xin, b, xout, xc, s);
-    default: return launch_smooth2<3>(mg, lev, xin, b, xout, xc, s);
+    case 0: return launch_smooth2<0>(mg, lev, xin, b, xout, xc, s, acc);
+    case 1: return launch_smooth2<1>(mg, lev, xin, b, xout, xc, s, acc);
+    case 2: return launch_smooth2<2>(mg, lev, xin, b, xout, xc, s, acc);
+    default: return launch_smooth2<3>(mg, lev, xin, b, xout, xc, s, acc);
   }
 }
 template <bool M, bool St, int I>
@@ -348,6 +403,21 @@ int op_residual(f2d_mg *mg, int lev, const double *x, const double *b, double *r
   Level &l = mg->L[lev];
   dim3 blk(32, 8);
   k_residual<<<grid2d(l.ny, l.nx, blk), blk, 0, s>>>(l.msk, l.A, x, b, r, l.ny, l.nx);
+  F2D_LAUNCHED();
+  return F2D_OK;
+}
+// residual of level 0 + sum of its squares -> out[0] (device)
+int op_resid_sumsq(f2d_mg *mg, const double *x, const double *b, double *r, double *out, cudaStream_t s) {
+  Level &l = mg->L[0];
+  fused::LevelK k = level_k(mg, 0);
+  int nb = l.ny - 2 * NH < RSB ? l.ny - 2 * NH : RSB;
+  switch (l.mode) {
+    case 1: k_resid_sumsq<false, false><<<nb, RST, 0, s>>>(k, x, b, r, mg->scratch); break;
+    case 2: k_resid_sumsq<true, false><<<nb, RST, 0, s>>>(k, x, b, r, mg->scratch); break;
+    default: k_resid_sumsq<true, true><<<nb, RST, 0, s>>>(k, x, b, r, mg->scratch); break;
+  }
+  F2D_LAUNCHED();
+  k_fold_partials<<<1, RST, 0, s>>>(mg->scratch, nb, out);
   F2D_LAUNCHED();
   return F2D_OK;
 }
@@ -404,7 +474,8 @@ int coarsest_enqueue(f2d_mg *mg, double *X, const double *B, cudaStream_t s) {
 
 // one launch of the shared-memory tail: program 0/1 = V-cycle (x = 0 / x = x_in first),
 // 2 = F-cycle of the levels tail0..last; rhs b_in, result x_out (both of level tail0)
-int tail_launch(f2d_mg *mg, int program, const double *b_in, const double *x_in, double *x_out, cudaStream_t s) {
+int tail_launch(f2d_mg *mg, int program, const double *b_in, const double *x_in, double *x_out, cudaStream_t s,
+                double *acc = nullptr) {
   tail::Params P;
   int n = (int)mg->L.size() - mg->tail0;
   P.nlev = n;
@@ -419,6 +490,7 @@ int tail_launch(f2d_mg *mg, int program, const double *b_in, const double *x_in,
   P.b_in = b_in;
   P.x_in = x_in;
   P.x_out = x_out;
+  P.acc = acc;
   if (mg->tail_const)
     tail::k_mg_tail<false, false><<<1, tail::NT, mg->tail_smem, s>>>(P, program);
   else
@@ -433,7 +505,8 @@ int tail_launch(f2d_mg *mg, int program, const double *b_in, const double *x_in,
 // Levels >= tail0 are done by one launch of the shared-memory tail kernel.
 // first_input: 0 = start from x0 as it is; 2 = x0 := I(x[lev1+1]) first (the F-cycle's
 // coarsetofine, hierarchy.py:145-146, fused into the pre-smoothing).
-int vcycle_enqueue(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s, int first_input = 0) {
+int vcycle_enqueue(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s, int first_input = 0,
+                   double *acc = nullptr) {
   int last = (int)mg->L.size() - 1;
   auto X = [&](int lev) { return lev == lev1 ? x0 : mg->L[lev].x; };
   auto B = [&](int lev) { return lev == lev1 ? b0 : mg->L[lev].b; };
@@ -453,42 +526,48 @@ int vcycle_enqueue(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s,
   else
     TRY(coarsest_enqueue(mg, X(last), B(last), s));
   for (int lev = bottom - 1; lev >= lev1; lev--)
-    TRY(smooth2(mg, lev, 3, mg->L[lev].t, B(lev), X(lev), X(lev + 1), s));
+    TRY(smooth2(mg, lev, 3, mg->L[lev].t, B(lev), X(lev), X(lev + 1), s, lev == lev1 ? acc : nullptr));
   return F2D_OK;
 }
 
 // hierarchy.py:131-151
-int fcycle_enqueue(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s) {
+// acc != nullptr (only with lev1 below the coarsest level): the result is added to acc
+// instead of being stored in x0
+int fcycle_enqueue(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s, double *acc = nullptr) {
   int last = (int)mg->L.size() - 1;
   auto X = [&](int lev) { return lev == lev1 ? x0 : mg->L[lev].x; };
   auto B = [&](int lev) { return lev == lev1 ? b0 : mg->L[lev].b; };
   const int t0 = mg->tail0;
   if (t0 >= 0 && lev1 <= t0) {
     for (int lev = lev1; lev < t0; lev++) TRY(op_restrict(mg, lev, B(lev), B(lev + 1), s));
-    TRY(tail_launch(mg, 2, B(t0), nullptr, X(t0), s));
+    TRY(tail_launch(mg, 2, B(t0), nullptr, X(t0), s, lev1 == t0 ? acc : nullptr));
     for (int lev = t0 - 1; lev >= lev1; lev--)
-      for (int k = 0; k < mg->nvcyc; k++) TRY(vcycle_enqueue(mg, lev, X(lev), B(lev), s, k == 0 ? 2 : 0));
+      for (int k = 0; k < mg->nvcyc; k++)
+        TRY(vcycle_enqueue(mg, lev, X(lev), B(lev), s, k == 0 ? 2 : 0,
+                           (lev == lev1 && k == mg->nvcyc - 1) ? acc : nullptr));
     return F2D_OK;
   }
   for (int lev = lev1; lev < last; lev++) TRY(op_restrict(mg, lev, B(lev), B(lev + 1), s));
   TRY(coarsest_enqueue(mg, X(last), B(last), s));
   for (int lev = last - 1; lev >= lev1; lev--)
-    for (int k = 0; k < mg->nvcyc; k++) TRY(vcycle_enqueue(mg, lev, X(lev), B(lev), s, k == 0 ? 2 : 0));
+    for (int k = 0; k < mg->nvcyc; k++)
+      TRY(vcycle_enqueue(mg, lev, X(lev), B(lev), s, k == 0 ? 2 : 0,
+                         (lev == lev1 && k == mg->nvcyc - 1) ? acc : nullptr));
   return F2D_OK;
 }
 
 // run `kind` (0 two V-cycles from level 0, 1 F-cycle, 2 single V-cycle) through a cached graph
-int run_cycle(f2d_mg *mg, int kind, int lev1, double *x0, double *b0, cudaStream_t s) {
+int run_cycle(f2d_mg *mg, int kind, int lev1, double *x0, double *b0, cudaStream_t s, double *acc = nullptr) {
   auto enqueue = [&](cudaStream_t st) -> int {
     if (kind == 0) {
       TRY(vcycle_enqueue(mg, 0, x0, b0, st));
       return vcycle_enqueue(mg, 0, x0, b0, st);
     }
-    if (kind == 1) return fcycle_enqueue(mg, lev1, x0, b0, st);
+    if (kind == 1) return fcycle_enqueue(mg, lev1, x0, b0, st, acc);
     return vcycle_enqueue(mg, lev1, x0, b0, st);
   };
   if (!mg->graphs) return enqueue(s);
-  auto key = std::make_tuple(kind, lev1, (const void *)x0, (const void *)b0);
+  auto key = std::make_tuple(kind, lev1, (const void *)x0, (const void *)b0, (const void *)acc);
   auto it = mg->cache.find(key);
   if (it == mg->cache.end()) {
     long long before = g_launches;
@@ -785,9 +864,8 @@ extern "C" int f2d_mg_solve(f2d_mg_t *mg, double *psi, const double *rhs, double
   if (!mg || !psi || !rhs) return fail(F2D_ERR_ARG, "mg_solve: null");
   cudaStream_t s = S(stream);
   Level &l = mg->L[0];
-  TRY(op_residual(mg, 0, psi, rhs, l.b, s));
   TRY(f2d_computenorm(l.msk, rhs, NH, l.ny, l.nx, mg->dscal, mg->scratch, stream));
-  TRY(f2d_computenorm(l.msk, l.b, NH, l.ny, l.nx, mg->dscal + 1, mg->scratch, stream));
+  TRY(op_resid_sumsq(mg, psi, rhs, l.b, mg->dscal + 1, s));
   TRY(read_scalars(mg, 2, s));
   double normb = sqrt(mg->hscal[0]);
   int nite = 0;
@@ -796,12 +874,14 @@ extern "C" int f2d_mg_solve(f2d_mg_t *mg, double *psi, const double *rhs, double
     double res0 = sqrt(mg->hscal[1]) / normb;
     res = res0;
     int ndiv = 0;
+    const bool fuse_add = mg->L.size() > 1;   // `x += self.x[0]` done by the F-cycle's last kernel
     while (nite < maxite && res0 > tol) {
-      TRY(run_cycle(mg, 1, 0, l.x, l.b, s));
-      k_add_inplace<<<nblocks1d(l.n()), 256, 0, s>>>(psi, l.x, l.n());
-      F2D_LAUNCHED();
-      TRY(op_residual(mg, 0, psi, rhs, l.b, s));
-      TRY(f2d_computenorm(l.msk, l.b, NH, l.ny, l.nx, mg->dscal + 1, mg->scratch, stream));
+      TRY(run_cycle(mg, 1, 0, l.x, l.b, s, fuse_add ? psi : nullptr));
+      if (!fuse_add) {
+        k_add_inplace<<<nblocks1d(l.n()), 256, 0, s>>>(psi, l.x, l.n());
+        F2D_LAUNCHED();
+      }
+      TRY(op_resid_sumsq(mg, psi, rhs, l.b, mg->dscal + 1, s));
       TRY(read_scalars(mg, 2, s));
       res = sqrt(mg->hscal[1]) / normb;
       double conv = res0 / res;
@@ -840,7 +920,8 @@ extern "C" int f2d_invert_vorticity(f2d_mg_t *mg, const int8_t *msk, const int8_
     if (nite) *nite = 1;
     if (res) *res = 0.;
   }
+  if (!psi_island) return f2d_mask_orthogradient(msk, mskp, psi, dx, dy, nh, u, v, l.ny, l.nx, stream);
   TRY(f2d_mul_mask(psi, mskp, n, stream));
-  if (psi_island) TRY(f2d_add_scaled(psi, 1., psi_island, n, stream));
+  TRY(f2d_add_scaled(psi, 1., psi_island, n, stream));
   return f2d_orthogradient(msk, psi, dx, dy, nh, u, v, l.ny, l.nx, stream);
 }

@@ -131,6 +131,34 @@ extern "C" int f2d_orthogradient(const int8_t *msk, const double *psi, double dx
   return F2D_OK;
 }
 
+// psi *= mskp, then computeorthogradient, in one pass (operators.py:481,493 without
+// islands).  A thread needs the masked psi of its south and west neighbours; it forms
+// them itself from psi and mskp.  psi is updated in place: a neighbour may already have
+// been masked when it is read, which is harmless because masking is idempotent
+// (x*1 = x, x*0 = +-0) -- this is why the island case (psi += psi_island) is not fused.
+__global__ void k_mask_orthogradient(const int8_t *__restrict__ msk, const int8_t *__restrict__ mskp,
+                                     double *psi, double zdx, double zdy, double *__restrict__ u,
+                                     double *__restrict__ v, int ny, int nx) {
+  IJ();
+  double p = __dmul_rn(psi[c], (double)mskp[c]);
+  psi[c] = p;
+  if (j < 1 || j > ny - 2 || i < 1 || i > nx - 2) return;
+  int m0 = msk[c];
+  double ps = __dmul_rn(psi[c - nx], (double)mskp[c - nx]);
+  double pw = __dmul_rn(psi[c - 1], (double)mskp[c - 1]);
+  u[c] = (m0 + msk[c + 1] == 2) ? zdy * (ps - p) : 0.;
+  v[c] = (m0 + msk[c + nx] == 2) ? zdx * (p - pw) : 0.;
+}
+extern "C" int f2d_mask_orthogradient(const int8_t *msk, const int8_t *mskp, double *psi, double dx, double dy,
+                                      int nh, double *u, double *v, int ny, int nx, f2d_stream_t s) {
+  (void)nh;
+  if (!msk || !mskp || !psi || !u || !v || ny < 3 || nx < 3) return fail(F2D_ERR_ARG, "mask_orthogradient: bad args");
+  dim3 b(32, 8);
+  k_mask_orthogradient<<<grid2d(ny, nx, b), b, 0, S(s)>>>(msk, mskp, psi, 1. / dx, 1. / dy, u, v, ny, nx);
+  F2D_LAUNCHED();
+  return F2D_OK;
+}
+
 // add_diffusion: fortran_operators.f90:125-156, rows/cols 2..m-1 where msk==1
 __global__ void k_add_diffusion(const int8_t *__restrict__ msk, const double *__restrict__ t,
                                 double coef, double *__restrict__ d, int ny, int nx) {

@@ -83,6 +83,10 @@ int f2d_cornertocell(const double *xp, double *xr, int ny, int nx, f2d_stream_t 
 /* :2-39 computeorthogradient(msk,psi,dx,dy,nh,u,v) */
 int f2d_orthogradient(const int8_t *msk, const double *psi, double dx, double dy, int nh,
                       double *u, double *v, int ny, int nx, f2d_stream_t stream);
+/* psi = psi*mskp followed by computeorthogradient in one pass (operators.py:481,493) */
+int f2d_mask_orthogradient(const int8_t *msk, const int8_t *mskp, double *psi, double dx,
+                           double dy, int nh, double *u, double *v, int ny, int nx,
+                           f2d_stream_t stream);
 /* :125-156 add_diffusion(msk,trac,dx,nh,Kdiff,dtrac) (+ optional halo fill,
  * operators.py:300) */
 int f2d_add_diffusion(const int8_t *msk, const double *trac, double dx, int nh,

@@ -116,14 +116,86 @@ struct Smooth2Smem {
   int8_t cm[CH][CW];
 };
 
-// 8-byte asynchronous global->shared copy (LDGSTS); !pred zero-fills the destination
-__device__ __forceinline__ void cp_async8(void *smem, const void *gmem, bool pred) {
-  unsigned d = (unsigned)__cvta_generic_to_shared(smem);
-  int sz = pred ? 8 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gmem), "r"(sz) : "memory");
+// ---- asynchronous tile loader -----------------------------------------------------
+// Copies a ROWS x COLS tile whose origin is `src` (row pitch nx doubles) into `dst` (row
+// pitch LD doubles): one tile row per warp and pass, 8 bytes per LDGSTS, every address a
+// constant offset from two per-thread bases.  FULL: all elements are inside the array (no
+// predicates); otherwise rows >= vrows / columns >= vcols are zero-filled.
+template <int ROWS, int COLS, int LD, bool FULL>
+__device__ __forceinline__ void load_tile(double *dst, const double *src, int nx, int vrows, int vcols) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = NT / 32;
+  constexpr int NK = (ROWS + NW - 1) / NW, NC = (COLS + 31) / 32;
+  const double *row = src + (size_t)warp * nx + lane;
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst + warp * LD + lane);
+  const size_t rstep = (size_t)NW * nx;
+#pragma unroll
+  for (int k = 0; k < NK; k++) {
+    if ((k + 1) * NW <= ROWS || warp + k * NW < ROWS) {
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        if ((c + 1) * 32 <= COLS || lane + c * 32 < COLS) {
+          const unsigned da = d + (unsigned)((k * NW * LD + c * 32) * 8);
+          if (FULL) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(da), "l"(row + c * 32) : "memory");
+          } else {
+            bool in = (warp + k * NW < vrows) && (lane + c * 32 < vcols);
+            int sz = in ? 8 : 0;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(da), "l"(in ? row + c * 32 : src), "r"(sz)
+                         : "memory");
+          }
+        }
+      }
+    }
+    row += rstep;
+  }
+}
+template <int ROWS, int COLS, int LD>
+__device__ __forceinline__ void load_tile_i8(int8_t *dst, const int8_t *src, int nx, int vrows, int vcols) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < ROWS; r += NT / 32)
+    for (int c = lane; c < COLS; c += 32)
+      dst[r * LD + c] = (r < vrows && c < vcols) ? src[(size_t)r * nx + c] : (int8_t)0;
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// one column strip of a Jacobi sweep: `sp` (pitch SLD) points at the window centre of the
+// first point in the source tile, `bp` (pitch BLD) at its b, `mp` (pitch MLD) at its mask;
+// the 3x3 window is carried in registers, so each point costs three shared loads.  GUARD:
+// per-point range test [lo, n-1-lo] (rim tiles); the fast path has none.  out(k, val)
+// consumes row k (called for in-range points only).
+template <bool MASKED, bool STORED, bool ZERO, bool GUARD, int NR, int SLD, int BLD, int MLD, class OUT>
+__device__ __forceinline__ void jacobi_strip(const LevelK &L, const Coefs<MASKED, STORED> &kc, const double *sp,
+                                             const double *bp, const int8_t *mp, int nr, int j, int i, int lo,
+                                             OUT out) {
+  const int ny = L.ny, nx = L.nx;
+  const size_t g = (size_t)j * nx + i;
+  double a0 = 0., a1 = 0., a2 = 0., m0 = 0., m1 = 0., m2 = 0.;
+  if (!ZERO) {
+    a0 = sp[-SLD - 1]; a1 = sp[-SLD]; a2 = sp[-SLD + 1];
+    m0 = sp[-1]; m1 = sp[0]; m2 = sp[1];
+  }
+#pragma unroll
+  for (int k = 0; k < NR; k++) {
+    if (k < nr) {
+      double h0 = 0., h1 = 0., h2 = 0.;
+      if (!ZERO) { h0 = sp[(k + 1) * SLD - 1]; h1 = sp[(k + 1) * SLD]; h2 = sp[(k + 1) * SLD + 1]; }
+      const bool ok = !GUARD || (j + k >= lo && j + k <= ny - 1 - lo && i >= lo && i <= nx - 1 - lo);
+      if (ok) {
+        double val = 0.;
+        if (!MASKED || mp[k * MLD] != 0) {
+          Coefs<MASKED, STORED> kk;
+          if (MASKED || STORED) kk.load(L, g + (size_t)k * nx, MASKED ? mp + k * MLD : nullptr, MLD); else kk = kc;
+          val = jacobi_val<MASKED, STORED>(L, kk, a0, a1, a2, m0, m1, m2, h0, h1, h2, bp[k * BLD]);
+        }
+        out(k, val);
+      }
+      a0 = m0; a1 = m1; a2 = m2;
+      m0 = h0; m1 = h1; m2 = h2;
+    }
+  }
 }
 
 // INPUT: 0 xin, 1 zero, 2 I(xc), 3 xin + I(xc)
@@ -138,169 +210,121 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
   const int i0 = NH + blockIdx.x * TX, j0 = NH + blockIdx.y * TY;
   constexpr bool INTERP = INPUT >= 2;
   constexpr bool HAVE_X = (INPUT == 0 || INPUT == 3);
+  constexpr bool ZERO = INPUT == 1;
   const int cj0 = ((j0 - 2) >> 1) + 1, ci0 = ((i0 - 2) >> 1) + 1;
-  // ---- stage everything with asynchronous copies: one tile row per warp and pass
-  if (HAVE_X) {
-    for (int r = warp; r < XH; r += NT / 32) {
-      int j = j0 - 2 + r;
-      const double *row = xin + (size_t)j * nx + (i0 - 2);
-#pragma unroll
-      for (int q = lane; q < XW; q += 32) {
-        bool in = j < ny && (i0 - 2 + q) < nx;
-        cp_async8(&S.xs[r][q], in ? row + q : xin, in);
-      }
+  // inner tile: every point of the sweep-1 ring and of the output tile is a valid target
+  const bool inner = (j0 + TY <= ny - 3) && (i0 + TX <= nx - 3);
+  // ---- stage the tiles with asynchronous copies
+  {
+    const int vr = ny - (j0 - 2), vc = nx - (i0 - 2);
+    if (HAVE_X) {
+      const double *src = xin + (size_t)(j0 - 2) * nx + (i0 - 2);
+      if (inner) load_tile<XH, XW, XW, true>(&S.xs[0][0], src, nx, 0, 0);
+      else load_tile<XH, XW, XW, false>(&S.xs[0][0], src, nx, vr, vc);
     }
-  }
-  for (int r = warp; r < YH; r += NT / 32) {
-    int j = j0 - 1 + r;
-    const double *row = b + (size_t)j * nx + (i0 - 1);
-#pragma unroll
-    for (int q = lane; q < YW; q += 32) {
-      bool in = j < ny && (i0 - 1 + q) < nx;
-      cp_async8(&S.bs[r][q], in ? row + q : b, in);
+    const double *bsrc = b + (size_t)(j0 - 1) * nx + (i0 - 1);
+    if (inner) load_tile<YH, YW, YW, true>(&S.bs[0][0], bsrc, nx, 0, 0);
+    else load_tile<YH, YW, YW, false>(&S.bs[0][0], bsrc, nx, vr - 1, vc - 1);
+    if (INTERP) {
+      load_tile<CH, CW, CW, false>(&S.cs[0][0], xc + (size_t)cj0 * nxc + ci0, nxc, nyc - cj0, nxc - ci0);
+      if (MASKED) load_tile_i8<CH, CW, CW>(&S.cm[0][0], mskc + (size_t)cj0 * nxc + ci0, nxc, nyc - cj0, nxc - ci0);
     }
-  }
-  if (INTERP) {
-    for (int r = warp; r < CH; r += NT / 32) {
-      int j = cj0 + r;
-      const double *row = xc + (size_t)j * nxc + ci0;
-      for (int q = lane; q < CW; q += 32) {
-        bool in = j < nyc && (ci0 + q) < nxc;
-        cp_async8(&S.cs[r][q], in ? row + q : xc, in);
-        if (MASKED) S.cm[r][q] = in ? mskc[(size_t)j * nxc + ci0 + q] : (int8_t)0;
-      }
-    }
-  }
-  if (MASKED) {
-    for (int r = warp; r < XH; r += NT / 32) {
-      int j = j0 - 2 + r;
-      for (int q = lane; q < XW; q += 32) {
-        int i = i0 - 2 + q;
-        S.ms[r][q] = (j < ny && i < nx) ? L.msk[(size_t)j * nx + i] : (int8_t)0;
-      }
-    }
+    if (MASKED) load_tile_i8<XH, XW, XW>(&S.ms[0][0], L.msk + (size_t)(j0 - 2) * nx + (i0 - 2), nx, vr, vc);
   }
   cp_async_wait_all();
   __syncthreads();
-  // ---- fused interpolation: xs = [xin +] I(xc)  (fortran_multigrid.f90:415-498)
+  // ---- fused interpolation: xs = [xin +] I(xc)  (fortran_multigrid.f90:415-498).
+  // One thread per coarse cell of the tile produces the 2x2 fine block it anchors.
   if (INTERP) {
-    for (int r = warp; r < XH; r += NT / 32) {
-      int j = j0 - 2 + r;
-      int lj = (j >> 1) + 1 - cj0, pj = j & 1;
-      for (int q = lane; q < XW; q += 32) {
-        int i = i0 - 2 + q;
-        double iv = 0.;
-        if (j < ny && i < nx && (!MASKED || S.ms[r][q] > 0)) {
-          int li = (i >> 1) + 1 - ci0, pi = i & 1;
-          if (!pj && !pi) {
-            iv = S.cs[lj][li];
-          } else if (!pj) {
-            int sm = MASKED ? S.cm[lj][li] + S.cm[lj][li + 1] : 2;
-            iv = (S.cs[lj][li] + S.cs[lj][li + 1]) * interp_w2(sm);
-          } else if (!pi) {
-            int sm = MASKED ? S.cm[lj][li] + S.cm[lj + 1][li] : 2;
-            iv = (S.cs[lj][li] + S.cs[lj + 1][li]) * interp_w2(sm);
-          } else {
-            int sm = MASKED ? S.cm[lj][li] + S.cm[lj][li + 1] + S.cm[lj + 1][li] + S.cm[lj + 1][li + 1] : 4;
-            iv = interp_w4(sm) * (((S.cs[lj][li] + S.cs[lj][li + 1]) + S.cs[lj + 1][li]) + S.cs[lj + 1][li + 1]);
-          }
+    // fine position (r,q) of the tile <-> coarse local (r+1)/2 ... ; the block anchored at
+    // coarse local (lj,li) covers fine rows 2*lj-1, 2*lj (tile coordinates) when j0 is odd
+    // (j0 = 3 + k*TY): fine tile row r has global parity (j0 - 2 + r) & 1 = (r + 1) & 1
+    for (int p = t; p < (XH / 2) * (XW / 2); p += NT) {
+      int bj = p / (XW / 2), bi = p % (XW / 2);   // 2x2 block index inside the x tile
+      int r = 2 * bj, q = 2 * bi;                 // its first (odd-global) row / column
+      // global (j,i) of (r,q) is odd/odd: coarse anchor lj = ((j>>1)+1-cj0) = bj, li = bi
+      int lj = bj, li = bi;
+      double c00 = S.cs[lj][li], c01 = S.cs[lj][li + 1], c10 = S.cs[lj + 1][li], c11 = S.cs[lj + 1][li + 1];
+      int m00 = 1, m01 = 1, m10 = 1, m11 = 1;
+      if (MASKED) { m00 = S.cm[lj][li]; m01 = S.cm[lj][li + 1]; m10 = S.cm[lj + 1][li]; m11 = S.cm[lj + 1][li + 1]; }
+      // the tile origin is odd/odd in global coordinates, so inside the block
+      //  (r  , q  ) odd row, odd col  : 4-point mean anchored at coarse (lj,li)
+      //  (r  , q+1) odd row, even col : mean in y along coarse column li+1 -> (c01,c11)
+      //  (r+1, q  ) even row, odd col : mean in x along coarse row lj+1    -> (c10,c11)
+      //  (r+1, q+1) even row, even col: injection of c11
+      double v_oo = interp_w4(m00 + m01 + m10 + m11) * (((c00 + c01) + c10) + c11);
+      double v_oe = (c01 + c11) * interp_w2(m01 + m11);
+      double v_eo = (c10 + c11) * interp_w2(m10 + m11);
+      double v_ee = c11;
+      auto put = [&](int rr, int qq, double iv) {
+        int j = j0 - 2 + rr, i = i0 - 2 + qq;
+        if (j < ny && i < nx) {
+          if (MASKED && !(S.ms[rr][qq] > 0)) iv = 0.;
+          S.xs[rr][qq] = (INPUT == 3) ? S.xs[rr][qq] + iv : iv;
+        } else if (INPUT != 3) {
+          S.xs[rr][qq] = 0.;
         }
-        S.xs[r][q] = (INPUT == 3) ? S.xs[r][q] + iv : iv;
-      }
+      };
+      put(r, q, v_oo);
+      put(r, q + 1, v_oe);
+      put(r + 1, q, v_eo);
+      put(r + 1, q + 1, v_ee);
     }
     __syncthreads();
   }
   // ---- sweep 1 on the tile + ring 1, restricted to [2, n-3] (all that sweep 2 reads).
-  // Thread (tx, tg) takes column tx of the y1 tile and a run of rows, carrying the 3x3
-  // window in registers (3 shared-memory loads per point); the two extra columns of
-  // the ring are done point-wise afterwards.
+  // Thread (tx, tg) takes column tx of the y1 tile and a run of rows (9,9,8,8); the two
+  // extra columns of the ring are done point-wise afterwards.
   const int tx = t & (TX - 1), tg = t >> 6;  // TX == 64
   Coefs<MASKED, STORED> kc;
   if (!MASKED && !STORED) kc.load(L, 0, nullptr, 0);
-  auto sweep1_point = [&](int r, int q) {   // r,q index the y1 tile
-    int j = j0 - 1 + r, i = i0 - 1 + q;
-    double val = 0.;
-    if (j >= 2 && j <= ny - 3 && i >= 2 && i <= nx - 3) {
-      int xr = r + 1, xq = q + 1;  // same point in the x tile
-      if (!MASKED || S.ms[xr][xq] != 0) {
-        Coefs<MASKED, STORED> k;
-        if (MASKED || STORED) k.load(L, (size_t)j * nx + i, MASKED ? &S.ms[xr][xq] : nullptr, XW); else k = kc;
-        double x00 = 0., x01 = 0., x02 = 0., x10 = 0., x11 = 0., x12 = 0., x20 = 0., x21 = 0., x22 = 0.;
-        if (INPUT != 1) {
-          x00 = S.xs[xr - 1][xq - 1]; x01 = S.xs[xr - 1][xq]; x02 = S.xs[xr - 1][xq + 1];
-          x10 = S.xs[xr][xq - 1];     x11 = S.xs[xr][xq];     x12 = S.xs[xr][xq + 1];
-          x20 = S.xs[xr + 1][xq - 1]; x21 = S.xs[xr + 1][xq]; x22 = S.xs[xr + 1][xq + 1];
-        }
-        val = jacobi_val<MASKED, STORED>(L, k, x00, x01, x02, x10, x11, x12, x20, x21, x22, S.bs[r][q]);
-      }
-    }
-    S.y1[r][q] = val;
-  };
   {
     const int r0 = tg * 8 + (tg < 2 ? tg : 2), nr = tg < 2 ? 9 : 8;
-    const int q = tx, xq = q + 1;
-    const int i = i0 - 1 + q;
-    const bool colok = (i >= 2 && i <= nx - 3);
-    double a0 = 0., a1 = 0., a2 = 0., m0 = 0., m1 = 0., m2 = 0.;
-    if (INPUT != 1) {
-      a0 = S.xs[r0][xq - 1]; a1 = S.xs[r0][xq]; a2 = S.xs[r0][xq + 1];
-      m0 = S.xs[r0 + 1][xq - 1]; m1 = S.xs[r0 + 1][xq]; m2 = S.xs[r0 + 1][xq + 1];
+    const int j = j0 - 1 + r0, i = i0 - 1 + tx;
+    const double *sp = &S.xs[r0 + 1][tx + 1];
+    const double *bp = &S.bs[r0][tx];
+    const int8_t *mp = &S.ms[r0 + 1][tx + 1];
+    double *yp = &S.y1[r0][tx];
+    auto out = [&](int k, double val) { yp[k * YW] = val; };
+    if (inner)
+      jacobi_strip<MASKED, STORED, ZERO, false, 9, XW, YW, XW>(L, kc, sp, bp, mp, nr, j, i, 2, out);
+    else
+      jacobi_strip<MASKED, STORED, ZERO, true, 9, XW, YW, XW>(L, kc, sp, bp, mp, nr, j, i, 2, out);
+    if (t < YH * 2) {   // ring columns TX, TX+1 of the y1 tile
+      const int r = t >> 1, q = TX + (t & 1);
+      double *y = &S.y1[r][q];
+      auto out1 = [&](int, double val) { *y = val; };
+      jacobi_strip<MASKED, STORED, ZERO, true, 1, XW, YW, XW>(L, kc, &S.xs[r + 1][q + 1], &S.bs[r][q],
+                                                              &S.ms[r + 1][q + 1], 1, j0 - 1 + r, i0 - 1 + q, 2, out1);
     }
-#pragma unroll 3
-    for (int r = r0; r < r0 + nr; r++) {
-      double h0 = 0., h1 = 0., h2 = 0.;
-      if (INPUT != 1) { h0 = S.xs[r + 2][xq - 1]; h1 = S.xs[r + 2][xq]; h2 = S.xs[r + 2][xq + 1]; }
-      int j = j0 - 1 + r;
-      double val = 0.;
-      if (colok && j >= 2 && j <= ny - 3 && (!MASKED || S.ms[r + 1][xq] != 0)) {
-        Coefs<MASKED, STORED> k;
-        if (MASKED || STORED) k.load(L, (size_t)j * nx + i, MASKED ? &S.ms[r + 1][xq] : nullptr, XW); else k = kc;
-        val = jacobi_val<MASKED, STORED>(L, k, a0, a1, a2, m0, m1, m2, h0, h1, h2, S.bs[r][q]);
-      }
-      S.y1[r][q] = val;
-      a0 = m0; a1 = m1; a2 = m2;
-      m0 = h0; m1 = h1; m2 = h2;
-    }
-    if (t < YH * 2) sweep1_point(t >> 1, TX + (t & 1));
   }
   __syncthreads();
   // ---- sweep 2 on the tile interior; tiles that touch the rim also store halo images
   {
     const bool rim = (j0 < 2 * NH) || (i0 < 2 * NH) || (j0 + TY > ny - 2 * NH) || (i0 + TX > nx - 2 * NH);
     const int r0 = tg * 8;
-    const int i = i0 + tx;
-    const int yq = tx + 1;
-    if (i <= nx - 1 - NH) {
-      double a0 = S.y1[r0][yq - 1], a1 = S.y1[r0][yq], a2 = S.y1[r0][yq + 1];
-      double m0 = S.y1[r0 + 1][yq - 1], m1 = S.y1[r0 + 1][yq], m2 = S.y1[r0 + 1][yq + 1];
-#pragma unroll 4
-      for (int r = r0; r < r0 + 8; r++) {
-        int j = j0 + r;
-        if (j > ny - 1 - NH) break;
-        double h0 = S.y1[r + 2][yq - 1], h1 = S.y1[r + 2][yq], h2 = S.y1[r + 2][yq + 1];
-        double val = 0.;
-        if (!MASKED || S.ms[r + 2][tx + 2] != 0) {
-          Coefs<MASKED, STORED> k;
-          if (MASKED || STORED) k.load(L, (size_t)j * nx + i, MASKED ? &S.ms[r + 2][tx + 2] : nullptr, XW); else k = kc;
-          val = jacobi_val<MASKED, STORED>(L, k, a0, a1, a2, m0, m1, m2, h0, h1, h2, S.bs[r + 1][yq]);
-        }
-        if (acc) {
-          // solve(): `x += self.x[0]` (hierarchy.py:171) fused into the last kernel of the
-          // F-cycle: the correction is added to psi instead of being stored
-          acc[(size_t)j * nx + i] = acc[(size_t)j * nx + i] + val;
-          if (rim)
-            f2d::for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) {
-              acc[(size_t)jj * nx + ii] = acc[(size_t)jj * nx + ii] + val;
-            });
-        } else {
-          xout[(size_t)j * nx + i] = val;
-          if (rim)
-            f2d::for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { xout[(size_t)jj * nx + ii] = val; });
-        }
-        a0 = m0; a1 = m1; a2 = m2;
-        m0 = h0; m1 = h1; m2 = h2;
-      }
-    }
+    const int j = j0 + r0, i = i0 + tx;
+    double *base = acc ? acc : xout;
+    double *dst = base + (size_t)j * nx + i;
+    const bool accum = acc != nullptr;
+    auto out = [&](int k, double val) {
+      double *d = dst + (size_t)k * nx;
+      // solve(): `x += self.x[0]` (hierarchy.py:171) fused into the last kernel of the
+      // F-cycle: the correction is added to psi (acc) instead of being stored
+      *d = accum ? *d + val : val;
+      if (rim)
+        f2d::for_each_halo_image(j + k, i, ny, nx, NH, [&](int j2, int i2) {
+          double *e = base + (size_t)j2 * nx + i2;
+          *e = accum ? *e + val : val;
+        });
+    };
+    const double *sp = &S.y1[r0 + 1][tx + 1];
+    const double *bp = &S.bs[r0 + 1][tx + 1];
+    const int8_t *mp = &S.ms[r0 + 2][tx + 2];
+    if (inner)
+      jacobi_strip<MASKED, STORED, false, false, 8, YW, YW, XW>(L, kc, sp, bp, mp, 8, j, i, NH, out);
+    else
+      jacobi_strip<MASKED, STORED, false, true, 8, YW, YW, XW>(L, kc, sp, bp, mp, 8, j, i, NH, out);
   }
 }
 
@@ -314,8 +338,8 @@ constexpr int RXW = RW + 2, RXH = RH + 2;          // x tile
 // residual at an arbitrary fine cell straight from global memory (ring cells whose
 // periodic source lies far from the tile)
 template <bool MASKED, bool STORED>
-__device__ double resid_global(const LevelK &L, const double *__restrict__ x, const double *__restrict__ b, int j,
-                               int i) {
+__device__ __noinline__ double resid_global(const LevelK &L, const double *__restrict__ x, const double *__restrict__ b,
+                                            int j, int i) {
   int nx = L.nx;
   size_t g = (size_t)j * nx + i;
   if (MASKED && L.msk[g] == 0) return 0.;
@@ -333,6 +357,40 @@ struct ResidSmem {
   int8_t ms[RXH][RXW];
 };
 
+// column strip of the residual tile (same register-window scheme as jacobi_strip)
+template <bool MASKED, bool STORED, bool GUARD, int NR>
+__device__ __forceinline__ void resid_strip(const LevelK &L, const Coefs<MASKED, STORED> &kc, const double *sp,
+                                            const double *bp, const int8_t *mp, double *rp, int nr, int j, int i,
+                                            const double *__restrict__ x, const double *__restrict__ b) {
+  const int ny = L.ny, nx = L.nx;
+  double a0 = sp[-RXW - 1], a1 = sp[-RXW], a2 = sp[-RXW + 1];
+  double m0 = sp[-1], m1 = sp[0], m2 = sp[1];
+  size_t g = (size_t)j * nx + i;
+#pragma unroll
+  for (int k = 0; k < NR; k++) {
+    if (k < nr) {
+      double h0 = sp[(k + 1) * RXW - 1], h1 = sp[(k + 1) * RXW], h2 = sp[(k + 1) * RXW + 1];
+      double val = 0.;
+      const int jj = j + k;
+      if (GUARD && (jj > ny - NH || i > nx - NH)) {
+        val = 0.;
+      } else if (GUARD && (jj == ny - NH || i == nx - NH)) {
+        // first halo ring on the high side: the reference reads the halo-filled residual
+        // there, i.e. the residual of the periodic source cell
+        val = resid_global<MASKED, STORED>(L, x, b, f2d::wrap_src(jj, ny, NH), f2d::wrap_src(i, nx, NH));
+      } else if (!MASKED || mp[k * RXW] != 0) {
+        Coefs<MASKED, STORED> kk;
+        if (MASKED || STORED) kk.load(L, g + (size_t)k * nx, MASKED ? mp + k * RXW : nullptr, RXW); else kk = kc;
+        double cdiag = STORED ? L.A[4 * (size_t)ny * nx + g + (size_t)k * nx] : L.c[4];
+        val = resid_val<MASKED, STORED>(L, kk, cdiag, a0, a1, a2, m0, m1, m2, h0, h1, h2, bp[k * RW]);
+      }
+      rp[k * RW] = val;
+      a0 = m0; a1 = m1; a2 = m2;
+      m0 = h0; m1 = h1; m2 = h2;
+    }
+  }
+}
+
 template <bool MASKED, bool STORED>
 __global__ void __launch_bounds__(NT)
 k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ bc,
@@ -340,71 +398,43 @@ k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restric
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ResidSmem &S = *reinterpret_cast<ResidSmem *>(smem_raw);
   const int ny = L.ny, nx = L.nx;
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int t = threadIdx.x;
   const int ci0 = NH + blockIdx.x * RTX, cj0 = NH + blockIdx.y * RTY;  // first coarse output
   const int fi0 = 2 * ci0 - 3, fj0 = 2 * cj0 - 3;                      // first fine residual point
-  for (int r = warp; r < RXH; r += NT / 32) {
-    int j = fj0 - 1 + r;
-    const double *row = x + (size_t)j * nx + (fi0 - 1);
-#pragma unroll
-    for (int q = lane; q < RXW; q += 32) {
-      bool in = j < ny && (fi0 - 1 + q) < nx;
-      cp_async8(&S.xs[r][q], in ? row + q : x, in);
-      if (MASKED) S.ms[r][q] = in ? L.msk[(size_t)j * nx + fi0 - 1 + q] : (int8_t)0;
+  // inner tile: the whole residual tile lies strictly inside the fine interior
+  const bool inner = (fj0 + RH <= ny - NH) && (fi0 + RW <= nx - NH);
+  {
+    const double *xsrc = x + (size_t)(fj0 - 1) * nx + (fi0 - 1);
+    const double *bsrc = b + (size_t)fj0 * nx + fi0;
+    const int vr = ny - (fj0 - 1), vc = nx - (fi0 - 1);
+    if (inner) {
+      load_tile<RXH, RXW, RXW, true>(&S.xs[0][0], xsrc, nx, 0, 0);
+      load_tile<RH, RW, RW, true>(&S.bs[0][0], bsrc, nx, 0, 0);
+    } else {
+      load_tile<RXH, RXW, RXW, false>(&S.xs[0][0], xsrc, nx, vr, vc);
+      load_tile<RH, RW, RW, false>(&S.bs[0][0], bsrc, nx, vr - 1, vc - 1);
     }
-  }
-  for (int r = warp; r < RH; r += NT / 32) {
-    int j = fj0 + r;
-    const double *row = b + (size_t)j * nx + fi0;
-#pragma unroll
-    for (int q = lane; q < RW; q += 32) {
-      bool in = j < ny && (fi0 + q) < nx;
-      cp_async8(&S.bs[r][q], in ? row + q : b, in);
-    }
+    if (MASKED) load_tile_i8<RXH, RXW, RXW>(&S.ms[0][0], L.msk + (size_t)(fj0 - 1) * nx + (fi0 - 1), nx, vr, vc);
   }
   cp_async_wait_all();
   __syncthreads();
-  // ---- fine residual on the (2RTX+1) x (2RTY+1) tile: column strips with the 3x3 window
-  // in registers; column 2RTX point-wise
+  // ---- fine residual on the (2RTX+1) x (2RTY+1) tile: column strips (rows 9,8,8,8) with
+  // the 3x3 window in registers; the last column point-wise
   Coefs<MASKED, STORED> kc;
   if (!MASKED && !STORED) kc.load(L, 0, nullptr, 0);
-  auto resid_point = [&](int r, int q, double x00, double x01, double x02, double x10, double x11, double x12,
-                         double x20, double x21, double x22) -> double {
-    int j = fj0 + r, i = fi0 + q;
-    double val = 0.;
-    if (j <= ny - NH && i <= nx - NH) {
-      if (j == ny - NH || i == nx - NH) {
-        // first halo ring on the high side: the reference reads the halo-filled residual
-        // there, i.e. the residual of the periodic source cell
-        val = resid_global<MASKED, STORED>(L, x, b, f2d::wrap_src(j, ny, NH), f2d::wrap_src(i, nx, NH));
-      } else if (!MASKED || S.ms[r + 1][q + 1] != 0) {
-        size_t g = (size_t)j * nx + i;
-        Coefs<MASKED, STORED> k;
-        if (MASKED || STORED) k.load(L, g, MASKED ? &S.ms[r + 1][q + 1] : nullptr, RXW); else k = kc;
-        double cdiag = STORED ? L.A[4 * (size_t)ny * nx + g] : L.c[4];
-        val = resid_val<MASKED, STORED>(L, k, cdiag, x00, x01, x02, x10, x11, x12, x20, x21, x22, S.bs[r][q]);
-      }
-    }
-    return val;
-  };
   {
     const int tx = t & 63, tg = t >> 6;
-    const int r0 = tg * 8 + (tg < 1 ? 0 : 1), nr = tg < 1 ? 9 : 8;   // 9,8,8,8 = 33 rows
-    const int xq = tx + 1;
-    double a0 = S.xs[r0][xq - 1], a1 = S.xs[r0][xq], a2 = S.xs[r0][xq + 1];
-    double m0 = S.xs[r0 + 1][xq - 1], m1 = S.xs[r0 + 1][xq], m2 = S.xs[r0 + 1][xq + 1];
-#pragma unroll 3
-    for (int r = r0; r < r0 + nr; r++) {
-      double h0 = S.xs[r + 2][xq - 1], h1 = S.xs[r + 2][xq], h2 = S.xs[r + 2][xq + 1];
-      S.rs[r][tx] = resid_point(r, tx, a0, a1, a2, m0, m1, m2, h0, h1, h2);
-      a0 = m0; a1 = m1; a2 = m2;
-      m0 = h0; m1 = h1; m2 = h2;
-    }
+    const int r0 = tg * 8 + (tg < 1 ? 0 : 1), nr = tg < 1 ? 9 : 8;
+    if (inner)
+      resid_strip<MASKED, STORED, false, 9>(L, kc, &S.xs[r0 + 1][tx + 1], &S.bs[r0][tx], &S.ms[r0 + 1][tx + 1],
+                                            &S.rs[r0][tx], nr, fj0 + r0, fi0 + tx, x, b);
+    else
+      resid_strip<MASKED, STORED, true, 9>(L, kc, &S.xs[r0 + 1][tx + 1], &S.bs[r0][tx], &S.ms[r0 + 1][tx + 1],
+                                           &S.rs[r0][tx], nr, fj0 + r0, fi0 + tx, x, b);
     if (t < RH) {
-      int r = t, q = RW - 1, xr = r + 1, xq2 = q + 1;
-      S.rs[r][q] = resid_point(r, q, S.xs[xr - 1][xq2 - 1], S.xs[xr - 1][xq2], S.xs[xr - 1][xq2 + 1],
-                               S.xs[xr][xq2 - 1], S.xs[xr][xq2], S.xs[xr][xq2 + 1], S.xs[xr + 1][xq2 - 1],
-                               S.xs[xr + 1][xq2], S.xs[xr + 1][xq2 + 1]);
+      const int r = t, q = RW - 1;
+      resid_strip<MASKED, STORED, true, 1>(L, kc, &S.xs[r + 1][q + 1], &S.bs[r][q], &S.ms[r + 1][q + 1], &S.rs[r][q], 1,
+                                           fj0 + r, fi0 + q, x, b);
     }
   }
   __syncthreads();
@@ -418,10 +448,9 @@ k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restric
     size_t g = (size_t)j * nxc + i;
     double val = 0.;
     if (!MASKED || mskc[g] != 0) {
-      int fr = 2 * r + 1, fq = 2 * q + 1;  // centre in the residual tile
-      val = 0.25 * S.rs[fr][fq] +
-            0.125 * (((S.rs[fr][fq - 1] + S.rs[fr][fq + 1]) + S.rs[fr - 1][fq]) + S.rs[fr + 1][fq]) +
-            0.0625 * (((S.rs[fr - 1][fq - 1] + S.rs[fr - 1][fq + 1]) + S.rs[fr + 1][fq - 1]) + S.rs[fr + 1][fq + 1]);
+      const double *c = &S.rs[2 * r + 1][2 * q + 1];  // centre in the residual tile
+      val = 0.25 * c[0] + 0.125 * (((c[-1] + c[1]) + c[-RW]) + c[RW]) +
+            0.0625 * (((c[-RW - 1] + c[-RW + 1]) + c[RW - 1]) + c[RW + 1]);
     }
     bc[g] = val;
     if (rim)

@@ -28,8 +28,9 @@ VARIANTS = {
 
 def _newest_source():
     t = 0.
-    for f in SOURCES + HEADERS:
-        t = max(t, os.path.getmtime(os.path.join(CSRC, f)))
+    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(CSRC, f) for f in HEADERS]
+    for f in files:
+        t = max(t, os.path.getmtime(f))
     return max(t, os.path.getmtime(os.path.abspath(__file__)))
 
 

@@ -221,17 +221,17 @@ def gpu_main(args):
     mgh = model.ope.gmg.h
     x0 = torch.zeros((n+6, n+6), dtype=torch.float64, device="cuda")
     b0 = torch.randn((n+6, n+6), dtype=torch.float64, device="cuda")
-    reps = 20
+    reps = 10
     for _ in range(3):
-        lib.mg_smooth(mgh, 0, r.ptr(x0), r.ptr(b0), 1, r.stream)
+        lib.mg_smooth(mgh, 0, r.ptr(x0), r.ptr(b0), 2, r.stream)
     torch.cuda.synchronize()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
     for _ in range(reps):
-        lib.mg_smooth(mgh, 0, r.ptr(x0), r.ptr(b0), 1, r.stream)
+        lib.mg_smooth(mgh, 0, r.ptr(x0), r.ptr(b0), 2, r.stream)   # 2 applications: x -> t -> x
     s1.record()
     torch.cuda.synchronize()
-    smooth_ms = s0.elapsed_time(s1)/reps
+    smooth_ms = s0.elapsed_time(s1)/(2*reps)
     achieved = SMOOTH_BYTES_PER_CELL*n*n/(smooth_ms*1e-3)/1e9
     # ---- V-cycle (metric part 2): one Vcycle(0) through its CUDA graph
     lib.mg_vcycle(mgh, 0, r.stream)
@@ -290,8 +290,11 @@ def gpu_main(args):
                    "grid": [n, n], "tracers": T, "n_F_mean": n_F,
                    "parallelism": "single GPU" if world == 1 else "%d independent replicas (slab exchange not in this build)" % world,
                    "cache": "working set %.1f GB >> 126 MB L2 (no flush needed)" % (40*(n+6)**2*8/1e9)},
-        "roofline": {"bound": "hbm", "kernel": "k_jacobi x2 (Grid.smooth, level 0)", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved/peak, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": "k_smooth2<0,0,0> (Grid.smooth = double Jacobi sweep + halo fill, level 0)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 4096^2, from
+                     # profiles/r01_ncu_full_smooth2_level0_v2.csv (269 MB + 107 MB; algorithmic 420 MB)
+                     "traffic": 3.76e8 if n == 4096 else None,
                      "peak_source": peak_src, "ms_per_launch": smooth_ms,
                      "algorithmic_bytes_per_cell": SMOOTH_BYTES_PER_CELL},
         "step_hbm": {"b_alg_bytes_per_cell": balg, "achieved_gbs": balg*value/world/1e9,

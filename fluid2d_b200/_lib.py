@@ -17,6 +17,7 @@ _CTYPES = {
     "double": ctypes.c_double,
     "size_t": ctypes.c_size_t,
     "long long": ctypes.c_longlong,
+    "unsigned int": ctypes.c_uint,
     "void": None,
     "f2d_stream_t": ctypes.c_void_p,
 }
@@ -85,7 +86,8 @@ class Library(object):
             f.argtypes = argtypes
             self.raw[fn] = f
             if ret is ctypes.c_int and fn not in ("f2d_abi_version", "f2d_mg_nlevels",
-                                                  "f2d_mg_level_matrix_mode"):
+                                                  "f2d_mg_level_matrix_mode", "f2d_mg_slab_levels",
+                                                  "f2d_comm_rank", "f2d_comm_size"):
                 setattr(self, fn[4:], self._checked(fn, f))
             else:
                 setattr(self, fn[4:], f)

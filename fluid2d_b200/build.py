@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-SOURCES = ["f2d_operators.cu", "f2d_advection.cu", "f2d_diag.cu", "f2d_multigrid.cu"]
+SOURCES = ["f2d_operators.cu", "f2d_advection.cu", "f2d_diag.cu", "f2d_multigrid.cu", "f2d_comm.cu"]
 HEADERS = ["f2d_common.cuh", os.path.join("..", "..", "include", "f2d_b200.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -91,7 +91,11 @@ class DeviceState(object):
     def __init__(self, nvar, ny, nx, device=None):
         self.nvar, self.ny, self.nx = nvar, ny, nx
         self.device = device if device is not None else torch.device('cuda', torch.cuda.current_device())
-        self.dev = torch.zeros((nvar, ny, nx), dtype=torch.float64, device=self.device)
+        if self.device.type == 'cuda':
+            from runtime import rt
+            self.dev = rt().alloc((nvar, ny, nx))     # symmetric heap when the domain is decomposed
+        else:
+            self.dev = torch.zeros((nvar, ny, nx), dtype=torch.float64, device=self.device)
         self._host_t = None        # pinned torch tensor, allocated on first host access
         self._host = None          # numpy view of it
         self.host_fresh = [True]*nvar

@@ -43,7 +43,7 @@ class LevelInfo(object):
 
 
 class Gmg(object):
-    def __init__(self, param, mskp):
+    def __init__(self, param, mskp, comm=None):
         """param: dict with n, m (local interior sizes), nh, dx, dy, omega, hydroepsilon
         [, qgoperator, Rd]; mskp: corner mask, 0/1 (numpy or device float64 tensor)"""
         r = rt()
@@ -57,8 +57,14 @@ class Gmg(object):
         assert tuple(mskp.shape) == (ny, nx)
         Rd = float(param['Rd']) if param.get('qgoperator', False) else 0.
         self.h = ctypes.c_void_p()
-        self.lib.mg_create(ctypes.byref(self.h), r.ptr(mskp), ny, nx, float(param['dx']), float(param['dy']),
-                           float(param.get('omega', 8./9.)), float(param.get('hydroepsilon', 1.)), Rd, r.stream)
+        args = (r.ptr(mskp), ny, nx, float(param['dx']), float(param['dy']),
+                float(param.get('omega', 8./9.)), float(param.get('hydroepsilon', 1.)), Rd, r.stream)
+        if comm is None:
+            self.lib.mg_create(ctypes.byref(self.h), *args)
+        else:
+            # y-slabs: (ny, nx) is the local slab; coarse levels are gathered and replicated
+            self.lib.mg_create_slab(ctypes.byref(self.h), comm, *args)
+        self.slab_levels = self.lib.mg_slab_levels(self.h)
         self.nlevs = self.lib.mg_nlevels(self.h)
         self.nglo, self.mglo = param['n'], param['m']
         self.grid = [LevelInfo(self, lev) for lev in range(self.nlevs)]

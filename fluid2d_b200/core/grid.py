@@ -17,6 +17,11 @@ class Grid(Param):
     def __init__(self, param):
         import os
         rank = int(os.environ.get('RANK', '0')) if param.npx*param.npy > 1 else 0
+        if param.npx*param.npy > 1:
+            if param.npx != 1:
+                raise NotImplementedError('the domain is decomposed in y-slabs: use npx = 1, npy = number of GPUs')
+            from runtime import ensure_dist
+            ensure_dist()
         param.myrank = rank
         param.nbproc = param.npx*param.npy
         param.nx = int(param.nx)

@@ -51,8 +51,12 @@ class Operators(Param):
         self.d_msknoslip = r.to_device(np.ascontiguousarray(self.msknoslip, dtype=np.int8))
 
         # work arrays of the inversion
-        self.work = torch.zeros((ny, nx), dtype=torch.float64, device=r.device)
-        self.work2 = torch.zeros((ny, nx), dtype=torch.float64, device=r.device)
+        # y-slab decomposition: kernels store their x images only (fill mode 2) and the
+        # y halo rows are pushed to the neighbours by f2d_comm_exchange_y
+        self.comm = r.comm
+        self.fillmode = 2 if r.comm is not None else 1
+        self.work = r.alloc((ny, nx))
+        self.work2 = r.alloc((ny, nx))
 
         pp = {'np': 1, 'mp': 1, 'nh': param.nh, 'n': nx-2*self.nh, 'm': ny-2*self.nh,
               'omega': 8./9., 'dx': grid.dx, 'dy': grid.dy, 'hydroepsilon': param.hydroepsilon,
@@ -64,7 +68,7 @@ class Operators(Param):
             print('-'*50)
             print(' Multigrid hierarchy (device)')
             print('-'*50)
-        self.gmg = Gmg(pp, mskp.astype(np.float64))
+        self.gmg = Gmg(pp, mskp.astype(np.float64), comm=r.comm)
         if self.myrank == 0:
             for g in self.gmg.grid:
                 print('Level %2i: %5ix%5i' % (g.lev, g.n, g.m))
@@ -130,9 +134,15 @@ class Operators(Param):
         scripts, e.g. grid.fill_halo(noise)), a state view, or a device tensor."""
         r = self.rt
         if isinstance(x, torch.Tensor):
-            self.lib.fill_halo(r.ptr(x), self.nh, x.shape[0], x.shape[1], r.stream)
+            self._fill(r.ptr(x), x.shape[0], x.shape[1])
             return
         a = np.asarray(x)
+        if self.comm is not None:
+            # slabs: through a scratch field of the symmetric heap (exchange with the neighbours)
+            self.work2.copy_(torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)))
+            self._fill(r.ptr(self.work2), a.shape[0], a.shape[1])
+            x[...] = self.work2.cpu().numpy().astype(a.dtype)
+            return
         if a.dtype == np.int8:
             d = r.to_device(a)
             self.lib.fill_halo_i8(r.ptr(d), self.nh, a.shape[0], a.shape[1], r.stream)
@@ -140,6 +150,20 @@ class Operators(Param):
             d = r.to_device(a, dtype=np.float64)
             self.lib.fill_halo(r.ptr(d), self.nh, a.shape[0], a.shape[1], r.stream)
         x[...] = d.cpu().numpy()
+
+    def _fill(self, ptr, ny, nx):
+        """full halo fill of a device field: local wrap, or x images + neighbour exchange"""
+        r = self.rt
+        if self.comm is None:
+            self.lib.fill_halo(ptr, self.nh, ny, nx, r.stream)
+        else:
+            self.lib.fill_halo_x(ptr, self.nh, ny, nx, r.stream)
+            self.lib.comm_exchange_y(self.comm, ptr, self.nh, ny, nx, r.stream)
+
+    def _xch(self, ptr):
+        """y halo rows of a field whose producer used fill mode 2 (no-op on one GPU)"""
+        if self.comm is not None:
+            self.lib.comm_exchange_y(self.comm, ptr, self.nh, self.nyl, self.nxl, self.rt.stream)
 
     # ------------------------------------------------------------------
     def rhs_adv(self, x, t, dxdt):
@@ -152,20 +176,23 @@ class Operators(Param):
         for trac in self.tracer_list:
             ik = self.ix(trac)
             adv(msk, x.rptr(ik), dxdt.wptr(ik), x.rptr(iu), x.rptr(iv), None, None, cst,
-                self.nh, self.fs_method, self.order, self.nyl, self.nxl, 1, r.stream)
+                self.nh, self.fs_method, self.order, self.nyl, self.nxl, self.fillmode, r.stream)
+            self._xch(dxdt.wptr(ik))
 
     def rhs_diffusion(self, x, t, dxdt, coef=1.):
         r, lib = self.rt, self.lib
         for trac in self.tracer_list:
             ik = self.ix(trac)
             lib.add_diffusion(r.ptr(self.d_msk), x.rptr(ik), self.dx, self.nh, coef*self.Kdiff[trac],
-                              dxdt.wptr(ik), self.nyl, self.nxl, 1, r.stream)
+                              dxdt.wptr(ik), self.nyl, self.nxl, self.fillmode, r.stream)
+            self._xch(dxdt.wptr(ik))
 
     def rhs_torque(self, x, t, dxdt):
         r, lib = self.rt, self.lib
         ib, iw = self.ix('buoyancy'), self.ix('vorticity')
         lib.add_torque(r.ptr(self.d_msk), x.rptr(ib), self.dx, self.nh, self.gravity, dxdt.wptr(iw),
-                       self.nyl, self.nxl, 1, 1, r.stream)
+                       self.nyl, self.nxl, 1, self.fillmode, r.stream)
+        self._xch(dxdt.wptr(iw))
 
     def rhs_noslip(self, x, source):
         """vorticity source along the walls that cancels the tangential velocity

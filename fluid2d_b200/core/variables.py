@@ -15,6 +15,9 @@ class Var(object):
         if type(self.sizevar) != list:
             raise TypeError('sizevar has to be a list')
         self.sizestate = [self.nvar]+self.sizevar
+        if getattr(param, 'npy', 1) > 1:
+            from runtime import rt
+            rt().ensure_comm(param.npy, self.sizevar[0]*self.sizevar[1]*8)
         self.dstate = DeviceState(self.nvar, self.sizevar[0], self.sizevar[1])
 
     @property

@@ -207,7 +207,7 @@ k_adv(const int8_t *__restrict__ msk, const double *__restrict__ q, double *__re
       yflx[c] = fy;
     }
     if (rim)
-      for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { dq[(size_t)jj * nx + ii] = y; });
+      for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { dq[(size_t)jj * nx + ii] = y; }, fill != 2);
     fym = fy;
   }
 }

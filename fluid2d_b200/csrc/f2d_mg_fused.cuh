@@ -34,6 +34,7 @@ struct LevelK {
   const double *A;   // 5 planes (STORED)
   double c[5];       // SW,S,SE,W,C (constant classes)
   double c1, c2, c3; // omega, 1-omega, omega/|C|
+  int ywrap;         // 1: y halo rows are local periodic images; 0: they belong to the neighbouring slabs
 };
 
 // coefficients of the 9-point operator at cell `g` (global index) / mask window
@@ -316,7 +317,7 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
         f2d::for_each_halo_image(j + k, i, ny, nx, NH, [&](int j2, int i2) {
           double *e = base + (size_t)j2 * nx + i2;
           *e = accum ? *e + val : val;
-        });
+        }, L.ywrap != 0);
     };
     const double *sp = &S.y1[r0 + 1][tx + 1];
     const double *bp = &S.bs[r0 + 1][tx + 1];
@@ -377,7 +378,8 @@ __device__ __forceinline__ void resid_strip(const LevelK &L, const Coefs<MASKED,
       } else if (GUARD && (jj == ny - NH || i == nx - NH)) {
         // first halo ring on the high side: the reference reads the halo-filled residual
         // there, i.e. the residual of the periodic source cell
-        val = resid_global<MASKED, STORED>(L, x, b, f2d::wrap_src(jj, ny, NH), f2d::wrap_src(i, nx, NH));
+        // (on a y-slab the halo row already holds the neighbour's data: evaluate in place)
+        val = resid_global<MASKED, STORED>(L, x, b, L.ywrap ? f2d::wrap_src(jj, ny, NH) : jj, f2d::wrap_src(i, nx, NH));
       } else if (!MASKED || mp[k * RXW] != 0) {
         Coefs<MASKED, STORED> kk;
         if (MASKED || STORED) kk.load(L, g + (size_t)k * nx, MASKED ? mp + k * RXW : nullptr, RXW); else kk = kc;
@@ -454,7 +456,8 @@ k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restric
     }
     bc[g] = val;
     if (rim)
-      f2d::for_each_halo_image(j, i, nyc, nxc, NH, [&](int jj, int ii) { bc[(size_t)jj * nxc + ii] = val; });
+      f2d::for_each_halo_image(j, i, nyc, nxc, NH, [&](int jj, int ii) { bc[(size_t)jj * nxc + ii] = val; },
+                               L.ywrap != 0);
   }
 }
 

@@ -27,6 +27,8 @@ struct Level {
   double *x = nullptr, *b = nullptr, *r = nullptr, *t = nullptr;
   int mode = 0;             // 0 stored, 1 constant, 2 constant x mask products
   double cst[5] = {0, 0, 0, 0, 0};  // SW,S,SE,W,C of the constant classes
+  int ywrap = 1;            // 0 on slab (distributed) levels
+  bool arena = false;       // x,b,t come from the communicator's symmetric heap
   size_t n() const { return (size_t)ny * nx; }
 };
 }  // namespace
@@ -40,6 +42,9 @@ struct f2d_mg {
   double *hscal = nullptr;    // pinned host mirror [4]
   cudaStream_t cap = nullptr; // capture stream for CUDA graphs
   bool graphs = true;
+  f2d_comm *comm = nullptr;   // y-slab decomposition (nullptr: single GPU)
+  int lg = 0;                 // number of distributed (slab) levels; L[0] is global level lg
+  std::vector<Level> S;       // slab levels 0..lg (S[lg]: slab-shaped view of L[0])
   int tail0 = -1;             // first level of the shared-memory tail (-1: no tail kernel)
   bool tail_const = false;    // every tail level is in the constant-stencil class
   size_t tail_smem = 0;
@@ -79,7 +84,7 @@ __device__ __forceinline__ double offdiag(const double *__restrict__ A, size_t p
 // fill != 0: the range is the interior and halo images are stored too
 __global__ void k_jacobi(const int8_t *__restrict__ msk, const double *__restrict__ A, const double *__restrict__ xin,
                          const double *__restrict__ b, double *__restrict__ xout, double c1, double c2, int ny,
-                         int nx, int lo, int fill) {
+                         int nx, int lo, int fill, int ywrap = 1) {
   IJ2();
   if (j < lo || j > ny - 1 - lo || i < lo || i > nx - 1 - lo) return;
   size_t pl = (size_t)ny * nx;
@@ -89,12 +94,12 @@ __global__ void k_jacobi(const int8_t *__restrict__ msk, const double *__restric
     val = xin[c] * c2 + c3 * (offdiag(A, pl, xin, c, nx) - b[c]);
   }
   xout[c] = val;
-  if (fill) for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { xout[(size_t)jj * nx + ii] = val; });
+  if (fill) for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { xout[(size_t)jj * nx + ii] = val; }, ywrap != 0);
 }
 
 // residual on the interior + halo images (fortran_multigrid.f90:320-362 + fill)
 __global__ void k_residual(const int8_t *__restrict__ msk, const double *__restrict__ A, const double *__restrict__ x,
-                           const double *__restrict__ b, double *__restrict__ r, int ny, int nx) {
+                           const double *__restrict__ b, double *__restrict__ r, int ny, int nx, int ywrap = 1) {
   IJ2();
   if (j < NH || j > ny - 1 - NH || i < NH || i > nx - 1 - NH) return;
   size_t pl = (size_t)ny * nx;
@@ -112,13 +117,13 @@ __global__ void k_residual(const int8_t *__restrict__ msk, const double *__restr
     val = val - A1[c + nx + 1] * x[c + nx + 1];
   }
   r[c] = val;
-  for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { r[(size_t)jj * nx + ii] = val; });
+  for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { r[(size_t)jj * nx + ii] = val; }, ywrap != 0);
 }
 
 // full-weighting restriction on the coarse interior + halo images
 // (fortran_multigrid.f90:501-546 + fill); msk2 == nullptr means all ones
 __global__ void k_restrict(const int8_t *__restrict__ msk2, const double *__restrict__ x1, double *__restrict__ x2,
-                           int ny, int nx /*coarse*/, int nx1) {
+                           int ny, int nx /*coarse*/, int nx1, int ywrap = 1) {
   IJ2();
   if (j < NH || j > ny - 1 - NH || i < NH || i > nx - 1 - NH) return;
   double val = 0.;
@@ -130,7 +135,7 @@ __global__ void k_restrict(const int8_t *__restrict__ msk2, const double *__rest
           0.0625 * (((x1[f - nx1 - 1] + x1[f - nx1 + 1]) + x1[f + nx1 - 1]) + x1[f + nx1 + 1]);
   }
   x2[c] = val;
-  for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { x2[(size_t)jj * nx + ii] = val; });
+  for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { x2[(size_t)jj * nx + ii] = val; }, ywrap != 0);
 }
 
 // mask-aware bilinear interpolation over the whole fine array
@@ -295,7 +300,7 @@ k_resid_sumsq(fused::LevelK L, const double *__restrict__ x, const double *__res
       }
       r[g] = val;
       if (rimrow || i < 2 * NH || i >= nx - 2 * NH)
-        for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { r[(size_t)jj * nx + ii] = val; });
+        for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { r[(size_t)jj * nx + ii] = val; }, L.ywrap != 0);
       acc += val * val;
     }
   }
@@ -317,9 +322,9 @@ inline int nblocks1d(size_t n) {
 // ---------------------------------------------------------------------------
 // per-level operators
 // ---------------------------------------------------------------------------
-fused::LevelK level_k(f2d_mg *mg, int lev) {
-  Level &l = mg->L[lev];
+fused::LevelK level_k(f2d_mg *mg, const Level &l) {
   fused::LevelK k;
+  k.ywrap = l.ywrap;
   k.ny = l.ny; k.nx = l.nx; k.msk = l.msk; k.A = l.A;
   for (int q = 0; q < 5; q++) k.c[q] = l.cst[q];
   k.c1 = mg->omega;
@@ -327,19 +332,19 @@ fused::LevelK level_k(f2d_mg *mg, int lev) {
   k.c3 = l.cst[4] != 0. ? mg->omega / fabs(l.cst[4]) : 0.;
   return k;
 }
+fused::LevelK level_k(f2d_mg *mg, int lev) { return level_k(mg, mg->L[lev]); }
 
 // fused double sweep: xout = S2(input), input = xin | 0 | I(xc) | xin + I(xc)
 template <int INPUT>
-int launch_smooth2(f2d_mg *mg, int lev, const double *xin, const double *b, double *xout, const double *xc,
-                   cudaStream_t s, double *acc) {
-  Level &l = mg->L[lev];
-  fused::LevelK k = level_k(mg, lev);
+int launch_smooth2(f2d_mg *mg, Level &l, Level *cl, const double *xin, const double *b, double *xout,
+                   const double *xc, cudaStream_t s, double *acc) {
+  fused::LevelK k = level_k(mg, l);
   dim3 grid(cdiv(l.nx - 2 * NH, fused::TX), cdiv(l.ny - 2 * NH, fused::TY));
   size_t sm = sizeof(fused::Smooth2Smem);
   const int8_t *mskc = nullptr;
   int nxc = 0, nyc = 0;
   if (INPUT >= 2) {
-    Level &c = mg->L[lev + 1];
+    Level &c = *cl;
     mskc = c.msk; nxc = c.nx; nyc = c.ny;
   }
   switch (l.mode) {
@@ -350,14 +355,19 @@ int launch_smooth2(f2d_mg *mg, int lev, const double *xin, const double *b, doub
   F2D_LAUNCHED();
   return F2D_OK;
 }
+int smooth2_L(f2d_mg *mg, Level &l, Level *cl, int input, const double *xin, const double *b, double *xout,
+              const double *xc, cudaStream_t s, double *acc = nullptr) {
+  switch (input) {
+    case 0: return launch_smooth2<0>(mg, l, cl, xin, b, xout, xc, s, acc);
+    case 1: return launch_smooth2<1>(mg, l, cl, xin, b, xout, xc, s, acc);
+    case 2: return launch_smooth2<2>(mg, l, cl, xin, b, xout, xc, s, acc);
+    default: return launch_smooth2<3>(mg, l, cl, xin, b, xout, xc, s, acc);
+  }
+}
 int smooth2(f2d_mg *mg, int lev, int input, const double *xin, const double *b, double *xout, const double *xc,
             cudaStream_t s, double *acc = nullptr) {
-  switch (input) {
-    case 0: return launch_smooth2<0>(mg, lev, xin, b, xout, xc, s, acc);
-    case 1: return launch_smooth2<1>(mg, lev, xin, b, xout, xc, s, acc);
-    case 2: return launch_smooth2<2>(mg, lev, xin, b, xout, xc, s, acc);
-    default: return launch_smooth2<3>(mg, lev, xin, b, xout, xc, s, acc);
-  }
+  Level *cl = lev + 1 < (int)mg->L.size() ? &mg->L[lev + 1] : nullptr;
+  return smooth2_L(mg, mg->L[lev], cl, input, xin, b, xout, xc, s, acc);
 }
 template <bool M, bool St, int I>
 cudaError_t set_smem_one() {
@@ -407,9 +417,9 @@ int op_residual(f2d_mg *mg, int lev, const double *x, const double *b, double *r
   return F2D_OK;
 }
 // residual of level 0 + sum of its squares -> out[0] (device)
-int op_resid_sumsq(f2d_mg *mg, const double *x, const double *b, double *r, double *out, cudaStream_t s) {
-  Level &l = mg->L[0];
-  fused::LevelK k = level_k(mg, 0);
+int op_resid_sumsq_L(f2d_mg *mg, Level &l, const double *x, const double *b, double *r, double *out,
+                     cudaStream_t s) {
+  fused::LevelK k = level_k(mg, l);
   int nb = l.ny - 2 * NH < RSB ? l.ny - 2 * NH : RSB;
   switch (l.mode) {
     case 1: k_resid_sumsq<false, false><<<nb, RST, 0, s>>>(k, x, b, r, mg->scratch); break;
@@ -421,18 +431,27 @@ int op_resid_sumsq(f2d_mg *mg, const double *x, const double *b, double *r, doub
   F2D_LAUNCHED();
   return F2D_OK;
 }
-int op_restrict(f2d_mg *mg, int lev, const double *xf, double *xc, cudaStream_t s) {
-  Level &c = mg->L[lev + 1];
+int op_resid_sumsq(f2d_mg *mg, const double *x, const double *b, double *r, double *out, cudaStream_t s) {
+  return op_resid_sumsq_L(mg, mg->L[0], x, b, r, out, s);
+}
+int op_restrict_L(f2d_mg *mg, Level &f, Level &c, const double *xf, double *xc, cudaStream_t s) {
   dim3 blk(32, 8);
-  k_restrict<<<grid2d(c.ny, c.nx, blk), blk, 0, s>>>(c.msk, xf, xc, c.ny, c.nx, mg->L[lev].nx);
+  k_restrict<<<grid2d(c.ny, c.nx, blk), blk, 0, s>>>(c.msk, xf, xc, c.ny, c.nx, f.nx, c.ywrap);
   F2D_LAUNCHED();
   return F2D_OK;
 }
+int op_restrict(f2d_mg *mg, int lev, const double *xf, double *xc, cudaStream_t s) {
+  return op_restrict_L(mg, mg->L[lev], mg->L[lev + 1], xf, xc, s);
+}
 // residual + restriction fused: bc = R(b - A x), the fine residual stays on chip
+int op_resid_restrict_L(f2d_mg *mg, Level &l, Level &c, const double *x, const double *b, double *bc,
+                        cudaStream_t s);
 int op_resid_restrict(f2d_mg *mg, int lev, const double *x, const double *b, double *bc, cudaStream_t s) {
-  Level &l = mg->L[lev];
-  Level &c = mg->L[lev + 1];
-  fused::LevelK k = level_k(mg, lev);
+  return op_resid_restrict_L(mg, mg->L[lev], mg->L[lev + 1], x, b, bc, s);
+}
+int op_resid_restrict_L(f2d_mg *mg, Level &l, Level &c, const double *x, const double *b, double *bc,
+                        cudaStream_t s) {
+  fused::LevelK k = level_k(mg, l);
   dim3 grid(cdiv(c.nx - 2 * NH, fused::RTX), cdiv(c.ny - 2 * NH, fused::RTY));
   size_t sm = sizeof(fused::ResidSmem);
   switch (l.mode) {
@@ -512,6 +531,7 @@ int vcycle_enqueue(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s,
   auto B = [&](int lev) { return lev == lev1 ? b0 : mg->L[lev].b; };
   const int t0 = mg->tail0;
   if (t0 >= 0 && lev1 == t0 && first_input == 0) return tail_launch(mg, 1, b0, x0, x0, s);
+  if (t0 >= 0 && lev1 == t0 && first_input == 1) return tail_launch(mg, 0, b0, nullptr, x0, s);
   const bool use_tail = t0 >= 0 && lev1 < t0;
   const int bottom = use_tail ? t0 : last;   // first level NOT handled by the big kernels
   if (lev1 == last) return coarsest_enqueue(mg, X(last), B(last), s);
@@ -556,9 +576,12 @@ int fcycle_enqueue(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s,
   return F2D_OK;
 }
 
+int slab_cycle_enqueue(f2d_mg *mg, int kind, int lev1, double *x0, double *b0, cudaStream_t s);
+
 // run `kind` (0 two V-cycles from level 0, 1 F-cycle, 2 single V-cycle) through a cached graph
 int run_cycle(f2d_mg *mg, int kind, int lev1, double *x0, double *b0, cudaStream_t s, double *acc = nullptr) {
   auto enqueue = [&](cudaStream_t st) -> int {
+    if (mg->comm) return slab_cycle_enqueue(mg, kind, lev1, x0, b0, st);
     if (kind == 0) {
       TRY(vcycle_enqueue(mg, 0, x0, b0, st));
       return vcycle_enqueue(mg, 0, x0, b0, st);
@@ -598,7 +621,8 @@ int read_scalars(f2d_mg *mg, int n, cudaStream_t s) {
 }
 
 void free_level(Level &l) {
-  cudaFree(l.msk); cudaFree(l.A); cudaFree(l.x); cudaFree(l.b); cudaFree(l.r); cudaFree(l.t);
+  cudaFree(l.msk); cudaFree(l.A); cudaFree(l.r);
+  if (!l.arena) { cudaFree(l.x); cudaFree(l.b); cudaFree(l.t); }   // arena memory belongs to the communicator
 }
 
 }  // namespace
@@ -606,142 +630,187 @@ void free_level(Level &l) {
 // ---------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------
-extern "C" int f2d_mg_create(f2d_mg_t **out, const double *cornermask, int ny, int nx, double dx, double dy,
-                             double omega, double hydroepsilon, double Rd, f2d_stream_t stream) {
-  if (!out || !cornermask) return fail(F2D_ERR_ARG, "mg_create: null pointer");
-  int m = ny - 2 * NH, n = nx - 2 * NH;
-  if (m < 4 || n < 4) return fail(F2D_ERR_ARG, "mg_create: grid too small");
-  if ((m & (m - 1)) || (n & (n - 1))) return fail(F2D_ERR_ARG, "mg_create: nx, ny must be powers of two");
-  if (hydroepsilon * dy / dx <= 0.2)
-    return fail(F2D_ERR_ARG, "mg_create: small aspect ratio needs the tridiagonal relaxation (not built yet)");
-  cudaStream_t s = S(stream);
-  f2d_mg *mg = new f2d_mg();
-  mg->omega = omega;
-  // Gridinfo, single rank (level.py:62-93): halve until n <= 4 or m <= 4
-  {
-    int nn = n, mm = m, lev = 0;
-    while (true) {
-      if (lev > 0) { nn /= 2; mm /= 2; }
-      Level l;
-      l.ny = mm + 2 * NH;
-      l.nx = nn + 2 * NH;
-      mg->L.push_back(l);
-      lev++;
-      if (nn <= 4 || mm <= 4) break;
-      if (lev > 20) { delete mg; return fail(F2D_ERR_ARG, "mg_create: too many levels"); }
-    }
-  }
+// ---------------------------------------------------------------------------
+// set-up
+// ---------------------------------------------------------------------------
+namespace {
+
 #define MGC(call)                                                         \
   do {                                                                    \
     cudaError_t e__ = (call);                                             \
-    if (e__ != cudaSuccess) { f2d_mg_destroy(mg); return cuda_fail(e__, #call); } \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call);                 \
   } while (0)
-  MGC(cudaStreamCreateWithFlags(&mg->cap, cudaStreamNonBlocking));
-  MGC(cudaMalloc(&mg->scratch, f2d_reduce_scratch_len() * sizeof(double)));
-  MGC(cudaMalloc(&mg->dscal, 8 * sizeof(double)));
-  MGC(cudaMallocHost(&mg->hscal, 8 * sizeof(double)));
-  for (auto &l : mg->L) {
-    size_t nb = l.n() * sizeof(double);
-    MGC(cudaMalloc(&l.msk, l.n()));
-    MGC(cudaMalloc(&l.A, 5 * nb));
+
+Stencil9 finest_stencil(double dx, double dy, double hydroepsilon) {
+  // level.py:261-302
+  double bx = dy / dx * hydroepsilon, by = dx / dy, a = -2 * (bx + by);
+  double st[9] = {0., by, 0., bx, a, bx, 0., by, 0.};
+  if (dx == dy && hydroepsilon == 1.) {
+    double aa = -6. / 2, bb = 1. / 2, cc = 0.5 / 2;
+    double st9[9] = {cc, bb, cc, bb, aa, bb, cc, bb, cc};
+    for (int k = 0; k < 9; k++) st[k] = st9[k];
+  }
+  double coef = 1. / (dx * dy);
+  Stencil9 S9;
+  for (int k = 0; k < 9; k++) S9.v[k] = st[k] * coef;
+  return S9;
+}
+
+// device allocation of a level's arrays; x, b, t come from the symmetric heap when asked
+int alloc_level(f2d_mg *mg, Level &l, bool arena, cudaStream_t s) {
+  size_t nb = l.n() * sizeof(double);
+  MGC(cudaMalloc(&l.msk, l.n()));
+  MGC(cudaMalloc(&l.A, 5 * nb));
+  MGC(cudaMalloc(&l.r, nb));
+  l.arena = arena;
+  if (arena) {
+    l.x = (double *)comm_alloc(mg->comm, nb);
+    l.b = (double *)comm_alloc(mg->comm, nb);
+    l.t = (double *)comm_alloc(mg->comm, nb);
+    if (!l.x || !l.b || !l.t) return fail(F2D_ERR_ARG, "mg: symmetric heap exhausted (raise the arena size)");
+  } else {
     MGC(cudaMalloc(&l.x, nb));
     MGC(cudaMalloc(&l.b, nb));
-    MGC(cudaMalloc(&l.r, nb));
     MGC(cudaMalloc(&l.t, nb));
-    MGC(cudaMemsetAsync(l.x, 0, nb, s));
-    MGC(cudaMemsetAsync(l.b, 0, nb, s));
-    MGC(cudaMemsetAsync(l.r, 0, nb, s));
-    MGC(cudaMemsetAsync(l.t, 0, nb, s));
   }
-  // matrices
-  double *A9prev = nullptr, *A9 = nullptr;
+  MGC(cudaMemsetAsync(l.x, 0, nb, s));
+  MGC(cudaMemsetAsync(l.b, 0, nb, s));
+  MGC(cudaMemsetAsync(l.r, 0, nb, s));
+  MGC(cudaMemsetAsync(l.t, 0, nb, s));
+  return F2D_OK;
+}
+
+// fill of one field of a level: local periodic wrap, or x images + exchange on a slab
+int level_fill(f2d_mg *mg, Level &l, double *x, cudaStream_t s) {
+  if (l.ywrap) return f2d_fill_halo(x, NH, l.ny, l.nx, (f2d_stream_t)s);
+  TRY(f2d_fill_halo_x(x, NH, l.ny, l.nx, (f2d_stream_t)s));
+  double *arr[1] = {x};
+  return comm_exchange(mg->comm, arr, 1, NH, l.ny, l.nx, s);
+}
+
+// coarse mask and Galerkin matrix of level c from level p (level.py:233-236,304-329);
+// A9p / A9c: 9 planes with filled halos (A9c in the symmetric heap on slab levels)
+int coarsen_level(f2d_mg *mg, Level &p, Level &c, const double *A9p, double *A9c, cudaStream_t s) {
   dim3 blk(32, 8);
-  for (size_t lev = 0; lev < mg->L.size(); lev++) {
+  size_t pl = c.n();
+  k_mask_to_double<<<nblocks1d(p.n()), 256, 0, s>>>(p.msk, p.t, p.n());
+  k_fill_const<<<nblocks1d(pl), 256, 0, s>>>(c.t, 1., pl);
+  k_restrict<<<grid2d(c.ny, c.nx, blk), blk, 0, s>>>(nullptr, p.t, c.t, c.ny, c.nx, p.nx, c.ywrap);
+  g_launches += 3;
+  if (!c.ywrap) {
+    double *arr[1] = {c.t};
+    TRY(comm_exchange(mg->comm, arr, 1, NH, c.ny, c.nx, s));
+  }
+  k_threshold_mask<<<nblocks1d(pl), 256, 0, s>>>(c.t, c.msk, pl);
+  k_coarsenmatrix<<<grid2d(c.ny, c.nx, blk), blk, 0, s>>>(A9p, A9c, p.msk, c.msk, c.ny, c.nx, p.ny, p.nx);
+  g_launches += 2;
+  for (int k = 0; k < 9; k++) TRY(level_fill(mg, c, A9c + k * pl, s));
+  return F2D_OK;
+}
+
+// replicated hierarchy below L[0]: L[0].msk and A9 (9 planes of L[0], halos filled) given
+int build_replicated(f2d_mg *mg, double *A9, bool a9_owned, cudaStream_t s) {
+  double *A9prev = A9;
+  bool prev_owned = a9_owned;
+  MGC(cudaMemcpyAsync(mg->L[0].A, A9, 5 * mg->L[0].n() * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  for (size_t lev = 1; lev < mg->L.size(); lev++) {
     Level &l = mg->L[lev];
-    size_t pl = l.n();
-    MGC(cudaMalloc(&A9, 9 * pl * sizeof(double)));
-    if (lev == 0) {
-      k_mask_from_double<<<nblocks1d(pl), 256, 0, s>>>(cornermask, l.msk, pl);
-      ++g_launches;
-      // level.py:261-302
-      double bx = dy / dx * hydroepsilon, by = dx / dy, a = -2 * (bx + by);
-      double st[9] = {0., by, 0., bx, a, bx, 0., by, 0.};
-      if (dx == dy && hydroepsilon == 1.) {
-        double aa = -6. / 2, bb = 1. / 2, cc = 0.5 / 2;
-        double st9[9] = {cc, bb, cc, bb, aa, bb, cc, bb, cc};
-        for (int k = 0; k < 9; k++) st[k] = st9[k];
-      }
-      double coef = 1. / (dx * dy);
-      Stencil9 S9;
-      for (int k = 0; k < 9; k++) S9.v[k] = st[k] * coef;
-      k_finest_matrix<<<grid2d(l.ny, l.nx, blk), blk, 0, s>>>(l.msk, A9, S9, l.ny, l.nx);
-      ++g_launches;
-    } else {
-      Level &p = mg->L[lev - 1];
-      // mask coarsening (level.py:233-236): w = ones; restrict(float(msk_fine)); fill; threshold
-      k_mask_to_double<<<nblocks1d(p.n()), 256, 0, s>>>(p.msk, p.t, p.n());
-      k_fill_const<<<nblocks1d(pl), 256, 0, s>>>(l.t, 1., pl);
-      k_restrict<<<grid2d(l.ny, l.nx, blk), blk, 0, s>>>(nullptr, p.t, l.t, l.ny, l.nx, p.nx);
-      k_threshold_mask<<<nblocks1d(pl), 256, 0, s>>>(l.t, l.msk, pl);
-      k_coarsenmatrix<<<grid2d(l.ny, l.nx, blk), blk, 0, s>>>(A9prev, A9, p.msk, l.msk, l.ny, l.nx, p.ny, p.nx);
-      g_launches += 5;
-    }
-    for (int k = 0; k < 9; k++) {
-      int rc = f2d_fill_halo(A9 + k * pl, NH, l.ny, l.nx, stream);
-      if (rc != F2D_OK) { cudaFree(A9); cudaFree(A9prev); f2d_mg_destroy(mg); return rc; }
-    }
-    MGC(cudaMemcpyAsync(l.A, A9, 5 * pl * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    double *A9c = nullptr;
+    MGC(cudaMalloc(&A9c, 9 * l.n() * sizeof(double)));
+    int rc = coarsen_level(mg, mg->L[lev - 1], l, A9prev, A9c, s);
+    if (rc != F2D_OK) { cudaFree(A9c); return rc; }
+    MGC(cudaMemcpyAsync(l.A, A9c, 5 * l.n() * sizeof(double), cudaMemcpyDeviceToDevice, s));
     MGC(cudaStreamSynchronize(s));
-    cudaFree(A9prev);
-    A9prev = A9;
-    A9 = nullptr;
+    if (prev_owned) cudaFree(A9prev);
+    A9prev = A9c;
+    prev_owned = true;
   }
-  cudaFree(A9prev);
+  MGC(cudaStreamSynchronize(s));
+  if (prev_owned) cudaFree(A9prev);
+  return F2D_OK;
+}
+
+// coefficient class of one level: read the stencil at the first cell whose 3x3
+// neighbourhood is fluid, then verify entry by entry that "constant stencil x mask
+// products" reproduces the stored matrix (f2d_mg_fused.cuh); ranks must agree
+int detect_mode(f2d_mg *mg, Level &l, int *dflag, unsigned long long *didx, cudaStream_t s) {
+  dim3 blk(32, 8);
+  l.mode = 0;
+  unsigned long long none = ~0ull, idx = none;
+  MGC(cudaMemcpyAsync(didx, &none, sizeof none, cudaMemcpyHostToDevice, s));
+  fused::k_find_interior<<<grid2d(l.ny, l.nx, blk), blk, 0, s>>>(l.msk, l.ny, l.nx, didx);
+  MGC(cudaMemcpyAsync(&idx, didx, sizeof idx, cudaMemcpyDeviceToHost, s));
+  MGC(cudaStreamSynchronize(s));
+  int flags[2] = {1, 1};
+  if (idx == none) {
+    flags[0] = 0;
+  } else {
+    for (int k = 0; k < 5; k++)
+      MGC(cudaMemcpyAsync(&l.cst[k], l.A + k * l.n() + idx, sizeof(double), cudaMemcpyDeviceToHost, s));
+    MGC(cudaMemcpyAsync(dflag, flags, sizeof flags, cudaMemcpyHostToDevice, s));
+    MGC(cudaStreamSynchronize(s));
+    fused::k_check_const<<<grid2d(l.ny, l.nx, blk), blk, 0, s>>>(level_k(mg, l), dflag);
+    MGC(cudaMemcpyAsync(flags, dflag, sizeof flags, cudaMemcpyDeviceToHost, s));
+    MGC(cudaStreamSynchronize(s));
+    g_launches += 2;
+  }
+  if (!l.ywrap && comm_size(mg->comm) > 1) {
+    // slab level: every rank must take the same class and the same constants
+    double h[12];
+    h[0] = flags[0]; h[1] = flags[1];
+    for (int k = 0; k < 5; k++) { h[2 + k] = flags[0] ? l.cst[k] : -1e300; h[7 + k] = flags[0] ? -l.cst[k] : -1e300; }
+    MGC(cudaMemcpyAsync(mg->dscal, h, sizeof h, cudaMemcpyHostToDevice, s));
+    TRY(comm_allreduce(mg->comm, mg->dscal, 12, 0xffcu, s));   // flags: sums; constants: max of c and of -c
+    MGC(cudaMemcpyAsync(h, mg->dscal, sizeof h, cudaMemcpyDeviceToHost, s));
+    MGC(cudaStreamSynchronize(s));
+    int G = comm_size(mg->comm);
+    flags[0] = (h[0] == G);
+    flags[1] = (h[1] == G);
+    for (int k = 0; k < 5; k++)
+      if (h[2 + k] != -h[7 + k]) flags[0] = 0;    // max(c) != min(c): not uniform across ranks
+  }
+  if (flags[0]) l.mode = flags[1] ? 1 : 2;
+  return F2D_OK;
+}
+
+int finish_setup(f2d_mg *mg, double Rd, cudaStream_t s) {
   if (Rd > 0.) {
-    for (auto &l : mg->L) {
-      k_helmholtz<<<nblocks1d(l.n()), 256, 0, s>>>(l.A + 4 * l.n(), 1. / (Rd * Rd), l.n());
-      ++g_launches;
-    }
+    for (auto *vec : {&mg->S, &mg->L})
+      for (auto &l : *vec) {
+        if (vec == &mg->S && &l == &mg->S.back()) continue;   // S[lg] shares L[0]'s matrix
+        k_helmholtz<<<nblocks1d(l.n()), 256, 0, s>>>(l.A + 4 * l.n(), 1. / (Rd * Rd), l.n());
+        ++g_launches;
+      }
   }
-  // coefficient class per level: read the stencil at the first cell whose 3x3
-  // neighbourhood is fluid, then verify entry by entry that "constant stencil x mask
-  // products" reproduces the stored matrix (f2d_mg_fused.cuh)
   MGC(set_smem_all());
   {
     int *dflag = nullptr;
     unsigned long long *didx = nullptr;
     MGC(cudaMalloc(&dflag, 2 * sizeof(int)));
     MGC(cudaMalloc(&didx, sizeof(unsigned long long)));
-    for (size_t lev = 0; lev < mg->L.size(); lev++) {
-      Level &l = mg->L[lev];
-      l.mode = 0;
-      unsigned long long none = ~0ull, idx = none;
-      MGC(cudaMemcpyAsync(didx, &none, sizeof none, cudaMemcpyHostToDevice, s));
-      fused::k_find_interior<<<grid2d(l.ny, l.nx, blk), blk, 0, s>>>(l.msk, l.ny, l.nx, didx);
-      MGC(cudaMemcpyAsync(&idx, didx, sizeof idx, cudaMemcpyDeviceToHost, s));
-      MGC(cudaStreamSynchronize(s));
-      if (idx == none) continue;
-      for (int k = 0; k < 5; k++)
-        MGC(cudaMemcpyAsync(&l.cst[k], l.A + k * l.n() + idx, sizeof(double), cudaMemcpyDeviceToHost, s));
-      int flags[2] = {1, 1};
-      MGC(cudaMemcpyAsync(dflag, flags, sizeof flags, cudaMemcpyHostToDevice, s));
-      MGC(cudaStreamSynchronize(s));
-      fused::k_check_const<<<grid2d(l.ny, l.nx, blk), blk, 0, s>>>(level_k(mg, (int)lev), dflag);
-      MGC(cudaMemcpyAsync(flags, dflag, sizeof flags, cudaMemcpyDeviceToHost, s));
-      MGC(cudaStreamSynchronize(s));
-      g_launches += 2;
-      if (flags[0]) l.mode = flags[1] ? 1 : 2;
-    }
+    for (int g = 0; g < mg->lg; g++) TRY(detect_mode(mg, mg->S[g], dflag, didx, s));
+    for (auto &l : mg->L) TRY(detect_mode(mg, l, dflag, didx, s));
     cudaFree(dflag);
     cudaFree(didx);
     // the mask-free kernels also skip the coarse-mask tests of the transfers they fuse:
     // a level stays in class 1 only if the next coarser level is all fluid as well
     for (size_t lev = mg->L.size() - 1; lev-- > 0;)
       if (mg->L[lev].mode == 1 && mg->L[lev + 1].mode != 1) mg->L[lev].mode = 2;
+    for (int g = mg->lg - 1; g >= 0; g--) {
+      int coarse_mode = (g + 1 < mg->lg) ? mg->S[g + 1].mode : mg->L[0].mode;
+      if (mg->S[g].mode == 1 && coarse_mode != 1) mg->S[g].mode = 2;
+    }
   }
   if (const char *force = getenv("F2D_MG_FORCE_STORED"))
-    if (force[0] == '1')
+    if (force[0] == '1') {
       for (auto &l : mg->L) l.mode = 0;
+      for (auto &l : mg->S) l.mode = 0;
+    }
+  if (mg->lg >= 0 && !mg->S.empty()) {   // slab view of L[0]: same class, no local y wrap
+    Level &v = mg->S.back();
+    v.mode = mg->L[0].mode == 1 ? 1 : 0;
+    for (int k = 0; k < 5; k++) v.cst[k] = mg->L[0].cst[k];
+  }
   // shared-memory tail: the deepest levels whose interior is at most 64 wide
   {
     int t0 = (int)mg->L.size();
@@ -769,15 +838,80 @@ extern "C" int f2d_mg_create(f2d_mg_t **out, const double *cornermask, int ny, i
   }
   MGC(cudaStreamSynchronize(s));
   MGC(cudaGetLastError());
-#undef MGC
+  return F2D_OK;
+}
+
+// Gridinfo, single rank (level.py:62-93): halve (m, n) until n <= 4 or m <= 4
+int level_sizes(int m, int n, std::vector<std::pair<int, int>> &out) {
+  int lev = 0;
+  while (true) {
+    if (lev > 0) { n /= 2; m /= 2; }
+    out.push_back({m, n});
+    lev++;
+    if (n <= 4 || m <= 4) break;
+    if (lev > 20) return fail(F2D_ERR_ARG, "mg_create: too many levels");
+  }
+  return F2D_OK;
+}
+
+int common_init(f2d_mg *mg) {
+  MGC(cudaStreamCreateWithFlags(&mg->cap, cudaStreamNonBlocking));
+  MGC(cudaMalloc(&mg->scratch, f2d_reduce_scratch_len() * sizeof(double)));
+  MGC(cudaMalloc(&mg->dscal, 16 * sizeof(double)));
+  MGC(cudaMallocHost(&mg->hscal, 16 * sizeof(double)));
+  return F2D_OK;
+}
+
+}  // namespace
+
+extern "C" int f2d_mg_destroy(f2d_mg_t *mg);
+
+extern "C" int f2d_mg_create(f2d_mg_t **out, const double *cornermask, int ny, int nx, double dx, double dy,
+                             double omega, double hydroepsilon, double Rd, f2d_stream_t stream) {
+  if (!out || !cornermask) return fail(F2D_ERR_ARG, "mg_create: null pointer");
+  int m = ny - 2 * NH, n = nx - 2 * NH;
+  if (m < 4 || n < 4) return fail(F2D_ERR_ARG, "mg_create: grid too small");
+  if ((m & (m - 1)) || (n & (n - 1))) return fail(F2D_ERR_ARG, "mg_create: nx, ny must be powers of two");
+  if (hydroepsilon * dy / dx <= 0.2)
+    return fail(F2D_ERR_ARG, "mg_create: small aspect ratio needs the tridiagonal relaxation (not built yet)");
+  cudaStream_t s = S(stream);
+  f2d_mg *mg = new f2d_mg();
+  mg->omega = omega;
+  auto bail = [&](int rc) { f2d_mg_destroy(mg); return rc; };
+  std::vector<std::pair<int, int>> sizes;
+  int rc = level_sizes(m, n, sizes);
+  if (rc != F2D_OK) return bail(rc);
+  for (auto &sz : sizes) {
+    Level l;
+    l.ny = sz.first + 2 * NH;
+    l.nx = sz.second + 2 * NH;
+    mg->L.push_back(l);
+  }
+  if ((rc = common_init(mg)) != F2D_OK) return bail(rc);
+  for (auto &l : mg->L)
+    if ((rc = alloc_level(mg, l, false, s)) != F2D_OK) return bail(rc);
+  Level &l0 = mg->L[0];
+  double *A9 = nullptr;
+  if (cudaMalloc(&A9, 9 * l0.n() * sizeof(double)) != cudaSuccess) return bail(fail(F2D_ERR_CUDA, "mg_create: out of memory"));
+  dim3 blk(32, 8);
+  k_mask_from_double<<<nblocks1d(l0.n()), 256, 0, s>>>(cornermask, l0.msk, l0.n());
+  k_finest_matrix<<<grid2d(l0.ny, l0.nx, blk), blk, 0, s>>>(l0.msk, A9, finest_stencil(dx, dy, hydroepsilon), l0.ny, l0.nx);
+  g_launches += 2;
+  for (int k = 0; k < 9; k++)
+    if ((rc = f2d_fill_halo(A9 + k * l0.n(), NH, l0.ny, l0.nx, stream)) != F2D_OK) { cudaFree(A9); return bail(rc); }
+  if ((rc = build_replicated(mg, A9, true, s)) != F2D_OK) return bail(rc);
+  if ((rc = finish_setup(mg, Rd, s)) != F2D_OK) return bail(rc);
   *out = mg;
   return F2D_OK;
 }
+
+#include "f2d_mg_slab.cuh"
 
 extern "C" int f2d_mg_destroy(f2d_mg_t *mg) {
   if (!mg) return F2D_OK;
   for (auto &kv : mg->cache) cudaGraphExecDestroy(kv.second.exec);
   for (auto &l : mg->L) free_level(l);
+  for (auto &l : mg->S) free_level(l);
   cudaFree(mg->scratch);
   cudaFree(mg->dscal);
   if (mg->hscal) cudaFreeHost(mg->hscal);
@@ -786,16 +920,24 @@ extern "C" int f2d_mg_destroy(f2d_mg_t *mg) {
   return F2D_OK;
 }
 
-extern "C" int f2d_mg_nlevels(const f2d_mg_t *mg) { return mg ? (int)mg->L.size() : 0; }
+// global level g: slab level (g < lg) or level g - lg of the replicated hierarchy
+static Level *level_at(const f2d_mg_t *mg, int g) {
+  f2d_mg *m = const_cast<f2d_mg *>(mg);
+  if (!m || g < 0 || g >= m->lg + (int)m->L.size()) return nullptr;
+  return g < m->lg ? &m->S[g] : &m->L[g - m->lg];
+}
+extern "C" int f2d_mg_nlevels(const f2d_mg_t *mg) { return mg ? mg->lg + (int)mg->L.size() : 0; }
 extern "C" int f2d_mg_level_shape(const f2d_mg_t *mg, int lev, int *ny, int *nx) {
-  if (!mg || lev < 0 || lev >= (int)mg->L.size()) return fail(F2D_ERR_ARG, "mg_level_shape: bad level");
-  *ny = mg->L[lev].ny;
-  *nx = mg->L[lev].nx;
+  Level *l = level_at(mg, lev);
+  if (!l) return fail(F2D_ERR_ARG, "mg_level_shape: bad level");
+  *ny = l->ny;
+  *nx = l->nx;
   return F2D_OK;
 }
 extern "C" void *f2d_mg_level_ptr(f2d_mg_t *mg, int lev, int which) {
-  if (!mg || lev < 0 || lev >= (int)mg->L.size()) return nullptr;
-  Level &l = mg->L[lev];
+  Level *lp = level_at(mg, lev);
+  if (!lp) return nullptr;
+  Level &l = *lp;
   switch (which) {
     case 0: return l.msk;
     case 1: return l.A;
@@ -806,9 +948,11 @@ extern "C" void *f2d_mg_level_ptr(f2d_mg_t *mg, int lev, int which) {
   return nullptr;
 }
 extern "C" int f2d_mg_level_matrix_mode(const f2d_mg_t *mg, int lev) {
-  if (!mg || lev < 0 || lev >= (int)mg->L.size()) return -1;
-  return mg->L[lev].mode;
+  Level *l = level_at(mg, lev);
+  return l ? l->mode : -1;
 }
+/* number of distributed (slab) levels of a handle made by f2d_mg_create_slab */
+extern "C" int f2d_mg_slab_levels(const f2d_mg_t *mg) { return mg ? mg->lg : 0; }
 extern "C" int f2d_mg_set_graphs(f2d_mg_t *mg, int enable) {
   if (!mg) return fail(F2D_ERR_ARG, "mg_set_graphs: null");
   mg->graphs = enable != 0;
@@ -863,6 +1007,7 @@ extern "C" int f2d_mg_solve(f2d_mg_t *mg, double *psi, const double *rhs, double
                             double *res_out, f2d_stream_t stream) {
   if (!mg || !psi || !rhs) return fail(F2D_ERR_ARG, "mg_solve: null");
   cudaStream_t s = S(stream);
+  if (mg->comm) return slab_solve(mg, psi, rhs, tol, maxite, nite_out, res_out, s);
   Level &l = mg->L[0];
   TRY(f2d_computenorm(l.msk, rhs, NH, l.ny, l.nx, mg->dscal, mg->scratch, stream));
   TRY(op_resid_sumsq(mg, psi, rhs, l.b, mg->dscal + 1, s));
@@ -904,7 +1049,7 @@ extern "C" int f2d_invert_vorticity(f2d_mg_t *mg, const int8_t *msk, const int8_
                                     f2d_stream_t stream) {
   if (!mg || !msk || !mskp || !w || !psi || !u || !v || !work) return fail(F2D_ERR_ARG, "invert_vorticity: null");
   if (nh != NH) return fail(F2D_ERR_NH, "invert_vorticity: nh must be 3");
-  Level &l = mg->L[0];
+  Level &l = mg->comm ? mg->S[0] : mg->L[0];
   size_t n = l.n();
   TRY(f2d_celltocorner(w, work, l.ny, l.nx, stream));
   if (rhsp) TRY(f2d_add_scaled(work, -1., rhsp, n, stream));
@@ -913,6 +1058,7 @@ extern "C" int f2d_invert_vorticity(f2d_mg_t *mg, const int8_t *msk, const int8_
     if (perio) {
       if (!scratch) return fail(F2D_ERR_ARG, "invert_vorticity: scratch needed");
       TRY(f2d_domain_sum(psi, NH, l.ny, l.nx, mg->dscal + 2, scratch, stream));
+      if (mg->comm) TRY(comm_allreduce(mg->comm, mg->dscal + 2, 1, 0u, S(stream)));   // area is the global one
       TRY(f2d_sub_devscalar(psi, mg->dscal + 2, area, n, stream));
     }
   } else {

@@ -30,11 +30,12 @@ extern "C" int f2d_zero(void *dst, size_t nbytes, f2d_stream_t s) {
 // halo fill: one thread per halo cell, pulls from the periodic interior source
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void k_fill_halo(T *__restrict__ x, int ny, int nx, int nh) {
-  // halo cells: 2*nh full rows + (ny-2nh) rows x 2*nh columns
+__global__ void k_fill_halo(T *__restrict__ x, int ny, int nx, int nh, int ywrap) {
+  // halo cells: 2*nh full rows + (ny-2nh) rows x 2*nh columns; without ywrap (y-slab
+  // decomposition) only the side columns of the interior rows are local
   long long nrowcells = 2LL * nh * nx;
   long long total = nrowcells + 2LL * nh * (ny - 2 * nh);
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+  for (long long t = (ywrap ? 0 : nrowcells) + blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
     int j, i;
     if (t < nrowcells) {
@@ -53,14 +54,14 @@ __global__ void k_fill_halo(T *__restrict__ x, int ny, int nx, int nh) {
 }
 
 template <typename T>
-static int fill_halo_t(T *x, int nh, int ny, int nx, cudaStream_t s) {
+static int fill_halo_t(T *x, int nh, int ny, int nx, cudaStream_t s, int ywrap = 1) {
   if (!x || ny <= 2 * nh || nx <= 2 * nh || nh < 1) return fail(F2D_ERR_ARG, "fill_halo: bad shape");
   if (ny - 2 * nh < nh || nx - 2 * nh < nh) return fail(F2D_ERR_ARG, "fill_halo: interior narrower than halo");
   long long total = 2LL * nh * nx + 2LL * nh * (ny - 2 * nh);
   int threads = 256;
   int blocks = cdiv(total, threads);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  k_fill_halo<T><<<blocks, threads, 0, s>>>(x, ny, nx, nh);
+  k_fill_halo<T><<<blocks, threads, 0, s>>>(x, ny, nx, nh, ywrap);
   F2D_LAUNCHED();
   return F2D_OK;
 }
@@ -70,6 +71,9 @@ extern "C" int f2d_fill_halo(double *x, int nh, int ny, int nx, f2d_stream_t s) 
 }
 extern "C" int f2d_fill_halo_i8(int8_t *x, int nh, int ny, int nx, f2d_stream_t s) {
   return fill_halo_t<int8_t>(x, nh, ny, nx, S(s));
+}
+extern "C" int f2d_fill_halo_x(double *x, int nh, int ny, int nx, f2d_stream_t s) {
+  return fill_halo_t<double>(x, nh, ny, nx, S(s), 0);
 }
 
 // ---------------------------------------------------------------------------
@@ -178,6 +182,7 @@ extern "C" int f2d_add_diffusion(const int8_t *msk, const double *trac, double d
   dim3 b(32, 8);
   k_add_diffusion<<<grid2d(ny, nx, b), b, 0, S(s)>>>(msk, trac, Kdiff / (dx * dx), dtrac, ny, nx);
   F2D_LAUNCHED();
+  if (fill == 2) return f2d_fill_halo_x(dtrac, nh, ny, nx, s);
   if (fill) return f2d_fill_halo(dtrac, nh, ny, nx, s);
   return F2D_OK;
 }
@@ -207,6 +212,7 @@ extern "C" int f2d_add_torque(const int8_t *msk, const double *buoy, double dx, 
   dim3 b(32, 8);
   k_add_torque<<<grid2d(ny, nx, b), b, 0, S(s)>>>(msk, buoy, 0.5 * gravity / dx, domega, ny, nx, nh, premask);
   F2D_LAUNCHED();
+  if (fill == 2) return f2d_fill_halo_x(domega, nh, ny, nx, s);
   if (fill) return f2d_fill_halo(domega, nh, ny, nx, s);
   return F2D_OK;
 }

@@ -58,13 +58,17 @@ int f2d_zero(void *dst, size_t nbytes, f2d_stream_t stream);
  * doubly periodic halo fill, corners included */
 int f2d_fill_halo(double *x, int nh, int ny, int nx, f2d_stream_t stream);
 int f2d_fill_halo_i8(int8_t *x, int nh, int ny, int nx, f2d_stream_t stream);
+/* x images only (y-slab decomposition: the y halo rows come from f2d_comm_exchange_y) */
+int f2d_fill_halo_x(double *x, int nh, int ny, int nx, f2d_stream_t stream);
 
 /* ---- core/fortran_advection.f90:2-165 adv_upwind(msk,x,y,u,v,cst,nh,method,order)
  *      core/fortran_fluxes.f90:2-170 when xflx,yflx != NULL (face fluxes stored too)
  * dq(interior) = -div(U q); cst5 is a HOST array {dx,dy,0.05,umax,aparab}
  * (operators.py:99-119).  method 0 minmax / 1 parabolic; order 1,3,5.
- * fill_halo != 0 also performs the periodic halo fill of dq that Operators.rhs_adv
- * always does next (operators.py:231). */
+ * fill_halo = 1 also performs the periodic halo fill of dq that Operators.rhs_adv
+ * always does next (operators.py:231); fill_halo = 2 stores the x images only (y-slab
+ * decomposition: follow with f2d_comm_exchange_y).  Same convention for the other
+ * operators that take fill_halo. */
 int f2d_adv_upwind(const int8_t *msk, const double *q, double *dq, const double *u,
                    const double *v, double *xflx, double *yflx, const double *cst5,
                    int nh, int method, int order, int ny, int nx, int fill_halo,
@@ -261,6 +265,43 @@ int f2d_invert_vorticity(f2d_mg_t *mg, const int8_t *msk, const int8_t *mskp,
                          const double *rhsp, const double *psi_island, int full, int perio,
                          double area, double dx, double dy, int nh, int *nite, double *res,
                          double *scratch, f2d_stream_t stream);
+
+/* ---- multi-GPU: y-slab decomposition (npx = 1, npy = nranks), one process per GPU.
+ * Replaces the mpi4py layer: gmg/halo.py (8 persistent Send/Recv per fill),
+ * gmg/subdomains.py (Allgatherv gluing of coarse levels), level.py:401 (allreduce of
+ * norms), mpitools.py (allgather of diagnostics).
+ * Every rank creates a communicator with an arena of the same size; the 64-byte CUDA IPC
+ * handles are exchanged by the host (torch.distributed) and passed, rank-ordered, to
+ * f2d_comm_connect.  Buffers whose halos are exchanged must come from f2d_comm_alloc,
+ * called in the same order with the same sizes on every rank (symmetric heap). */
+typedef struct f2d_comm f2d_comm_t;
+int f2d_comm_create(f2d_comm_t **comm, int rank, int nranks, size_t arena_bytes,
+                    void *ipc_handle_out /* 64 bytes */);
+int f2d_comm_connect(f2d_comm_t *comm, const void *all_handles /* nranks x 64 bytes */);
+void *f2d_comm_alloc(f2d_comm_t *comm, size_t nbytes);
+int f2d_comm_rank(const f2d_comm_t *comm);
+int f2d_comm_size(const f2d_comm_t *comm);
+int f2d_comm_destroy(f2d_comm_t *comm);
+/* device-side barrier of all ranks (no host synchronisation) */
+int f2d_comm_barrier(f2d_comm_t *comm, f2d_stream_t stream);
+/* Halo.fill of the y direction (halo.py:214-292): push the nh top / bottom interior rows
+ * (full width) into the neighbours' halo rows over NVLink, then lock-step with them.
+ * With one rank it is the plain periodic fill. */
+int f2d_comm_exchange_y(f2d_comm_t *comm, double *x, int nh, int ny, int nx,
+                        f2d_stream_t stream);
+/* in-place all-reduce of n <= 32 DEVICE doubles (bit k of maxmask: max instead of sum),
+ * folded in rank order (deterministic); mpitools.py:16-40, level.py:401 */
+int f2d_comm_allreduce(f2d_comm_t *comm, double *vals, int n, unsigned int maxmask,
+                       f2d_stream_t stream);
+/* multigrid on slabs: the local corner-mask slab [ny_loc][nx]; levels with more than
+ * F2D_SLAB_MIN_CELLS (default 2^20) global cells stay distributed (halo rows exchanged
+ * after every operator), coarser levels are gathered onto every rank and computed
+ * redundantly (the reference's "peak" levels, level.py:71-86, taken to their end state).
+ * psi / rhs passed to the cycles must live in the symmetric heap. */
+int f2d_mg_slab_levels(const f2d_mg_t *mg);
+int f2d_mg_create_slab(f2d_mg_t **mg, f2d_comm_t *comm, const double *cornermask, int ny_loc,
+                       int nx, double dx, double dy, double omega, double hydroepsilon,
+                       double Rd, f2d_stream_t stream);
 
 #ifdef __cplusplus
 }

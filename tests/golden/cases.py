@@ -31,13 +31,16 @@ def _common(param, expname, datadir):
     param.tee_stdout = False   # (fluid2d_b200 extension: do not tee stdout into expdir)
 
 
-def freedecay(api, datadir, n=64, order=5, tracer=True, timestepping='RK3_SSP'):
+def freedecay(api, datadir, n=64, order=5, tracer=True, timestepping='RK3_SSP', ny=None, npy=1):
+    """ny != n gives a rectangular domain with dx = dy; npy > 1 splits it in y-slabs (one
+    rank per slab, like the reference run under mpirun with npx=1, npy=nranks)"""
     param = api.Param('default.xml')
     param.modelname = 'euler'
     _common(param, 'freedecay_%i' % n, datadir)
     param.nx = n
-    param.ny = n
-    param.Ly = param.Lx
+    param.ny = n if ny is None else ny
+    param.Ly = param.Lx*param.ny/param.nx
+    param.npy = npy
     param.geometry = 'perio'
     param.cfl = 1.2
     param.adaptable_dt = True
@@ -72,7 +75,9 @@ def freedecay(api, datadir, n=64, order=5, tracer=True, timestepping='RK3_SSP'):
     hnoise = np.exp(-(kk-k0)**2/(2*dk))*np.exp(1j*phase)
     noise = np.zeros_like(vor)
     nh = grid.nh
-    noise[nh:-nh, nh:-nh] = 1e3*np.real(np.fft.ifft2(hnoise))
+    field = 1e3*np.real(np.fft.ifft2(hnoise))     # the global field, identical on every rank
+    rows = param.ny//param.npy
+    noise[nh:-nh, nh:-nh] = field[grid.j0*rows:(grid.j0+1)*rows, :]
     grid.fill_halo(noise)
     vor[:] = noise
     if tracer:

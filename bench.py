@@ -94,10 +94,15 @@ class ClockSampler(object):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_case(api, n, tracers, datadir):
+def build_case(api, n, tracers, datadir, world=1):
+    """world > 1: weak scaling -- the global domain is n x (n*world), split in `world`
+    y-slabs of n x n cells (npx = 1, npy = world); the n x n freedecay field is repeated in
+    every slab (periodic tiling), so each GPU carries the single-GPU workload plus the halo
+    exchange with its neighbours"""
     import cases
-    f2d = cases.freedecay(api, datadir, n, order=5, tracer=(tracers > 1))
-    return f2d
+    if world == 1:
+        return cases.freedecay(api, datadir, n, order=5, tracer=(tracers > 1))
+    return cases.freedecay(api, datadir, n, order=5, tracer=(tracers > 1), ny=n*world, npy=world, tile=True)
 
 
 def loop_body(f2d):
@@ -171,6 +176,8 @@ def gpu_main(args):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl")
+    if args.replicas:
+        os.environ.pop("RANK", None)     # N independent single-GPU replicas (debug aid)
     import fluid2d_b200
     api = fluid2d_b200.api()
     from runtime import rt
@@ -180,7 +187,8 @@ def gpu_main(args):
     sys.stdout = sys.stderr
     n, T = args.n, args.tracers
     t0 = time.time()
-    f2d = build_case(api, n, T, tempfile.mkdtemp())
+    slabs = world > 1 and not args.replicas
+    f2d = build_case(api, n, T, tempfile.mkdtemp(), world if slabs else 1)
     model = f2d.model
     model.diagnostics(model.var, 0.)
     torch.cuda.synchronize()
@@ -218,7 +226,16 @@ def gpu_main(args):
 
     # ---- dominant kernel: the level-0 double Jacobi sweep (Grid.smooth), timed alone
     peak, peak_src = measured_peaks()
-    mgh = model.ope.gmg.h
+    if slabs:
+        # kernel-level numbers come from a single-GPU hierarchy of the slab's size on this rank
+        cm = torch.ones((n+6, n+6), dtype=torch.float64, device="cuda")
+        cm[-1, :] = 0
+        cm[:, -1] = 0
+        import ctypes
+        mgh = ctypes.c_void_p()
+        lib.mg_create(ctypes.byref(mgh), r.ptr(cm), n+6, n+6, 1./n, 1./n, 8./9., 1., 0., r.stream)
+    else:
+        mgh = model.ope.gmg.h
     x0 = torch.zeros((n+6, n+6), dtype=torch.float64, device="cuda")
     b0 = torch.randn((n+6, n+6), dtype=torch.float64, device="cuda")
     reps = 10
@@ -288,7 +305,10 @@ def gpu_main(args):
                                "upwind5 + parabolic splitting, 2 truncated MG inversions + full solve per step, "
                                "T=%d advected tracer(s)" % (n, n, T),
                    "grid": [n, n], "tracers": T, "n_F_mean": n_F,
-                   "parallelism": "single GPU" if world == 1 else "%d independent replicas (slab exchange not in this build)" % world,
+                   "parallelism": "single GPU" if world == 1 else (
+                       "%d y-slabs of %dx%d (global %dx%d), peer halo exchange over NVLink, coarse levels gathered"
+                       % (world, n, n, n, n*world) if slabs else "%d independent replicas" % world),
+                   "mg_slab_levels": getattr(model.ope.gmg, "slab_levels", 0),
                    "cache": "working set %.1f GB >> 126 MB L2 (no flush needed)" % (40*(n+6)**2*8/1e9)},
         "roofline": {"bound": "hbm", "kernel": "k_smooth2<0,0,0> (Grid.smooth = double Jacobi sweep + halo fill, level 0)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak,
@@ -318,6 +338,7 @@ def main():
     ap.add_argument("--n", type=int, default=4096)
     ap.add_argument("--tracers", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--replicas", action="store_true", help="N>1: independent replicas instead of slabs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -233,6 +233,11 @@ int comm_barrier(f2d_comm *c, int all, cudaStream_t s) {
 }
 // slab (interior rows) -> the same rows of every rank's replicated array `full` (symmetric address)
 int comm_gather(f2d_comm *c, const double *slab, double *full, int ny_loc, int nx, int nh, cudaStream_t s) {
+  // The replicated levels run without any synchronisation, so a fast rank could push the
+  // next cycle's data into `full` while a slow rank still reads the previous contents:
+  // all ranks first agree that everything enqueued before this gather has completed.
+  int rc = comm_barrier(c, 1, s);
+  if (rc != F2D_OK) return rc;
   char **d_arena = reinterpret_cast<char **>(c->d_ctrl + MAXRANKS);
   size_t off = reinterpret_cast<char *>(full) - c->base;
   int row0 = c->rank * (ny_loc - 2 * nh);

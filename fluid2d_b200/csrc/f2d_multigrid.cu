@@ -960,7 +960,8 @@ extern "C" int f2d_mg_set_graphs(f2d_mg_t *mg, int enable) {
 }
 
 #define CHECK_LEV(mg, lev, name)                                                       \
-  if (!(mg) || (lev) < 0 || (lev) >= (int)(mg)->L.size()) return fail(F2D_ERR_ARG, name ": bad handle/level")
+  if (!(mg) || (lev) < 0 || (lev) >= (int)(mg)->L.size()) return fail(F2D_ERR_ARG, name ": bad handle/level"); \
+  if ((mg)->comm) return fail(F2D_ERR_ARG, name ": the per-level entry points are not available on a slab hierarchy")
 
 extern "C" int f2d_mg_smooth(f2d_mg_t *mg, int lev, double *x, const double *b, int nite, f2d_stream_t s) {
   CHECK_LEV(mg, lev, "mg_smooth");

@@ -31,9 +31,10 @@ def _common(param, expname, datadir):
     param.tee_stdout = False   # (fluid2d_b200 extension: do not tee stdout into expdir)
 
 
-def freedecay(api, datadir, n=64, order=5, tracer=True, timestepping='RK3_SSP', ny=None, npy=1):
+def freedecay(api, datadir, n=64, order=5, tracer=True, timestepping='RK3_SSP', ny=None, npy=1, tile=False):
     """ny != n gives a rectangular domain with dx = dy; npy > 1 splits it in y-slabs (one
-    rank per slab, like the reference run under mpirun with npx=1, npy=nranks)"""
+    rank per slab, like the reference run under mpirun with npx=1, npy=nranks); tile=True
+    (needs ny = n*npy) repeats the n x n field in every slab instead of drawing a global one"""
     param = api.Param('default.xml')
     param.modelname = 'euler'
     _common(param, 'freedecay_%i' % n, datadir)
@@ -67,17 +68,19 @@ def freedecay(api, datadir, n=64, order=5, tracer=True, timestepping='RK3_SSP', 
         k = ((n//2+np.arange(n)) % n) - n//2
         return 2*np.pi*k/L
 
-    kkx, kky = np.meshgrid(wavenumbers(param.nx, np.pi), wavenumbers(param.ny, np.pi))
+    fny = param.nx if tile else param.ny
+    kkx, kky = np.meshgrid(wavenumbers(param.nx, np.pi), wavenumbers(fny, np.pi))
     kk = np.sqrt(kkx**2 + kky**2)
     k0 = param.nx*0.48
     dk = 1
-    phase = np.random.normal(size=(param.ny, param.nx))*2*np.pi
+    phase = np.random.normal(size=(fny, param.nx))*2*np.pi
     hnoise = np.exp(-(kk-k0)**2/(2*dk))*np.exp(1j*phase)
     noise = np.zeros_like(vor)
     nh = grid.nh
     field = 1e3*np.real(np.fft.ifft2(hnoise))     # the global field, identical on every rank
     rows = param.ny//param.npy
-    noise[nh:-nh, nh:-nh] = field[grid.j0*rows:(grid.j0+1)*rows, :]
+    j0 = 0 if tile else grid.j0
+    noise[nh:-nh, nh:-nh] = field[j0*rows:(j0+1)*rows, :]
     grid.fill_halo(noise)
     vor[:] = noise
     if tracer:

@@ -157,8 +157,17 @@ class Operators(Param):
         if self.comm is None:
             self.lib.fill_halo(ptr, self.nh, ny, nx, r.stream)
         else:
+            # the field was written whole (halo rows included) by this rank; a faster
+            # neighbour must not push its rows before that write has completed here
+            self.lib.comm_barrier(self.comm, r.stream)
             self.lib.fill_halo_x(ptr, self.nh, ny, nx, r.stream)
             self.lib.comm_exchange_y(self.comm, ptr, self.nh, ny, nx, r.stream)
+
+    def _barrier(self):
+        """device-side barrier of all ranks (no-op on one GPU): needed before an exchange of
+        a field whose halo rows this rank has just overwritten (memset, upload)"""
+        if self.comm is not None:
+            self.lib.comm_barrier(self.comm, self.rt.stream)
 
     def _xch(self, ptr):
         """y halo rows of a field whose producer used fill mode 2 (no-op on one GPU)"""

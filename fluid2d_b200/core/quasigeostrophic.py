@@ -61,6 +61,7 @@ class QG(object):
     def dynamics(self, x, t, dxdt):
         r, lib = self.rt, self.rt.lib
         lib.zero(dxdt.all_ptr(True), dxdt.size*8, r.stream)
+        self.ope._barrier()
         self.ope.rhs_adv(x, t, dxdt)
         if self.tscheme.kstage == self.tscheme.kforcing:
             if self.forcing:

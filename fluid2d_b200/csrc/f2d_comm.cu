@@ -335,6 +335,16 @@ extern "C" int f2d_comm_destroy(f2d_comm_t *c) {
 
 extern "C" int f2d_comm_barrier(f2d_comm_t *c, f2d_stream_t s) { return comm_barrier(c, 1, S(s)); }
 
+/* number of lock-step synchronisations this rank has completed (synchronises the device);
+ * equal on every rank at matching program points -- a debugging / test aid */
+extern "C" long long f2d_comm_epoch(f2d_comm_t *c) {
+  if (!c) return 0;
+  unsigned long long d = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpy(&d, &c->ctrl[c->rank]->done, sizeof d, cudaMemcpyDeviceToHost);
+  return (long long)d;
+}
+
 extern "C" int f2d_comm_exchange_y(f2d_comm_t *c, double *x, int nh, int ny, int nx, f2d_stream_t s) {
   if (!c || c->nranks == 1) return f2d_fill_halo(x, nh, ny, nx, s);
   double *arrs[1] = {x};

@@ -160,6 +160,7 @@ extern "C" int f2d_mg_create_slab(f2d_mg_t **out, f2d_comm_t *comm, const double
   cudaStream_t s = S(stream);
   f2d_mg *mg = new f2d_mg();
   mg->omega = omega;
+  if (const char *ng = getenv("F2D_MG_NO_GRAPHS")) mg->graphs = !(ng[0] == '1');
   mg->comm = comm;
   auto bail = [&](int rc) { f2d_mg_destroy(mg); return rc; };
   std::vector<std::pair<int, int>> sizes;   // global (m, n) per level

@@ -877,6 +877,7 @@ extern "C" int f2d_mg_create(f2d_mg_t **out, const double *cornermask, int ny, i
   cudaStream_t s = S(stream);
   f2d_mg *mg = new f2d_mg();
   mg->omega = omega;
+  if (const char *ng = getenv("F2D_MG_NO_GRAPHS")) mg->graphs = !(ng[0] == '1');
   auto bail = [&](int rc) { f2d_mg_destroy(mg); return rc; };
   std::vector<std::pair<int, int>> sizes;
   int rc = level_sizes(m, n, sizes);

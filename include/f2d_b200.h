@@ -282,6 +282,8 @@ void *f2d_comm_alloc(f2d_comm_t *comm, size_t nbytes);
 int f2d_comm_rank(const f2d_comm_t *comm);
 int f2d_comm_size(const f2d_comm_t *comm);
 int f2d_comm_destroy(f2d_comm_t *comm);
+/* lock-step synchronisations completed by this rank (debug / test aid; synchronises) */
+long long f2d_comm_epoch(f2d_comm_t *comm);
 /* device-side barrier of all ranks (no host synchronisation) */
 int f2d_comm_barrier(f2d_comm_t *comm, f2d_stream_t stream);
 /* Halo.fill of the y direction (halo.py:214-292): push the nh top / bottom interior rows

@@ -50,7 +50,19 @@ def main():
             n = np.linalg.norm(g[k][3:-3])
             e = np.linalg.norm(gstate[k][3:-3]-g[k][3:-3])/(n if n > 0 else 1.)
             report["errors"]["%s:%s" % (tag, nm)] = float(e)
+            if e > 1e-10 and tag == "state0":
+                d = np.abs(gstate[k]-g[k])
+                report.setdefault("detail", {})[nm] = {
+                    "rowmax": [float(x) for x in d.max(axis=1)[::8]], "mean_diff": float((gstate[k]-g[k])[3:-3, 3:-3].mean()),
+                    "ref_absmax": float(np.abs(g[k]).max())}
 
+    report["solve0"] = list(model.ope.last_solve)
+    report["modes"] = [g.matrix_mode for g in model.ope.gmg.grid]
+    from runtime import rt
+    ep = torch.tensor([rt().lib.comm_epoch(rt().comm)], dtype=torch.int64, device="cuda")
+    eps = [torch.zeros_like(ep) for _ in range(world)]
+    dist.all_gather(eps, ep)
+    report["epochs_after_setup"] = [int(e.item()) for e in eps]
     g0 = gather_global(np.array(model.var.state), 3, world)
     if rank == 0:
         compare("state0", g0)

@@ -43,6 +43,7 @@ def test_two_slabs_match_single_gpu(nx, ny, min_cells):
     d = tempfile.mkdtemp()
     f2d = cases.freedecay(api, d, nx, ny=ny)
     ref = {"state0": np.array(f2d.model.var.state)}
+    print("single-GPU solve:", f2d.model.ope.last_solve)
     res = cases.run_steps(f2d, (1, nsteps))
     for k in (1, nsteps):
         ref["state%d" % k] = res[k][0]

@@ -60,7 +60,8 @@ if rank == 0:
     L.mg_create(ctypes.byref(h1), ptr(torch.from_numpy(cm).cuda()), ny+6, nx+6, 1./nx, 1./nx, 8./9., 1., 0., s)
     p1 = torch.from_numpy(Ph.copy()).cuda(); r1 = torch.from_numpy(Gh.copy()).cuda()
 
-for step in ("two_vcycle", "two_vcycle", "solve"):
+order = sys.argv[3].split(",") if len(sys.argv) > 3 else ["two_vcycle", "two_vcycle", "solve"]
+for step in order:
     nite, res = ctypes.c_int(), ctypes.c_double()
     if step == "two_vcycle":
         L.mg_two_vcycle(h, ptr(psi), ptr(rhs), s)

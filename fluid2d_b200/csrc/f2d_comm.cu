@@ -21,20 +21,6 @@
 
 using namespace f2d;
 
-namespace {
-constexpr int MAXRANKS = 16;
-constexpr int RED_SLOTS = 32;
-
-struct Ctrl {
-  unsigned long long done;                 // exchanges/barriers completed by this rank
-  unsigned long long slot[MAXRANKS];       // slot[r]: last epoch published here by rank r
-  unsigned int blocks_done;                // last-block detection of the current kernel
-  unsigned int pad;
-  double red[2][MAXRANKS][RED_SLOTS];      // all-reduce staging, double buffered
-  unsigned long long red_epoch;
-};
-}  // namespace
-
 struct f2d_comm {
   int rank = 0, nranks = 1;
   size_t arena_bytes = 0, used = 0;
@@ -52,23 +38,17 @@ __device__ __forceinline__ void publish_and_wait(Ctrl *me, Ctrl *const *peers, i
   unsigned long long D = me->done + 1;
   me->done = D;
   int north = (rank + 1) % nranks, south = (rank + nranks - 1) % nranks;
-  if (all) {
-    for (int r = 0; r < nranks; r++)
-      if (r != rank) *((volatile unsigned long long *)&peers[r]->slot[rank]) = D;
-  } else {
-    *((volatile unsigned long long *)&peers[north]->slot[rank]) = D;
-    if (south != north) *((volatile unsigned long long *)&peers[south]->slot[rank]) = D;
-  }
-  __threadfence_system();
+  // always published to every rank: slot[r] tracks rank r's progress everywhere
+  for (int r = 0; r < nranks; r++)
+    if (r != rank) *((volatile unsigned long long *)&peers[r]->slot[rank]) = D;
   if (all) {
     for (int r = 0; r < nranks; r++)
       if (r != rank)
-        while (*((volatile unsigned long long *)&me->slot[r]) < D) {}
+        while (ld_acquire_sys(&me->slot[r]) < D) {}
   } else {
-    while (*((volatile unsigned long long *)&me->slot[north]) < D) {}
-    while (*((volatile unsigned long long *)&me->slot[south]) < D) {}
+    while (ld_acquire_sys(&me->slot[north]) < D) {}
+    while (ld_acquire_sys(&me->slot[south]) < D) {}
   }
-  __threadfence_system();
 }
 
 struct XchArgs {
@@ -79,6 +59,15 @@ struct XchArgs {
 // push my top interior rows into north's bottom halo and my bottom interior rows into
 // south's top halo (all arrays of `a`), then lock-step with both neighbours
 __global__ void k_exchange_y(XchArgs a, Ctrl *me, Ctrl *const *peers, int rank, int nranks) {
+  // the fused kernels publish without waiting: before storing into a neighbour make sure
+  // it has completed every synchronising kernel this rank has (no reader of the old halo)
+  if (threadIdx.x == 0) {
+    const unsigned long long d = *((volatile unsigned long long *)&me->done);
+    const int rn = (rank + 1) % nranks, rs = (rank + nranks - 1) % nranks;
+    while (ld_acquire_sys(&me->slot[rs]) < d) {}
+    while (ld_acquire_sys(&me->slot[rn]) < d) {}
+  }
+  __syncthreads();
   const size_t rowlen = (size_t)a.nx;
   const size_t per = (size_t)a.nh * rowlen;          // elements of one 3-row strip
   const size_t total = 2 * per * a.narr;
@@ -92,14 +81,25 @@ __global__ void k_exchange_y(XchArgs a, Ctrl *me, Ctrl *const *peers, int rank, 
     else
       a.south[arr][(size_t)(a.ny - a.nh) * rowlen + e] = a.self[arr][(size_t)a.nh * rowlen + e];  // -> rows ny-nh..
   }
-  __threadfence_system();
-  __syncthreads();
+  __syncthreads();   // the block's stores happen-before thread 0's system fence (cumulativity)
   if (threadIdx.x == 0) {
+    __threadfence_system();
     unsigned int t = atomicAdd(&me->blocks_done, 1u);
     if (t == gridDim.x - 1) {
       me->blocks_done = 0;
       publish_and_wait(me, peers, rank, nranks, 0);
     }
+  }
+}
+
+// wait (without publishing) until both neighbours have caught up: placed before kernels
+// that read halo rows but do not take part in the protocol themselves
+__global__ void k_drain(Ctrl *me, int rank, int nranks) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const unsigned long long d = *((volatile unsigned long long *)&me->done);
+    const int rn = (rank + 1) % nranks, rs = (rank + nranks - 1) % nranks;
+    while (ld_acquire_sys(&me->slot[rs]) < d) {}
+    while (ld_acquire_sys(&me->slot[rn]) < d) {}
   }
 }
 
@@ -140,6 +140,15 @@ __global__ void k_allreduce(double *vals, int n, unsigned maxmask, Ctrl *me, Ctr
 __global__ void k_gather_push(const double *slab, int ny_loc, int nx, int nh, size_t full_off /*bytes from arena base*/,
                               int row0 /*first global interior row of my slab*/, char *const *arena, Ctrl *me,
                               Ctrl *const *peers, int rank, int nranks) {
+  // no rank may still be reading the previous contents of `full`: every rank must have
+  // completed the synchronising kernels this rank has (see comm_gather)
+  if (threadIdx.x == 0) {
+    const unsigned long long d = *((volatile unsigned long long *)&me->done);
+    for (int r = 0; r < nranks; r++)
+      if (r != rank)
+        while (ld_acquire_sys(&me->slot[r]) < d) {}
+  }
+  __syncthreads();
   const int nrows = ny_loc - 2 * nh;
   const size_t total = (size_t)nrows * nx;
   for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
@@ -148,9 +157,9 @@ __global__ void k_gather_push(const double *slab, int ny_loc, int nx, int nh, si
     size_t dst = (size_t)(nh + row0 + r) * nx + c;
     for (int k = 0; k < nranks; k++) reinterpret_cast<double *>(arena[k] + full_off)[dst] = v;
   }
-  __threadfence_system();
-  __syncthreads();
+  __syncthreads();   // the block's stores happen-before thread 0's system fence (cumulativity)
   if (threadIdx.x == 0) {
+    __threadfence_system();
     unsigned int t = atomicAdd(&me->blocks_done, 1u);
     if (t == gridDim.x - 1) {
       me->blocks_done = 0;
@@ -162,6 +171,15 @@ __global__ void k_gather_push(const double *slab, int ny_loc, int nx, int nh, si
 // so the first / last rank also contribute their outer halo rows
 __global__ void k_gather_push_i8(const int8_t *slab, int ny_loc, int nx, int nh, size_t full_off, int row0,
                                  char *const *arena, Ctrl *me, Ctrl *const *peers, int rank, int nranks) {
+  // no rank may still be reading the previous contents of `full`: every rank must have
+  // completed the synchronising kernels this rank has (see comm_gather)
+  if (threadIdx.x == 0) {
+    const unsigned long long d = *((volatile unsigned long long *)&me->done);
+    for (int r = 0; r < nranks; r++)
+      if (r != rank)
+        while (ld_acquire_sys(&me->slot[r]) < d) {}
+  }
+  __syncthreads();
   const int nrows = ny_loc - 2 * nh;
   const int rlo = rank == 0 ? -nh : 0, rhi = rank == nranks - 1 ? nrows + nh : nrows;
   const size_t total = (size_t)(rhi - rlo) * nx;
@@ -171,9 +189,9 @@ __global__ void k_gather_push_i8(const int8_t *slab, int ny_loc, int nx, int nh,
     size_t dst = (size_t)(nh + row0 + r) * nx + c;
     for (int k = 0; k < nranks; k++) reinterpret_cast<int8_t *>(arena[k] + full_off)[dst] = v;
   }
-  __threadfence_system();
-  __syncthreads();
+  __syncthreads();   // the block's stores happen-before thread 0's system fence (cumulativity)
   if (threadIdx.x == 0) {
+    __threadfence_system();
     unsigned int t = atomicAdd(&me->blocks_done, 1u);
     if (t == gridDim.x - 1) {
       me->blocks_done = 0;
@@ -232,12 +250,18 @@ int comm_barrier(f2d_comm *c, int all, cudaStream_t s) {
   return F2D_OK;
 }
 // slab (interior rows) -> the same rows of every rank's replicated array `full` (symmetric address)
-int comm_gather(f2d_comm *c, const double *slab, double *full, int ny_loc, int nx, int nh, cudaStream_t s) {
+int comm_gather(f2d_comm *c, const double *slab, double *full, int ny_loc, int nx, int nh, cudaStream_t s,
+                bool barrier_first) {
   // The replicated levels run without any synchronisation, so a fast rank could push the
-  // next cycle's data into `full` while a slow rank still reads the previous contents:
-  // all ranks first agree that everything enqueued before this gather has completed.
-  int rc = comm_barrier(c, 1, s);
-  if (rc != F2D_OK) return rc;
+  // next cycle's data into `full` while a slow rank still reads the previous contents.
+  // The push kernel first waits until every rank has completed the synchronising kernels
+  // this rank has; that is enough when at least one such kernel separates the readers of
+  // `full` from this gather (slab levels above the gather level).  Otherwise
+  // (barrier_first) all ranks first agree that everything enqueued so far has completed.
+  if (barrier_first) {
+    int rc = comm_barrier(c, 1, s);
+    if (rc != F2D_OK) return rc;
+  }
   char **d_arena = reinterpret_cast<char **>(c->d_ctrl + MAXRANKS);
   size_t off = reinterpret_cast<char *>(full) - c->base;
   int row0 = c->rank * (ny_loc - 2 * nh);
@@ -258,6 +282,25 @@ int comm_gather_i8(f2d_comm *c, const int8_t *slab, int8_t *full, int ny_loc, in
   if (blocks > 128) blocks = 128;
   k_gather_push_i8<<<blocks, 256, 0, s>>>(slab, ny_loc, nx, nh, off, row0, d_arena, c->ctrl[c->rank], c->d_ctrl,
                                           c->rank, c->nranks);
+  F2D_LAUNCHED();
+  return F2D_OK;
+}
+Peer comm_peer(const f2d_comm *c) {
+  Peer P;
+  P.me = nullptr; P.peers = nullptr; P.north_off = P.south_off = 0; P.rank = 0; P.nranks = 1;
+  if (!c || c->nranks == 1) return P;
+  int north = (c->rank + 1) % c->nranks, south = (c->rank + c->nranks - 1) % c->nranks;
+  P.me = c->ctrl[c->rank];
+  P.peers = c->d_ctrl;
+  P.north_off = (long long)((intptr_t)c->peer[north] - (intptr_t)c->base);
+  P.south_off = (long long)((intptr_t)c->peer[south] - (intptr_t)c->base);
+  P.rank = c->rank;
+  P.nranks = c->nranks;
+  return P;
+}
+int comm_drain(f2d_comm *c, cudaStream_t s) {
+  if (!c || c->nranks == 1) return F2D_OK;
+  k_drain<<<1, 32, 0, s>>>(c->ctrl[c->rank], c->rank, c->nranks);
   F2D_LAUNCHED();
   return F2D_OK;
 }

@@ -200,15 +200,24 @@ __device__ __forceinline__ void jacobi_strip(const LevelK &L, const Coefs<MASKED
 }
 
 // INPUT: 0 xin, 1 zero, 2 I(xc), 3 xin + I(xc)
-template <bool MASKED, bool STORED, int INPUT>
+// PEER (y-slab levels on several GPUs): the tiles of the first / last tile row wait for the
+// neighbouring rank's epoch before reading halo rows, store their 3 outermost rows into the
+// neighbour's halo rows as well (peer stores), and the last of them publishes the epoch --
+// the halo exchange of the reference (halo.fill after every smooth) without a kernel of
+// its own, overlapped with the interior tiles.
+template <bool MASKED, bool STORED, int INPUT, bool PEER>
 __global__ void __launch_bounds__(NT)
 k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b, double *__restrict__ xout,
-          const double *__restrict__ xc, const int8_t *__restrict__ mskc, int nxc, int nyc, double *acc) {
+          const double *__restrict__ xc, const int8_t *__restrict__ mskc, int nxc, int nyc, double *acc,
+          f2d::Peer P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smooth2Smem &S = *reinterpret_cast<Smooth2Smem *>(smem_raw);
   const int ny = L.ny, nx = L.nx;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int i0 = NH + blockIdx.x * TX, j0 = NH + blockIdx.y * TY;
+  const int by = PEER ? f2d::peer_tile_row(blockIdx.y, gridDim.y) : blockIdx.y;
+  const bool bsouth = PEER && by == 0, bnorth = PEER && by == (int)gridDim.y - 1;
+  if (PEER && (bsouth || bnorth)) f2d::peer_wait(P, bsouth, bnorth);
+  const int i0 = NH + blockIdx.x * TX, j0 = NH + by * TY;
   constexpr bool INTERP = INPUT >= 2;
   constexpr bool HAVE_X = (INPUT == 0 || INPUT == 3);
   constexpr bool ZERO = INPUT == 1;
@@ -308,16 +317,33 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
     double *base = acc ? acc : xout;
     double *dst = base + (size_t)j * nx + i;
     const bool accum = acc != nullptr;
+    double *bsouth_p = PEER ? f2d::peer_addr(base, P.south_off) : nullptr;
+    double *bnorth_p = PEER ? f2d::peer_addr(base, P.north_off) : nullptr;
+    const int m2 = ny - 2 * NH;
     auto out = [&](int k, double val) {
       double *d = dst + (size_t)k * nx;
       // solve(): `x += self.x[0]` (hierarchy.py:171) fused into the last kernel of the
       // F-cycle: the correction is added to psi (acc) instead of being stored
-      *d = accum ? *d + val : val;
+      const double nv = accum ? *d + val : val;
+      *d = nv;
       if (rim)
         f2d::for_each_halo_image(j + k, i, ny, nx, NH, [&](int j2, int i2) {
           double *e = base + (size_t)j2 * nx + i2;
           *e = accum ? *e + val : val;
         }, L.ywrap != 0);
+      if (PEER) {
+        // rows NH..2NH-1 are the south rank's top halo, rows m2..m2+NH-1 the north rank's
+        // bottom halo (x images included, so the corners arrive too)
+        const int jr = j + k;
+        if (bsouth && jr < 2 * NH) {
+          bsouth_p[(size_t)(jr + m2) * nx + i] = nv;
+          f2d::for_each_halo_image(jr + m2, i, ny, nx, NH, [&](int j2, int i2) { bsouth_p[(size_t)j2 * nx + i2] = nv; }, false);
+        }
+        if (bnorth && jr >= m2) {
+          bnorth_p[(size_t)(jr - m2) * nx + i] = nv;
+          f2d::for_each_halo_image(jr - m2, i, ny, nx, NH, [&](int j2, int i2) { bnorth_p[(size_t)j2 * nx + i2] = nv; }, false);
+        }
+      }
     };
     const double *sp = &S.y1[r0 + 1][tx + 1];
     const double *bp = &S.bs[r0 + 1][tx + 1];
@@ -327,6 +353,7 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
     else
       jacobi_strip<MASKED, STORED, false, true, 8, YW, YW, XW>(L, kc, sp, bp, mp, 8, j, i, NH, out);
   }
+  if (PEER && (bsouth || bnorth)) f2d::peer_done(P, gridDim.x * (gridDim.y == 1 ? 1u : 2u));
 }
 
 // ---------------------------------------------------------------------------
@@ -393,15 +420,18 @@ __device__ __forceinline__ void resid_strip(const LevelK &L, const Coefs<MASKED,
   }
 }
 
-template <bool MASKED, bool STORED>
+template <bool MASKED, bool STORED, bool PEER>
 __global__ void __launch_bounds__(NT)
 k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ bc,
-                 const int8_t *__restrict__ mskc, int nyc, int nxc) {
+                 const int8_t *__restrict__ mskc, int nyc, int nxc, f2d::Peer P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ResidSmem &S = *reinterpret_cast<ResidSmem *>(smem_raw);
   const int ny = L.ny, nx = L.nx;
   const int t = threadIdx.x;
-  const int ci0 = NH + blockIdx.x * RTX, cj0 = NH + blockIdx.y * RTY;  // first coarse output
+  const int by = PEER ? f2d::peer_tile_row(blockIdx.y, gridDim.y) : blockIdx.y;
+  const bool bsouth = PEER && by == 0, bnorth = PEER && by == (int)gridDim.y - 1;
+  if (PEER && (bsouth || bnorth)) f2d::peer_wait(P, bsouth, bnorth);
+  const int ci0 = NH + blockIdx.x * RTX, cj0 = NH + by * RTY;  // first coarse output
   const int fi0 = 2 * ci0 - 3, fj0 = 2 * cj0 - 3;                      // first fine residual point
   // inner tile: the whole residual tile lies strictly inside the fine interior
   const bool inner = (fj0 + RH <= ny - NH) && (fi0 + RW <= nx - NH);
@@ -458,7 +488,21 @@ k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restric
     if (rim)
       f2d::for_each_halo_image(j, i, nyc, nxc, NH, [&](int jj, int ii) { bc[(size_t)jj * nxc + ii] = val; },
                                L.ywrap != 0);
+    if (PEER) {
+      const int m2c = nyc - 2 * NH;
+      if (bsouth && j < 2 * NH) {
+        double *q2 = f2d::peer_addr(bc, P.south_off);
+        q2[(size_t)(j + m2c) * nxc + i] = val;
+        f2d::for_each_halo_image(j + m2c, i, nyc, nxc, NH, [&](int jj, int ii) { q2[(size_t)jj * nxc + ii] = val; }, false);
+      }
+      if (bnorth && j >= m2c) {
+        double *q2 = f2d::peer_addr(bc, P.north_off);
+        q2[(size_t)(j - m2c) * nxc + i] = val;
+        f2d::for_each_halo_image(j - m2c, i, nyc, nxc, NH, [&](int jj, int ii) { q2[(size_t)jj * nxc + ii] = val; }, false);
+      }
+    }
   }
+  if (PEER && (bsouth || bnorth)) f2d::peer_done(P, gridDim.x * (gridDim.y == 1 ? 1u : 2u));
 }
 
 // ---------------------------------------------------------------------------

@@ -29,7 +29,8 @@ inline int xch1(f2d_mg *mg, Level &l, double *x, cudaStream_t s) {
 int gather_to_full(f2d_mg *mg, const double *slab, double *full, cudaStream_t s) {
   Level &v = mg->S[mg->lg];
   Level &f = mg->L[0];
-  TRY(comm_gather(mg->comm, slab, full, v.ny, v.nx, NH, s));
+  // lg == 0: nothing but gathers between two uses of `full` -> explicit barrier first
+  TRY(comm_gather(mg->comm, slab, full, v.ny, v.nx, NH, s, mg->lg == 0));
   return f2d_fill_halo(full, NH, f.ny, f.nx, (f2d_stream_t)s);
 }
 int scatter_from_full(f2d_mg *mg, const double *full, double *slab, cudaStream_t s) {
@@ -41,17 +42,19 @@ int scatter_from_full(f2d_mg *mg, const double *full, double *slab, cudaStream_t
 }
 
 // V-cycle from slab level lev1 <= lg (hierarchy.py:98-127); x0/b0 are slab arrays of lev1
-int slab_vcycle(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s, int first_input = 0) {
+// acc != nullptr (lg >= 1): the last smoother adds its result to acc (psi) instead of storing x0
+int slab_vcycle(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s, int first_input = 0,
+                double *acc = nullptr) {
   const int lg = mg->lg;
   auto X = [&](int g) { return g == lev1 ? x0 : mg->S[g].x; };
   auto B = [&](int g) { return g == lev1 ? b0 : mg->S[g].b; };
   for (int g = lev1; g < lg; g++) {
     Level &l = mg->S[g], &c = mg->S[g + 1];
     int input = g > lev1 ? 1 : first_input;
+    // the smoother and the residual/restriction kernels fill the neighbours' halo rows of
+    // their outputs themselves (fused::k_smooth2<..., PEER>): no exchange kernels here
     TRY(smooth2_L(mg, l, &c, input, X(g), B(g), l.t, input == 2 ? X(g + 1) : nullptr, s));
-    TRY(xch1(mg, l, l.t, s));
     TRY(op_resid_restrict_L(mg, l, c, l.t, B(g), B(g + 1), s));
-    if (g + 1 < lg) TRY(xch1(mg, c, B(g + 1), s));
   }
   // levels >= lg: gathered, then the replicated single-GPU cycle
   Level &f = mg->L[0];
@@ -67,40 +70,46 @@ int slab_vcycle(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s, in
   TRY(scatter_from_full(mg, f.x, X(lg), s));
   for (int g = lg - 1; g >= lev1; g--) {
     Level &l = mg->S[g], &c = mg->S[g + 1];
-    TRY(smooth2_L(mg, l, &c, 3, l.t, B(g), X(g), X(g + 1), s));
-    TRY(xch1(mg, l, X(g), s));
+    TRY(smooth2_L(mg, l, &c, 3, l.t, B(g), X(g), X(g + 1), s, g == lev1 ? acc : nullptr));
   }
   return F2D_OK;
 }
 
 // F-cycle from slab level 0 (hierarchy.py:131-151)
-int slab_fcycle(f2d_mg *mg, double *x0, double *b0, cudaStream_t s) {
+int slab_fcycle(f2d_mg *mg, double *x0, double *b0, cudaStream_t s, double *acc = nullptr) {
   const int lg = mg->lg;
   auto X = [&](int g) { return g == 0 ? x0 : mg->S[g].x; };
   auto B = [&](int g) { return g == 0 ? b0 : mg->S[g].b; };
   for (int g = 0; g < lg; g++) {
-    TRY(op_restrict_L(mg, mg->S[g], mg->S[g + 1], B(g), B(g + 1), s));
-    if (g + 1 < lg) TRY(xch1(mg, mg->S[g + 1], B(g + 1), s));
+    TRY(op_restrict_L(mg, mg->S[g], mg->S[g + 1], B(g), B(g + 1), s));   // fills the neighbours' halo rows itself
   }
   Level &f = mg->L[0];
   TRY(gather_to_full(mg, B(lg), f.b, s));
   TRY(fcycle_enqueue(mg, 0, f.x, f.b, s));
   TRY(scatter_from_full(mg, f.x, X(lg), s));
   for (int g = lg - 1; g >= 0; g--)
-    for (int k = 0; k < mg->nvcyc; k++) TRY(slab_vcycle(mg, g, X(g), B(g), s, k == 0 ? 2 : 0));
+    for (int k = 0; k < mg->nvcyc; k++)
+      TRY(slab_vcycle(mg, g, X(g), B(g), s, k == 0 ? 2 : 0, (g == 0 && k == mg->nvcyc - 1) ? acc : nullptr));
   return F2D_OK;
 }
 
-int slab_cycle_enqueue(f2d_mg *mg, int kind, int lev1, double *x0, double *b0, cudaStream_t s) {
+int slab_cycle_enqueue(f2d_mg *mg, int kind, int lev1, double *x0, double *b0, cudaStream_t s, double *acc) {
   if (lev1 != 0) return fail(F2D_ERR_ARG, "slab multigrid: cycles start from level 0");
   if (!comm_owns(mg->comm, x0))
     return fail(F2D_ERR_ARG, "slab multigrid: psi must live in the symmetric heap (f2d_comm_alloc)");
   if (kind == 0) {
     TRY(slab_vcycle(mg, 0, x0, b0, s));
-    return slab_vcycle(mg, 0, x0, b0, s);
+    TRY(slab_vcycle(mg, 0, x0, b0, s));
+  } else if (kind == 1) {
+    if (acc && (mg->lg == 0 || !comm_owns(mg->comm, acc)))
+      return fail(F2D_ERR_ARG, "slab multigrid: fused accumulation needs a slab level and psi in the symmetric heap");
+    TRY(slab_fcycle(mg, x0, b0, s, acc));
+  } else {
+    TRY(slab_vcycle(mg, 0, x0, b0, s));
   }
-  if (kind == 1) return slab_fcycle(mg, x0, b0, s);
-  return slab_vcycle(mg, 0, x0, b0, s);
+  // the last smoother published its halo rows without waiting: kernels outside the
+  // protocol (psi += x, the velocity operators) read them, so wait for the neighbours here
+  return comm_drain(mg->comm, s);
 }
 
 // Gmg.solve on slabs (hierarchy.py:154-192): norms are all-reduced, so every rank takes
@@ -123,10 +132,13 @@ int slab_solve(f2d_mg *mg, double *psi, const double *rhs, double tol, int maxit
     double res0 = sqrt(mg->hscal[1]) / normb;
     res = res0;
     int ndiv = 0;
+    const bool fuse_add = mg->lg >= 1;   // `x += self.x[0]` done by the F-cycle's last kernel
     while (nite < maxite && res0 > tol) {
-      TRY(run_cycle(mg, 1, 0, l.x, l.b, s));
-      k_add_inplace<<<nblocks1d(l.n()), 256, 0, s>>>(psi, l.x, l.n());
-      F2D_LAUNCHED();
+      TRY(run_cycle(mg, 1, 0, l.x, l.b, s, fuse_add ? psi : nullptr));
+      if (!fuse_add) {
+        k_add_inplace<<<nblocks1d(l.n()), 256, 0, s>>>(psi, l.x, l.n());
+        F2D_LAUNCHED();
+      }
       TRY(op_resid_sumsq_L(mg, l, psi, rhs, l.b, mg->dscal + 1, s));
       TRY(xch1(mg, l, l.b, s));
       TRY(comm_allreduce(mg->comm, mg->dscal + 1, 1, 0u, s));

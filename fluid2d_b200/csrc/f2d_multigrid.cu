@@ -122,10 +122,30 @@ __global__ void k_residual(const int8_t *__restrict__ msk, const double *__restr
 
 // full-weighting restriction on the coarse interior + halo images
 // (fortran_multigrid.f90:501-546 + fill); msk2 == nullptr means all ones
+// PEER: y-slab levels -- the block rows holding the 3 bottom / top interior rows also fill
+// the neighbouring ranks' halo rows (see f2d::Peer)
+template <bool PEER>
 __global__ void k_restrict(const int8_t *__restrict__ msk2, const double *__restrict__ x1, double *__restrict__ x2,
-                           int ny, int nx /*coarse*/, int nx1, int ywrap = 1) {
-  IJ2();
-  if (j < NH || j > ny - 1 - NH || i < NH || i > nx - 1 - NH) return;
+                           int ny, int nx /*coarse*/, int nx1, int ywrap, f2d::Peer P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const size_t c = (size_t)j * nx + i;
+  const int m2 = ny - 2 * NH;
+  const int rown = m2 / (int)blockDim.y;   // block row of the top interior rows m2..m2+NH-1
+  const bool bsouth = PEER && blockIdx.y == 0, bnorth = PEER && (int)blockIdx.y == rown;
+  if (PEER && (bsouth || bnorth)) {
+    // peer_wait / peer_done use threadIdx.x == 0 as the CTA's leader: 2-D blocks here
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+      const unsigned long long d = *((volatile unsigned long long *)&P.me->done);
+      const int rn = (P.rank + 1) % P.nranks, rs = (P.rank + P.nranks - 1) % P.nranks;
+      if (bsouth) while (f2d::ld_acquire_sys(&P.me->slot[rs]) < d) {}
+      if (bnorth) while (f2d::ld_acquire_sys(&P.me->slot[rn]) < d) {}
+    }
+    __syncthreads();
+  }
+  const bool inside = !(j < NH || j > ny - 1 - NH || i < NH || i > nx - 1 - NH);
+  if (!PEER && !inside) return;
+  if (inside) {
   double val = 0.;
   if (!msk2 || msk2[c] != 0) {
     // coarse 0-based J2 <-> fine 0-based J1 = 2*J2 - 2
@@ -136,6 +156,35 @@ __global__ void k_restrict(const int8_t *__restrict__ msk2, const double *__rest
   }
   x2[c] = val;
   for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { x2[(size_t)jj * nx + ii] = val; }, ywrap != 0);
+  if (PEER) {
+    if (j < 2 * NH) {
+      double *q = f2d::peer_addr(x2, P.south_off);
+      q[(size_t)(j + m2) * nx + i] = val;
+      for_each_halo_image(j + m2, i, ny, nx, NH, [&](int jj, int ii) { q[(size_t)jj * nx + ii] = val; }, false);
+    }
+    if (j >= m2) {
+      double *q = f2d::peer_addr(x2, P.north_off);
+      q[(size_t)(j - m2) * nx + i] = val;
+      for_each_halo_image(j - m2, i, ny, nx, NH, [&](int jj, int ii) { q[(size_t)jj * nx + ii] = val; }, false);
+    }
+  }
+  }
+  if (PEER && (bsouth || bnorth)) {
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+      __threadfence_system();
+      const unsigned nbound = gridDim.x * (rown == 0 ? 1u : 2u);
+      unsigned t = atomicAdd(&P.me->blocks_done, 1u);
+      if (t == nbound - 1) {
+        P.me->blocks_done = 0;
+        __threadfence_system();
+        const unsigned long long D = P.me->done + 1;
+        *((volatile unsigned long long *)&P.me->done) = D;
+        for (int r = 0; r < P.nranks; r++)
+          if (r != P.rank) *((volatile unsigned long long *)&P.peers[r]->slot[P.rank]) = D;
+      }
+    }
+  }
 }
 
 // mask-aware bilinear interpolation over the whole fine array
@@ -347,11 +396,22 @@ int launch_smooth2(f2d_mg *mg, Level &l, Level *cl, const double *xin, const dou
     Level &c = *cl;
     mskc = c.msk; nxc = c.nx; nyc = c.ny;
   }
+  // slab levels of a multi-GPU hierarchy: the kernel also fills the neighbours' halo rows
+  const bool peer = mg->comm != nullptr && l.ywrap == 0;
+  f2d::Peer P = comm_peer(peer ? mg->comm : nullptr);
+  if (peer && !comm_owns(mg->comm, acc ? acc : xout))
+    return fail(F2D_ERR_ARG, "smooth: the output of a slab level must live in the symmetric heap");
+#define F2D_SM2(M, St)                                                                                              \
+  do {                                                                                                              \
+    if (peer) fused::k_smooth2<M, St, INPUT, true><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc, acc, P); \
+    else fused::k_smooth2<M, St, INPUT, false><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc, acc, P);     \
+  } while (0)
   switch (l.mode) {
-    case 1: fused::k_smooth2<false, false, INPUT><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc, acc); break;
-    case 2: fused::k_smooth2<true, false, INPUT><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc, acc); break;
-    default: fused::k_smooth2<true, true, INPUT><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc, acc); break;
+    case 1: F2D_SM2(false, false); break;
+    case 2: F2D_SM2(true, false); break;
+    default: F2D_SM2(true, true); break;
   }
+#undef F2D_SM2
   F2D_LAUNCHED();
   return F2D_OK;
 }
@@ -371,7 +431,10 @@ int smooth2(f2d_mg *mg, int lev, int input, const double *xin, const double *b, 
 }
 template <bool M, bool St, int I>
 cudaError_t set_smem_one() {
-  return cudaFuncSetAttribute(fused::k_smooth2<M, St, I>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(fused::k_smooth2<M, St, I, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(fused::Smooth2Smem));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(fused::k_smooth2<M, St, I, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)sizeof(fused::Smooth2Smem));
 }
 template <int I>
@@ -383,7 +446,10 @@ cudaError_t set_smem_input() {
 }
 template <bool M, bool St>
 cudaError_t set_smem_resid() {
-  return cudaFuncSetAttribute(fused::k_resid_restrict<M, St>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(fused::k_resid_restrict<M, St, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(fused::ResidSmem));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(fused::k_resid_restrict<M, St, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)sizeof(fused::ResidSmem));
 }
 cudaError_t set_smem_all() {
@@ -436,7 +502,12 @@ int op_resid_sumsq(f2d_mg *mg, const double *x, const double *b, double *r, doub
 }
 int op_restrict_L(f2d_mg *mg, Level &f, Level &c, const double *xf, double *xc, cudaStream_t s) {
   dim3 blk(32, 8);
-  k_restrict<<<grid2d(c.ny, c.nx, blk), blk, 0, s>>>(c.msk, xf, xc, c.ny, c.nx, f.nx, c.ywrap);
+  const bool peer = mg->comm != nullptr && c.ywrap == 0;
+  f2d::Peer P = comm_peer(peer ? mg->comm : nullptr);
+  if (peer && !comm_owns(mg->comm, xc))
+    return fail(F2D_ERR_ARG, "restrict: the output of a slab level must live in the symmetric heap");
+  if (peer) k_restrict<true><<<grid2d(c.ny, c.nx, blk), blk, 0, s>>>(c.msk, xf, xc, c.ny, c.nx, f.nx, c.ywrap, P);
+  else k_restrict<false><<<grid2d(c.ny, c.nx, blk), blk, 0, s>>>(c.msk, xf, xc, c.ny, c.nx, f.nx, c.ywrap, P);
   F2D_LAUNCHED();
   return F2D_OK;
 }
@@ -454,11 +525,21 @@ int op_resid_restrict_L(f2d_mg *mg, Level &l, Level &c, const double *x, const d
   fused::LevelK k = level_k(mg, l);
   dim3 grid(cdiv(c.nx - 2 * NH, fused::RTX), cdiv(c.ny - 2 * NH, fused::RTY));
   size_t sm = sizeof(fused::ResidSmem);
+  const bool peer = mg->comm != nullptr && l.ywrap == 0;
+  f2d::Peer P = comm_peer(peer ? mg->comm : nullptr);
+  if (peer && !comm_owns(mg->comm, bc))
+    return fail(F2D_ERR_ARG, "restrict: the output of a slab level must live in the symmetric heap");
+#define F2D_RR(M, St)                                                                                         \
+  do {                                                                                                        \
+    if (peer) fused::k_resid_restrict<M, St, true><<<grid, fused::NT, sm, s>>>(k, x, b, bc, c.msk, c.ny, c.nx, P); \
+    else fused::k_resid_restrict<M, St, false><<<grid, fused::NT, sm, s>>>(k, x, b, bc, c.msk, c.ny, c.nx, P);     \
+  } while (0)
   switch (l.mode) {
-    case 1: fused::k_resid_restrict<false, false><<<grid, fused::NT, sm, s>>>(k, x, b, bc, c.msk, c.ny, c.nx); break;
-    case 2: fused::k_resid_restrict<true, false><<<grid, fused::NT, sm, s>>>(k, x, b, bc, c.msk, c.ny, c.nx); break;
-    default: fused::k_resid_restrict<true, true><<<grid, fused::NT, sm, s>>>(k, x, b, bc, c.msk, c.ny, c.nx); break;
+    case 1: F2D_RR(false, false); break;
+    case 2: F2D_RR(true, false); break;
+    default: F2D_RR(true, true); break;
   }
+#undef F2D_RR
   F2D_LAUNCHED();
   return F2D_OK;
 }
@@ -576,12 +657,12 @@ int fcycle_enqueue(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s,
   return F2D_OK;
 }
 
-int slab_cycle_enqueue(f2d_mg *mg, int kind, int lev1, double *x0, double *b0, cudaStream_t s);
+int slab_cycle_enqueue(f2d_mg *mg, int kind, int lev1, double *x0, double *b0, cudaStream_t s, double *acc);
 
 // run `kind` (0 two V-cycles from level 0, 1 F-cycle, 2 single V-cycle) through a cached graph
 int run_cycle(f2d_mg *mg, int kind, int lev1, double *x0, double *b0, cudaStream_t s, double *acc = nullptr) {
   auto enqueue = [&](cudaStream_t st) -> int {
-    if (mg->comm) return slab_cycle_enqueue(mg, kind, lev1, x0, b0, st);
+    if (mg->comm) return slab_cycle_enqueue(mg, kind, lev1, x0, b0, st, acc);
     if (kind == 0) {
       TRY(vcycle_enqueue(mg, 0, x0, b0, st));
       return vcycle_enqueue(mg, 0, x0, b0, st);
@@ -695,7 +776,7 @@ int coarsen_level(f2d_mg *mg, Level &p, Level &c, const double *A9p, double *A9c
   size_t pl = c.n();
   k_mask_to_double<<<nblocks1d(p.n()), 256, 0, s>>>(p.msk, p.t, p.n());
   k_fill_const<<<nblocks1d(pl), 256, 0, s>>>(c.t, 1., pl);
-  k_restrict<<<grid2d(c.ny, c.nx, blk), blk, 0, s>>>(nullptr, p.t, c.t, c.ny, c.nx, p.nx, c.ywrap);
+  k_restrict<false><<<grid2d(c.ny, c.nx, blk), blk, 0, s>>>(nullptr, p.t, c.t, c.ny, c.nx, p.nx, c.ywrap, f2d::Peer{});
   g_launches += 3;
   if (!c.ywrap) {
     double *arr[1] = {c.t};

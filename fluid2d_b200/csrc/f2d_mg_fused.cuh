@@ -107,15 +107,21 @@ __device__ __forceinline__ double interp_w4(int s) {
 constexpr int XW = TX + 4, XH = TY + 4;  // x tile (halo 2)
 constexpr int YW = TX + 2, YH = TY + 2;  // sweep-1 tile (halo 1)
 constexpr int CW = XW / 2 + 2, CH = XH / 2 + 2;  // coarse tile for the fused interpolation
+// TMA boxes must start at an even column (16-byte aligned innermost coordinate): the x and
+// coarse tiles start at odd columns (i0 - 2 = 1 + 64k, ci0 = 1 + 32k), so their boxes begin
+// one column earlier and are two columns wider; the tile proper sits at column offset 1.
+constexpr int XP = XW + 2, CP = CW + 2;
 
 struct Smooth2Smem {
-  double xs[XH][XW];
+  alignas(128) double xs[XH][XP];   // TMA destinations: 128-byte aligned, dense boxes
+  alignas(128) double bs[YH][YW];
+  alignas(128) double cs[CH][CP];
   double y1[YH][YW];
-  double bs[YH][YW];
-  double cs[CH][CW];
   int8_t ms[XH][XW];
   int8_t cm[CH][CW];
+  alignas(8) uint64_t bar;          // mbarrier of the TMA loads
 };
+static_assert(XP % 2 == 0 && YW % 2 == 0 && CP % 2 == 0, "TMA boxes need an even number of doubles per row");
 
 // ---- asynchronous tile loader -----------------------------------------------------
 // Copies a ROWS x COLS tile whose origin is `src` (row pitch nx doubles) into `dst` (row
@@ -209,7 +215,8 @@ template <bool MASKED, bool STORED, int INPUT, bool PEER>
 __global__ void __launch_bounds__(NT)
 k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b, double *__restrict__ xout,
           const double *__restrict__ xc, const int8_t *__restrict__ mskc, int nxc, int nyc, double *acc,
-          f2d::Peer P) {
+          f2d::Peer P, int use_tma, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmb,
+          const __grid_constant__ CUtensorMap tmc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smooth2Smem &S = *reinterpret_cast<Smooth2Smem *>(smem_raw);
   const int ny = L.ny, nx = L.nx;
@@ -224,24 +231,41 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
   const int cj0 = ((j0 - 2) >> 1) + 1, ci0 = ((i0 - 2) >> 1) + 1;
   // inner tile: every point of the sweep-1 ring and of the output tile is a valid target
   const bool inner = (j0 + TY <= ny - 3) && (i0 + TX <= nx - 3);
-  // ---- stage the tiles with asynchronous copies
-  {
+  // ---- stage the tiles: TMA boxes (one instruction per tile, zero fill outside the
+  // array) or, on levels smaller than a box, per-element asynchronous copies
+  if (use_tma) {
+    if (t == 0) f2d::mbar_init(&S.bar, 1);
+    __syncthreads();
+    if (t == 0) {
+      // (PEER) the neighbour's halo rows were observed through the generic proxy
+      if (PEER) asm volatile("fence.proxy.async;" ::: "memory");
+      constexpr unsigned bytes = (HAVE_X ? XH * XP * 8 : 0) + YH * YW * 8 + (INTERP ? CH * CP * 8 : 0);
+      f2d::mbar_expect_tx(&S.bar, bytes);
+      if (HAVE_X) f2d::tma_load_2d(&S.xs[0][0], &tmx, &S.bar, i0 - 3, j0 - 2);
+      f2d::tma_load_2d(&S.bs[0][0], &tmb, &S.bar, i0 - 1, j0 - 1);
+      if (INTERP) f2d::tma_load_2d(&S.cs[0][0], &tmc, &S.bar, ci0 - 1, cj0);
+    }
+    const int vr = ny - (j0 - 2), vc = nx - (i0 - 2);
+    if (INTERP && MASKED) load_tile_i8<CH, CW, CW>(&S.cm[0][0], mskc + (size_t)cj0 * nxc + ci0, nxc, nyc - cj0, nxc - ci0);
+    if (MASKED) load_tile_i8<XH, XW, XW>(&S.ms[0][0], L.msk + (size_t)(j0 - 2) * nx + (i0 - 2), nx, vr, vc);
+    f2d::mbar_wait(&S.bar, 0);
+  } else {
     const int vr = ny - (j0 - 2), vc = nx - (i0 - 2);
     if (HAVE_X) {
       const double *src = xin + (size_t)(j0 - 2) * nx + (i0 - 2);
-      if (inner) load_tile<XH, XW, XW, true>(&S.xs[0][0], src, nx, 0, 0);
-      else load_tile<XH, XW, XW, false>(&S.xs[0][0], src, nx, vr, vc);
+      if (inner) load_tile<XH, XW, XP, true>(&S.xs[0][1], src, nx, 0, 0);
+      else load_tile<XH, XW, XP, false>(&S.xs[0][1], src, nx, vr, vc);
     }
     const double *bsrc = b + (size_t)(j0 - 1) * nx + (i0 - 1);
     if (inner) load_tile<YH, YW, YW, true>(&S.bs[0][0], bsrc, nx, 0, 0);
     else load_tile<YH, YW, YW, false>(&S.bs[0][0], bsrc, nx, vr - 1, vc - 1);
     if (INTERP) {
-      load_tile<CH, CW, CW, false>(&S.cs[0][0], xc + (size_t)cj0 * nxc + ci0, nxc, nyc - cj0, nxc - ci0);
+      load_tile<CH, CW, CP, false>(&S.cs[0][1], xc + (size_t)cj0 * nxc + ci0, nxc, nyc - cj0, nxc - ci0);
       if (MASKED) load_tile_i8<CH, CW, CW>(&S.cm[0][0], mskc + (size_t)cj0 * nxc + ci0, nxc, nyc - cj0, nxc - ci0);
     }
     if (MASKED) load_tile_i8<XH, XW, XW>(&S.ms[0][0], L.msk + (size_t)(j0 - 2) * nx + (i0 - 2), nx, vr, vc);
+    cp_async_wait_all();
   }
-  cp_async_wait_all();
   __syncthreads();
   // ---- fused interpolation: xs = [xin +] I(xc)  (fortran_multigrid.f90:415-498).
   // One thread per coarse cell of the tile produces the 2x2 fine block it anchors.
@@ -254,7 +278,7 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
       int r = 2 * bj, q = 2 * bi;                 // its first (odd-global) row / column
       // global (j,i) of (r,q) is odd/odd: coarse anchor lj = ((j>>1)+1-cj0) = bj, li = bi
       int lj = bj, li = bi;
-      double c00 = S.cs[lj][li], c01 = S.cs[lj][li + 1], c10 = S.cs[lj + 1][li], c11 = S.cs[lj + 1][li + 1];
+      double c00 = S.cs[lj][li + 1], c01 = S.cs[lj][li + 2], c10 = S.cs[lj + 1][li + 1], c11 = S.cs[lj + 1][li + 2];
       int m00 = 1, m01 = 1, m10 = 1, m11 = 1;
       if (MASKED) { m00 = S.cm[lj][li]; m01 = S.cm[lj][li + 1]; m10 = S.cm[lj + 1][li]; m11 = S.cm[lj + 1][li + 1]; }
       // the tile origin is odd/odd in global coordinates, so inside the block
@@ -270,9 +294,9 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
         int j = j0 - 2 + rr, i = i0 - 2 + qq;
         if (j < ny && i < nx) {
           if (MASKED && !(S.ms[rr][qq] > 0)) iv = 0.;
-          S.xs[rr][qq] = (INPUT == 3) ? S.xs[rr][qq] + iv : iv;
+          S.xs[rr][qq + 1] = (INPUT == 3) ? S.xs[rr][qq + 1] + iv : iv;
         } else if (INPUT != 3) {
-          S.xs[rr][qq] = 0.;
+          S.xs[rr][qq + 1] = 0.;
         }
       };
       put(r, q, v_oo);
@@ -291,20 +315,20 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
   {
     const int r0 = tg * 8 + (tg < 2 ? tg : 2), nr = tg < 2 ? 9 : 8;
     const int j = j0 - 1 + r0, i = i0 - 1 + tx;
-    const double *sp = &S.xs[r0 + 1][tx + 1];
+    const double *sp = &S.xs[r0 + 1][tx + 2];
     const double *bp = &S.bs[r0][tx];
     const int8_t *mp = &S.ms[r0 + 1][tx + 1];
     double *yp = &S.y1[r0][tx];
     auto out = [&](int k, double val) { yp[k * YW] = val; };
     if (inner)
-      jacobi_strip<MASKED, STORED, ZERO, false, 9, XW, YW, XW>(L, kc, sp, bp, mp, nr, j, i, 2, out);
+      jacobi_strip<MASKED, STORED, ZERO, false, 9, XP, YW, XW>(L, kc, sp, bp, mp, nr, j, i, 2, out);
     else
-      jacobi_strip<MASKED, STORED, ZERO, true, 9, XW, YW, XW>(L, kc, sp, bp, mp, nr, j, i, 2, out);
+      jacobi_strip<MASKED, STORED, ZERO, true, 9, XP, YW, XW>(L, kc, sp, bp, mp, nr, j, i, 2, out);
     if (t < YH * 2) {   // ring columns TX, TX+1 of the y1 tile
       const int r = t >> 1, q = TX + (t & 1);
       double *y = &S.y1[r][q];
       auto out1 = [&](int, double val) { *y = val; };
-      jacobi_strip<MASKED, STORED, ZERO, true, 1, XW, YW, XW>(L, kc, &S.xs[r + 1][q + 1], &S.bs[r][q],
+      jacobi_strip<MASKED, STORED, ZERO, true, 1, XP, YW, XW>(L, kc, &S.xs[r + 1][q + 2], &S.bs[r][q],
                                                               &S.ms[r + 1][q + 1], 1, j0 - 1 + r, i0 - 1 + q, 2, out1);
     }
   }
@@ -378,11 +402,13 @@ __device__ __noinline__ double resid_global(const LevelK &L, const double *__res
                                    x[g + nx - 1], x[g + nx], x[g + nx + 1], b[g]);
 }
 
+constexpr int RXP = RXW + 1, RBP = RW + 1;         // row pitches of the x / b tiles (even: TMA boxes)
 struct ResidSmem {
-  double xs[RXH][RXW];
+  alignas(128) double xs[RXH][RXP];
+  alignas(128) double bs[RH][RBP];
   double rs[RH][RW];
-  double bs[RH][RW];
   int8_t ms[RXH][RXW];
+  alignas(8) uint64_t bar;
 };
 
 // column strip of the residual tile (same register-window scheme as jacobi_strip)
@@ -391,13 +417,13 @@ __device__ __forceinline__ void resid_strip(const LevelK &L, const Coefs<MASKED,
                                             const double *bp, const int8_t *mp, double *rp, int nr, int j, int i,
                                             const double *__restrict__ x, const double *__restrict__ b) {
   const int ny = L.ny, nx = L.nx;
-  double a0 = sp[-RXW - 1], a1 = sp[-RXW], a2 = sp[-RXW + 1];
+  double a0 = sp[-RXP - 1], a1 = sp[-RXP], a2 = sp[-RXP + 1];
   double m0 = sp[-1], m1 = sp[0], m2 = sp[1];
   size_t g = (size_t)j * nx + i;
 #pragma unroll
   for (int k = 0; k < NR; k++) {
     if (k < nr) {
-      double h0 = sp[(k + 1) * RXW - 1], h1 = sp[(k + 1) * RXW], h2 = sp[(k + 1) * RXW + 1];
+      double h0 = sp[(k + 1) * RXP - 1], h1 = sp[(k + 1) * RXP], h2 = sp[(k + 1) * RXP + 1];
       double val = 0.;
       const int jj = j + k;
       if (GUARD && (jj > ny - NH || i > nx - NH)) {
@@ -411,7 +437,7 @@ __device__ __forceinline__ void resid_strip(const LevelK &L, const Coefs<MASKED,
         Coefs<MASKED, STORED> kk;
         if (MASKED || STORED) kk.load(L, g + (size_t)k * nx, MASKED ? mp + k * RXW : nullptr, RXW); else kk = kc;
         double cdiag = STORED ? L.A[4 * (size_t)ny * nx + g + (size_t)k * nx] : L.c[4];
-        val = resid_val<MASKED, STORED>(L, kk, cdiag, a0, a1, a2, m0, m1, m2, h0, h1, h2, bp[k * RW]);
+        val = resid_val<MASKED, STORED>(L, kk, cdiag, a0, a1, a2, m0, m1, m2, h0, h1, h2, bp[k * RBP]);
       }
       rp[k * RW] = val;
       a0 = m0; a1 = m1; a2 = m2;
@@ -423,7 +449,8 @@ __device__ __forceinline__ void resid_strip(const LevelK &L, const Coefs<MASKED,
 template <bool MASKED, bool STORED, bool PEER>
 __global__ void __launch_bounds__(NT)
 k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ bc,
-                 const int8_t *__restrict__ mskc, int nyc, int nxc, f2d::Peer P) {
+                 const int8_t *__restrict__ mskc, int nyc, int nxc, f2d::Peer P, int use_tma,
+                 const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ResidSmem &S = *reinterpret_cast<ResidSmem *>(smem_raw);
   const int ny = L.ny, nx = L.nx;
@@ -435,20 +462,32 @@ k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restric
   const int fi0 = 2 * ci0 - 3, fj0 = 2 * cj0 - 3;                      // first fine residual point
   // inner tile: the whole residual tile lies strictly inside the fine interior
   const bool inner = (fj0 + RH <= ny - NH) && (fi0 + RW <= nx - NH);
-  {
+  if (use_tma) {
+    if (t == 0) f2d::mbar_init(&S.bar, 1);
+    __syncthreads();
+    if (t == 0) {
+      if (PEER) asm volatile("fence.proxy.async;" ::: "memory");
+      f2d::mbar_expect_tx(&S.bar, (RXH * RXP + RH * RBP) * 8);
+      f2d::tma_load_2d(&S.xs[0][0], &tmx, &S.bar, fi0 - 1, fj0 - 1);
+      f2d::tma_load_2d(&S.bs[0][0], &tmb, &S.bar, fi0 - 1, fj0);   // even column: the tile sits at column offset 1
+    }
+    if (MASKED)
+      load_tile_i8<RXH, RXW, RXW>(&S.ms[0][0], L.msk + (size_t)(fj0 - 1) * nx + (fi0 - 1), nx, ny - (fj0 - 1), nx - (fi0 - 1));
+    f2d::mbar_wait(&S.bar, 0);
+  } else {
     const double *xsrc = x + (size_t)(fj0 - 1) * nx + (fi0 - 1);
     const double *bsrc = b + (size_t)fj0 * nx + fi0;
     const int vr = ny - (fj0 - 1), vc = nx - (fi0 - 1);
     if (inner) {
-      load_tile<RXH, RXW, RXW, true>(&S.xs[0][0], xsrc, nx, 0, 0);
-      load_tile<RH, RW, RW, true>(&S.bs[0][0], bsrc, nx, 0, 0);
+      load_tile<RXH, RXW, RXP, true>(&S.xs[0][0], xsrc, nx, 0, 0);
+      load_tile<RH, RW, RBP, true>(&S.bs[0][1], bsrc, nx, 0, 0);
     } else {
-      load_tile<RXH, RXW, RXW, false>(&S.xs[0][0], xsrc, nx, vr, vc);
-      load_tile<RH, RW, RW, false>(&S.bs[0][0], bsrc, nx, vr - 1, vc - 1);
+      load_tile<RXH, RXW, RXP, false>(&S.xs[0][0], xsrc, nx, vr, vc);
+      load_tile<RH, RW, RBP, false>(&S.bs[0][1], bsrc, nx, vr - 1, vc - 1);
     }
     if (MASKED) load_tile_i8<RXH, RXW, RXW>(&S.ms[0][0], L.msk + (size_t)(fj0 - 1) * nx + (fi0 - 1), nx, vr, vc);
+    cp_async_wait_all();
   }
-  cp_async_wait_all();
   __syncthreads();
   // ---- fine residual on the (2RTX+1) x (2RTY+1) tile: column strips (rows 9,8,8,8) with
   // the 3x3 window in registers; the last column point-wise
@@ -458,14 +497,14 @@ k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restric
     const int tx = t & 63, tg = t >> 6;
     const int r0 = tg * 8 + (tg < 1 ? 0 : 1), nr = tg < 1 ? 9 : 8;
     if (inner)
-      resid_strip<MASKED, STORED, false, 9>(L, kc, &S.xs[r0 + 1][tx + 1], &S.bs[r0][tx], &S.ms[r0 + 1][tx + 1],
+      resid_strip<MASKED, STORED, false, 9>(L, kc, &S.xs[r0 + 1][tx + 1], &S.bs[r0][tx + 1], &S.ms[r0 + 1][tx + 1],
                                             &S.rs[r0][tx], nr, fj0 + r0, fi0 + tx, x, b);
     else
-      resid_strip<MASKED, STORED, true, 9>(L, kc, &S.xs[r0 + 1][tx + 1], &S.bs[r0][tx], &S.ms[r0 + 1][tx + 1],
+      resid_strip<MASKED, STORED, true, 9>(L, kc, &S.xs[r0 + 1][tx + 1], &S.bs[r0][tx + 1], &S.ms[r0 + 1][tx + 1],
                                            &S.rs[r0][tx], nr, fj0 + r0, fi0 + tx, x, b);
     if (t < RH) {
       const int r = t, q = RW - 1;
-      resid_strip<MASKED, STORED, true, 1>(L, kc, &S.xs[r + 1][q + 1], &S.bs[r][q], &S.ms[r + 1][q + 1], &S.rs[r][q], 1,
+      resid_strip<MASKED, STORED, true, 1>(L, kc, &S.xs[r + 1][q + 1], &S.bs[r][q + 1], &S.ms[r + 1][q + 1], &S.rs[r][q], 1,
                                            fj0 + r, fi0 + q, x, b);
     }
   }

@@ -173,6 +173,7 @@ extern "C" int f2d_mg_create_slab(f2d_mg_t **out, f2d_comm_t *comm, const double
   f2d_mg *mg = new f2d_mg();
   mg->omega = omega;
   if (const char *ng = getenv("F2D_MG_NO_GRAPHS")) mg->graphs = !(ng[0] == '1');
+  if (const char *tm = getenv("F2D_MG_TMA")) mg->tma = !(tm[0] == '0');
   mg->comm = comm;
   auto bail = [&](int rc) { f2d_mg_destroy(mg); return rc; };
   std::vector<std::pair<int, int>> sizes;   // global (m, n) per level

@@ -12,6 +12,7 @@
 #include <tuple>
 
 #include "f2d_common.cuh"
+#include "f2d_tma.cuh"
 #include "f2d_mg_fused.cuh"
 #include "f2d_mg_tail.cuh"
 
@@ -50,6 +51,15 @@ struct f2d_mg {
   size_t tail_smem = 0;
   struct G { cudaGraphExec_t exec; long long kernels; };
   std::map<std::tuple<int, int, const void *, const void *, const void *>, G> cache;
+  // Gmg.solve as ONE graph: norms, a device-side WHILE node around (F-cycle, residual,
+  // convergence test), result read back once
+  struct SolveState { double normb, res0, res; int nite, ndiv, diverged, pad; };
+  struct SG { cudaGraphExec_t exec; long long pre, body; };
+  std::map<std::tuple<const void *, const void *, double, int>, SG> solve_cache;
+  bool tma = true;                 // stage tiles with TMA (F2D_MG_TMA=0: per-element cp.async everywhere)
+  std::map<std::tuple<const void *, int, int, int, int>, CUtensorMap> tmaps;
+  cudaStream_t cap2 = nullptr;     // capture stream of the WHILE body
+  SolveState *dstate = nullptr, *hstate = nullptr;
 };
 
 namespace {
@@ -383,6 +393,20 @@ fused::LevelK level_k(f2d_mg *mg, const Level &l) {
 }
 fused::LevelK level_k(f2d_mg *mg, int lev) { return level_k(mg, mg->L[lev]); }
 
+// tensor map (cached) of a level array for boxh x boxw tiles; false: TMA not usable here
+bool get_tmap(f2d_mg *mg, const double *base, int ny, int nx, int boxh, int boxw, CUtensorMap *out) {
+  if (!mg->tma || !base || nx < boxw || ny < boxh) return false;
+  auto key = std::make_tuple((const void *)base, ny, nx, boxh, boxw);
+  auto it = mg->tmaps.find(key);
+  if (it == mg->tmaps.end()) {
+    CUtensorMap tm;
+    if (make_tmap_2d(&tm, base, ny, nx, boxh, boxw) != 0) return false;
+    it = mg->tmaps.emplace(key, tm).first;
+  }
+  *out = it->second;
+  return true;
+}
+
 // fused double sweep: xout = S2(input), input = xin | 0 | I(xc) | xin + I(xc)
 template <int INPUT>
 int launch_smooth2(f2d_mg *mg, Level &l, Level *cl, const double *xin, const double *b, double *xout,
@@ -401,10 +425,15 @@ int launch_smooth2(f2d_mg *mg, Level &l, Level *cl, const double *xin, const dou
   f2d::Peer P = comm_peer(peer ? mg->comm : nullptr);
   if (peer && !comm_owns(mg->comm, acc ? acc : xout))
     return fail(F2D_ERR_ARG, "smooth: the output of a slab level must live in the symmetric heap");
+  CUtensorMap tmx, tmb, tmc;
+  memset(&tmx, 0, sizeof tmx); memset(&tmb, 0, sizeof tmb); memset(&tmc, 0, sizeof tmc);
+  int use_tma = get_tmap(mg, b, l.ny, l.nx, fused::YH, fused::YW, &tmb);
+  if (use_tma && (INPUT == 0 || INPUT == 3)) use_tma = get_tmap(mg, xin, l.ny, l.nx, fused::XH, fused::XP, &tmx);
+  if (use_tma && INPUT >= 2) use_tma = get_tmap(mg, xc, nyc, nxc, fused::CH, fused::CP, &tmc);
 #define F2D_SM2(M, St)                                                                                              \
   do {                                                                                                              \
-    if (peer) fused::k_smooth2<M, St, INPUT, true><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc, acc, P); \
-    else fused::k_smooth2<M, St, INPUT, false><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc, acc, P);     \
+    if (peer) fused::k_smooth2<M, St, INPUT, true><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc, acc, P, use_tma, tmx, tmb, tmc); \
+    else fused::k_smooth2<M, St, INPUT, false><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc, acc, P, use_tma, tmx, tmb, tmc);     \
   } while (0)
   switch (l.mode) {
     case 1: F2D_SM2(false, false); break;
@@ -529,10 +558,14 @@ int op_resid_restrict_L(f2d_mg *mg, Level &l, Level &c, const double *x, const d
   f2d::Peer P = comm_peer(peer ? mg->comm : nullptr);
   if (peer && !comm_owns(mg->comm, bc))
     return fail(F2D_ERR_ARG, "restrict: the output of a slab level must live in the symmetric heap");
+  CUtensorMap tmx, tmb;
+  memset(&tmx, 0, sizeof tmx); memset(&tmb, 0, sizeof tmb);
+  int use_tma = get_tmap(mg, x, l.ny, l.nx, fused::RXH, fused::RXP, &tmx);
+  if (use_tma) use_tma = get_tmap(mg, b, l.ny, l.nx, fused::RH, fused::RBP, &tmb);
 #define F2D_RR(M, St)                                                                                         \
   do {                                                                                                        \
-    if (peer) fused::k_resid_restrict<M, St, true><<<grid, fused::NT, sm, s>>>(k, x, b, bc, c.msk, c.ny, c.nx, P); \
-    else fused::k_resid_restrict<M, St, false><<<grid, fused::NT, sm, s>>>(k, x, b, bc, c.msk, c.ny, c.nx, P);     \
+    if (peer) fused::k_resid_restrict<M, St, true><<<grid, fused::NT, sm, s>>>(k, x, b, bc, c.msk, c.ny, c.nx, P, use_tma, tmx, tmb); \
+    else fused::k_resid_restrict<M, St, false><<<grid, fused::NT, sm, s>>>(k, x, b, bc, c.msk, c.ny, c.nx, P, use_tma, tmx, tmb);     \
   } while (0)
   switch (l.mode) {
     case 1: F2D_RR(false, false); break;
@@ -698,6 +731,126 @@ int run_cycle(f2d_mg *mg, int kind, int lev1, double *x0, double *b0, cudaStream
 int read_scalars(f2d_mg *mg, int n, cudaStream_t s) {
   F2D_CUDA(cudaMemcpyAsync(mg->hscal, mg->dscal, n * sizeof(double), cudaMemcpyDeviceToHost, s));
   F2D_CUDA(cudaStreamSynchronize(s));
+  return F2D_OK;
+}
+
+// ---- device-side iteration control of Gmg.solve (hierarchy.py:154-192) -------------
+// The loop `while nite < maxite and res0 > tol` runs inside the graph: a conditional WHILE
+// node whose condition these two kernels set from the (all-reduced) norms, so a solve costs
+// one graph launch and one host read instead of a host round trip per F-cycle.
+__global__ void k_solve_init(const double *dscal, f2d_mg::SolveState *st, cudaGraphConditionalHandle h, double tol,
+                             int maxite) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double normb = sqrt(dscal[0]);
+  double res0 = 0.;
+  bool go = false;
+  if (normb > 0) {
+    res0 = sqrt(dscal[1]) / normb;
+    go = maxite > 0 && res0 > tol;
+  }
+  st->normb = normb; st->res0 = res0; st->res = res0;
+  st->nite = 0; st->ndiv = 0; st->diverged = 0;
+  cudaGraphSetConditional(h, go ? 1u : 0u);
+}
+__global__ void k_solve_step(const double *dscal, f2d_mg::SolveState *st, cudaGraphConditionalHandle h, double tol,
+                             int maxite) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double res = sqrt(dscal[1]) / st->normb;
+  const double conv = st->res0 / res;
+  st->res0 = res; st->res = res;
+  const int nite = st->nite + 1;
+  st->nite = nite;
+  int ndiv = st->ndiv;
+  if (conv < 1) st->ndiv = ++ndiv;
+  bool go = nite < maxite && res > tol;
+  if (ndiv > 4) { st->diverged = 1; go = false; }
+  cudaGraphSetConditional(h, go ? 1u : 0u);
+}
+
+int solve_pre(f2d_mg *mg, double *psi, const double *rhs, cudaStream_t s);
+int solve_body(f2d_mg *mg, double *psi, const double *rhs, cudaStream_t s);
+
+int build_solve_graph(f2d_mg *mg, double *psi, const double *rhs, double tol, int maxite, f2d_mg::SG &out) {
+  cudaStream_t s = mg->cap;
+  const long long before = g_launches;
+  F2D_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  cudaGraph_t graph = nullptr;
+  auto abort_capture = [&](int rc) {
+    cudaGraph_t g = nullptr;
+    cudaStreamEndCapture(s, &g);
+    if (g) cudaGraphDestroy(g);
+    g_launches = before;
+    return rc;
+  };
+  int rc = solve_pre(mg, psi, rhs, s);
+  if (rc != F2D_OK) return abort_capture(rc);
+  cudaStreamCaptureStatus status;
+  cudaGraph_t g = nullptr;
+  const cudaGraphNode_t *deps = nullptr;
+  size_t ndeps = 0;
+  cudaError_t e = cudaStreamGetCaptureInfo_v2(s, &status, nullptr, &g, &deps, &ndeps);
+  if (e != cudaSuccess) return abort_capture(cuda_fail(e, "cudaStreamGetCaptureInfo"));
+  cudaGraphConditionalHandle h;
+  e = cudaGraphConditionalHandleCreate(&h, g, 0, cudaGraphCondAssignDefault);
+  if (e != cudaSuccess) return abort_capture(cuda_fail(e, "cudaGraphConditionalHandleCreate"));
+  k_solve_init<<<1, 32, 0, s>>>(mg->dscal, mg->dstate, h, tol, maxite);
+  ++g_launches;
+  out.pre = g_launches - before;
+  e = cudaStreamGetCaptureInfo_v2(s, &status, nullptr, &g, &deps, &ndeps);
+  if (e != cudaSuccess) return abort_capture(cuda_fail(e, "cudaStreamGetCaptureInfo"));
+  cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+  np.type = cudaGraphNodeTypeConditional;
+  np.conditional.handle = h;
+  np.conditional.type = cudaGraphCondTypeWhile;
+  np.conditional.size = 1;
+  cudaGraphNode_t wnode;
+  e = cudaGraphAddNode(&wnode, g, deps, ndeps, &np);
+  if (e != cudaSuccess) return abort_capture(cuda_fail(e, "cudaGraphAddNode(conditional)"));
+  cudaGraph_t body = np.conditional.phGraph_out[0];
+  e = cudaStreamUpdateCaptureDependencies(s, &wnode, 1, cudaStreamSetCaptureDependencies);
+  if (e != cudaSuccess) return abort_capture(cuda_fail(e, "cudaStreamUpdateCaptureDependencies"));
+  // ---- the loop body, captured into the conditional node's graph
+  const long long b0 = g_launches;
+  e = cudaStreamBeginCaptureToGraph(mg->cap2, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) return abort_capture(cuda_fail(e, "cudaStreamBeginCaptureToGraph"));
+  rc = solve_body(mg, psi, rhs, mg->cap2);
+  if (rc == F2D_OK) {
+    k_solve_step<<<1, 32, 0, mg->cap2>>>(mg->dscal, mg->dstate, h, tol, maxite);
+    ++g_launches;
+  }
+  e = cudaStreamEndCapture(mg->cap2, nullptr);
+  if (rc != F2D_OK) return abort_capture(rc);
+  if (e != cudaSuccess) return abort_capture(cuda_fail(e, "cudaStreamEndCapture(body)"));
+  out.body = g_launches - b0;
+  // ---- result -> pinned host
+  e = cudaMemcpyAsync(mg->hstate, mg->dstate, sizeof(f2d_mg::SolveState), cudaMemcpyDeviceToHost, s);
+  if (e != cudaSuccess) return abort_capture(cuda_fail(e, "cudaMemcpyAsync(state)"));
+  e = cudaStreamEndCapture(s, &graph);
+  g_launches = before;
+  if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture(solve)");
+  e = cudaGraphInstantiate(&out.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate(solve)");
+  return F2D_OK;
+}
+
+// solve through the cached WHILE graph; one synchronising read of (nite, res)
+int solve_graph(f2d_mg *mg, double *psi, const double *rhs, double tol, int maxite, int *nite_out, double *res_out,
+                cudaStream_t s) {
+  auto key = std::make_tuple((const void *)psi, (const void *)rhs, tol, maxite);
+  auto it = mg->solve_cache.find(key);
+  if (it == mg->solve_cache.end()) {
+    f2d_mg::SG sg;
+    TRY(build_solve_graph(mg, psi, rhs, tol, maxite, sg));
+    it = mg->solve_cache.emplace(key, sg).first;
+  }
+  F2D_CUDA(cudaGraphLaunch(it->second.exec, s));
+  F2D_CUDA(cudaStreamSynchronize(s));
+  const f2d_mg::SolveState &st = *mg->hstate;
+  g_launches += it->second.pre + (long long)st.nite * it->second.body;
+  if (st.diverged) return fail(F2D_ERR_DIVERGE, "solver is not converging");
+  if (nite_out) *nite_out = st.nite;
+  if (res_out) *res_out = st.res;
   return F2D_OK;
 }
 
@@ -940,6 +1093,9 @@ int common_init(f2d_mg *mg) {
   MGC(cudaMalloc(&mg->scratch, f2d_reduce_scratch_len() * sizeof(double)));
   MGC(cudaMalloc(&mg->dscal, 16 * sizeof(double)));
   MGC(cudaMallocHost(&mg->hscal, 16 * sizeof(double)));
+  MGC(cudaStreamCreateWithFlags(&mg->cap2, cudaStreamNonBlocking));
+  MGC(cudaMalloc(&mg->dstate, sizeof(f2d_mg::SolveState)));
+  MGC(cudaMallocHost(&mg->hstate, sizeof(f2d_mg::SolveState)));
   return F2D_OK;
 }
 
@@ -959,6 +1115,7 @@ extern "C" int f2d_mg_create(f2d_mg_t **out, const double *cornermask, int ny, i
   f2d_mg *mg = new f2d_mg();
   mg->omega = omega;
   if (const char *ng = getenv("F2D_MG_NO_GRAPHS")) mg->graphs = !(ng[0] == '1');
+  if (const char *tm = getenv("F2D_MG_TMA")) mg->tma = !(tm[0] == '0');
   auto bail = [&](int rc) { f2d_mg_destroy(mg); return rc; };
   std::vector<std::pair<int, int>> sizes;
   int rc = level_sizes(m, n, sizes);
@@ -989,9 +1146,48 @@ extern "C" int f2d_mg_create(f2d_mg_t **out, const double *cornermask, int ny, i
 
 #include "f2d_mg_slab.cuh"
 
+namespace {
+// norms of the rhs and of the first residual -> dscal[0..1] (all-reduced on slabs)
+int solve_pre(f2d_mg *mg, double *psi, const double *rhs, cudaStream_t s) {
+  Level &l = mg->comm ? mg->S[0] : mg->L[0];
+  if (mg->comm && !comm_owns(mg->comm, psi))
+    return fail(F2D_ERR_ARG, "slab multigrid: psi must live in the symmetric heap (f2d_comm_alloc)");
+  TRY(f2d_computenorm(l.msk, rhs, NH, l.ny, l.nx, mg->dscal, mg->scratch, (f2d_stream_t)s));
+  TRY(op_resid_sumsq_L(mg, l, psi, rhs, l.b, mg->dscal + 1, s));
+  if (mg->comm) {
+    TRY(xch1(mg, l, l.b, s));
+    TRY(comm_allreduce(mg->comm, mg->dscal, 2, 0u, s));
+  }
+  return F2D_OK;
+}
+// one iteration: psi += Fcycle(r); r = rhs - A psi; |r|^2 -> dscal[1]
+int solve_body(f2d_mg *mg, double *psi, const double *rhs, cudaStream_t s) {
+  Level &l = mg->comm ? mg->S[0] : mg->L[0];
+  if (mg->comm) {
+    TRY(slab_cycle_enqueue(mg, 1, 0, l.x, l.b, s, psi));
+  } else if (mg->L.size() > 1) {
+    TRY(fcycle_enqueue(mg, 0, l.x, l.b, s, psi));
+  } else {
+    TRY(fcycle_enqueue(mg, 0, l.x, l.b, s, nullptr));
+    k_add_inplace<<<nblocks1d(l.n()), 256, 0, s>>>(psi, l.x, l.n());
+    F2D_LAUNCHED();
+  }
+  TRY(op_resid_sumsq_L(mg, l, psi, rhs, l.b, mg->dscal + 1, s));
+  if (mg->comm) {
+    TRY(xch1(mg, l, l.b, s));
+    TRY(comm_allreduce(mg->comm, mg->dscal + 1, 1, 0u, s));
+  }
+  return F2D_OK;
+}
+}  // namespace
+
 extern "C" int f2d_mg_destroy(f2d_mg_t *mg) {
   if (!mg) return F2D_OK;
   for (auto &kv : mg->cache) cudaGraphExecDestroy(kv.second.exec);
+  for (auto &kv : mg->solve_cache) cudaGraphExecDestroy(kv.second.exec);
+  if (mg->cap2) cudaStreamDestroy(mg->cap2);
+  cudaFree(mg->dstate);
+  if (mg->hstate) cudaFreeHost(mg->hstate);
   for (auto &l : mg->L) free_level(l);
   for (auto &l : mg->S) free_level(l);
   cudaFree(mg->scratch);
@@ -1090,6 +1286,8 @@ extern "C" int f2d_mg_solve(f2d_mg_t *mg, double *psi, const double *rhs, double
                             double *res_out, f2d_stream_t stream) {
   if (!mg || !psi || !rhs) return fail(F2D_ERR_ARG, "mg_solve: null");
   cudaStream_t s = S(stream);
+  if (mg->graphs && !(mg->comm && mg->lg == 0)) return solve_graph(mg, psi, rhs, tol, maxite, nite_out, res_out, s);
+  // host-driven loop (graphs disabled): same operations, one host round trip per F-cycle
   if (mg->comm) return slab_solve(mg, psi, rhs, tol, maxite, nite_out, res_out, s);
   Level &l = mg->L[0];
   TRY(f2d_computenorm(l.msk, rhs, NH, l.ny, l.nx, mg->dscal, mg->scratch, stream));

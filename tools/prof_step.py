@@ -13,11 +13,15 @@ import bench  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+graphs = int(sys.argv[3]) if len(sys.argv) > 3 else 1   # 0: no CUDA graphs, so ncu lists the kernels of the solve
 api = fluid2d_b200.api()
 so = sys.stdout
 sys.stdout = sys.stderr
 f2d = bench.build_case(api, n, T, tempfile.mkdtemp())
 f2d.model.diagnostics(f2d.model.var, 0.)
+if not graphs:
+    g = f2d.model.ope.gmg
+    g.lib.mg_set_graphs(g.h, 0)
 for _ in range(3):
     bench.loop_body(f2d)
 torch.cuda.synchronize()

@@ -81,9 +81,11 @@ class Fluid2d(object):
             self.model.ope.rhsp = grid.island.rhsp
             self.model.ope.psi = grid.island.psi
         if self.diag_fluxes:
-            raise NotImplementedError('diag_fluxes: the flux kernels exist (f2d_adv_* with xflx/yflx) but the '
-                                      'Fluxes driver is not built yet')
-        flxlist = None
+            from fluxes import Fluxes
+            self.flx = Fluxes(param, grid, self.model.ope)
+            flxlist = self.flx.fullflx_list
+        else:
+            flxlist = None
         if self.plot_interactive:
             p = import_module(self.plotting_module)
             self.plotting = p.Plotting(param, grid, self.model.var, self.model.diags)
@@ -116,6 +118,7 @@ class Fluid2d(object):
             print(' Output files:')
             print('-'*50)
             for f in [self.output.hisfile, self.output.diagfile] + \
+                    ([self.output.flxfile] if self.diag_fluxes else []) + \
                     ([self.savedscript] if hasattr(self, 'savedscript') else []):
                 print('  - %s' % f)
             print('-'*50)
@@ -131,6 +134,11 @@ class Fluid2d(object):
         model.diags['dkedt'] = 0.
         model.diags['dvdt'] = 0.
         data = {'his': model.var, 'diag': model.diags}
+        if self.diag_fluxes:
+            data['flx'] = self.flx
+            # dt must be set first (adaptable_dt), fluid2d.py:204-210
+            self.set_dt(self.kt)
+            self.flx.diag_fluxes(model.var.dstate, self.t, self.dt)
         self.output.do(data, self.t, self.kt)
         if self.plot_interactive and not hasattr(self.plotting, 'fig'):
             self.plotting.create_fig(self.t)
@@ -178,6 +186,9 @@ class Fluid2d(object):
             if ((ke > ke_old) and (self.myrank == 0) and (self.decay) and (self.modelname == 'euler')):
                 print('\rkt=%-4i \033[0;32;40mWARNING dlog(ke)\033[0m = %.2g' %
                       (self.kt, float(np.ravel((ke-ke_old)/ke)[0])), end='')
+            if self.diag_fluxes and (self.t >= self.output.tnexthis):
+                # costly (two extra time steps): only before it is written
+                self.flx.diag_fluxes(model.var.dstate, self.t, self.dt)
             self.output.do(data, self.t, self.kt)
             flag = '*' if self.dt == self.dtmax else ''
             if (self.myrank == 0) and (self.kt % self.nprint == 0) or (self.t >= self.tend):

@@ -40,6 +40,8 @@ class Output(object):
         self.first = True
         self.his_t = []
         self.his = {v: [] for v in self.var_to_save}
+        self.flxlist = flxlist if self.diag_fluxes else None
+        self.flx = {v: [] for v in (self.flxlist or [])}
         self.diag_t = []
         self.diag_kt = []
         self.diag_rec = {}
@@ -67,10 +69,16 @@ class Output(object):
             for v in self.var_to_save:
                 field = var.get(v)     # D2H of that field only
                 self.his[v].append(np.array(field[nh:-nh, nh:-nh], dtype=np.float32))
+            if self.flxlist:
+                stack = data['flx'].flx     # D2H of the flux stack (output.py:94-95)
+                for k, v in enumerate(self.flxlist):
+                    self.flx[v].append(np.array(stack[k][nh:-nh, nh:-nh], dtype=np.float32))
 
     def dump_diag(self):
         self._write_diag()
         self._write_his()
+        if self.flxlist:
+            self._write_his(self.flxfile, self.flxlist, self.flx)
 
     def _write_diag(self):
         if HAVE_NETCDF:
@@ -85,13 +93,17 @@ class Output(object):
             np.savez(self.diagfile, t=np.array(self.diag_t), kt=np.array(self.diag_kt),
                      **{k: np.array(v) for k, v in self.diag_rec.items()})
 
-    def _write_his(self):
+    def _write_his(self, hisfile=None, names=None, rec=None):
+        """history-type file (output.py NcfileIO): the model snapshots, or the flux stack"""
         if not self.his_t:
             return
         g, nh = self.grid, self.nh
+        hisfile = hisfile or self.hisfile
+        names = names if names is not None else self.var_to_save
+        rec = rec if rec is not None else self.his
         if HAVE_NETCDF:
             from netCDF4 import Dataset
-            with Dataset(self.hisfile, 'w') as nc:
+            with Dataset(hisfile, 'w') as nc:
                 for k, v in self.param_attrs.items():
                     nc.setncattr(k, v*1 if isinstance(v, bool) else v)
                 nc.createDimension('t', None)
@@ -101,11 +113,11 @@ class Output(object):
                 nc.createVariable('y', 'f', ('y',))[:] = g.y1d[nh:-nh]
                 nc.createVariable('msk', 'i', ('y', 'x'))[:] = g.msk[nh:-nh, nh:-nh]
                 nc.createVariable('t', 'f', ('t',))[:] = np.array(self.his_t)
-                for v in self.var_to_save:
-                    nc.createVariable(v, 'f', ('t', 'y', 'x'))[:] = np.stack(self.his[v])
+                for v in names:
+                    nc.createVariable(v, 'f', ('t', 'y', 'x'))[:] = np.stack(rec[v])
         else:
-            np.savez(self.hisfile, t=np.array(self.his_t), x=g.x1d[nh:-nh], y=g.y1d[nh:-nh],
-                     msk=g.msk[nh:-nh, nh:-nh], **{v: np.stack(self.his[v]) for v in self.var_to_save})
+            np.savez(hisfile, t=np.array(self.his_t), x=g.x1d[nh:-nh], y=g.y1d[nh:-nh],
+                     msk=g.msk[nh:-nh, nh:-nh], **{v: np.stack(rec[v]) for v in names})
 
     def join(self):
         """per-rank history files are left as they are (one file per slab)"""

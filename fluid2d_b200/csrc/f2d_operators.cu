@@ -357,6 +357,42 @@ extern "C" int f2d_add_scaled_mask(double *y, double alpha, const int8_t *a, siz
 extern "C" int f2d_set_sum(double *y, const double *a, double alpha, const double *b, size_t n, f2d_stream_t s) {
   return elementwise(n, S(s), [=] __device__(size_t k) { y[k] = add_rn(a[k], mul_rn(alpha, b[k])); });
 }
+// core/fluxes.py:120-127: cell-centred velocities uc = 0.5*(u + roll(u,1,axis=1)),
+// vc = 0.5*(v + roll(v,1,axis=0)) on the interior, periodic images stored by the
+// owning cell (the fill_halo that follows each in the reference)
+__global__ void k_flx_cellvel(const double *__restrict__ u, const double *__restrict__ v, double *__restrict__ uc,
+                              double *__restrict__ vc, int nh, int ny, int nx, int fill) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x + nh;
+  int j = blockIdx.y * blockDim.y + threadIdx.y + nh;
+  if (i >= nx - nh || j >= ny - nh) return;
+  size_t c = (size_t)j * nx + i;
+  double a = mul_rn(0.5, add_rn(u[c], u[c - 1]));
+  double b = mul_rn(0.5, add_rn(v[c], v[c - nx]));
+  uc[c] = a;
+  vc[c] = b;
+  if (fill)
+    for_each_halo_image(j, i, ny, nx, nh, [&](int jj, int ii) {
+      uc[(size_t)jj * nx + ii] = a;
+      vc[(size_t)jj * nx + ii] = b;
+    }, fill == 1);
+}
+extern "C" int f2d_flx_cellvel(const double *u, const double *v, double *uc, double *vc, int nh, int ny, int nx,
+                               int fill_halo, f2d_stream_t s) {
+  if (nh < 1 || ny <= 2 * nh || nx <= 2 * nh) return fail(F2D_ERR_ARG, "flx_cellvel: bad shape");
+  dim3 blk(32, 8), grd(cdiv(nx - 2 * nh, 32), cdiv(ny - 2 * nh, 8));
+  k_flx_cellvel<<<grd, blk, 0, S(s)>>>(u, v, uc, vc, nh, ny, nx, fill_halo);
+  F2D_LAUNCHED();
+  return F2D_OK;
+}
+// core/fluxes.py:160-177: rev = cff*(fwd + sign*bwd), irr = cff*(fwd - sign*bwd), sign = +-1
+extern "C" int f2d_flx_split(double *rev, double *irr, const double *fwd, const double *bwd, double cff, double sign,
+                             size_t n, f2d_stream_t s) {
+  return elementwise(n, S(s), [=] __device__(size_t k) {
+    double sb = mul_rn(sign, bwd[k]);
+    rev[k] = mul_rn(cff, add_rn(fwd[k], sb));
+    irr[k] = mul_rn(cff, add_rn(fwd[k], -sb));
+  });
+}
 extern "C" int f2d_div_scalar(double *y, double d, size_t n, f2d_stream_t s) {
   return elementwise(n, S(s), [=] __device__(size_t k) { y[k] = __ddiv_rn(y[k], d); });
 }

@@ -205,6 +205,14 @@ int f2d_sub_devscalar(double *y, const double *dev_scalar, double denom, size_t 
 int f2d_sub_devscalar_mask(double *y, const double *dev_scalar, double denom,
                            const int8_t *a, size_t n, f2d_stream_t stream);
 
+/* ---- core/fluxes.py (diag_fluxes: reversible / irreversible advective fluxes)
+ * :120-127 uc = 0.5*(u + roll(u,1,axis=1)), vc = 0.5*(v + roll(v,1,axis=0)) + fill_halo */
+int f2d_flx_cellvel(const double *u, const double *v, double *uc, double *vc, int nh, int ny,
+                    int nx, int fill_halo, f2d_stream_t stream);
+/* :160-177 rev = cff*(fwd + sign*bwd), irr = cff*(fwd - sign*bwd)  (sign = +1 or -1) */
+int f2d_flx_split(double *rev, double *irr, const double *fwd, const double *bwd, double cff,
+                  double sign, size_t n, f2d_stream_t stream);
+
 /* ---- core/gmg: hierarchy.Gmg (hierarchy.py:21-218) + level.Grid (level.py:120-496)
  * + the kernels of gmg/fortran_multigrid.f90.
  * f2d_mg_create builds the whole hierarchy on the device: Gridinfo (level.py:24-117,

@@ -12,6 +12,7 @@ reference itself is not available (the GPU box has no /root/reference):
   Stepper                  core/timescheme.py:78-201
   EulerModel/BoussinesqModel  core/euler.py:19-223, core/boussinesq.py:17-153
   Fluid2d (set_dt, ...)    core/fluid2d.py:20-145,351-397
+  Fluxes                   core/fluxes.py:6-213
 
 It is PINNED: tests/test_oracle_golden.py requires that, for the cases of
 tests/golden/cases.py it supports, it reproduces bit for bit the fixtures that
@@ -31,6 +32,7 @@ fa = K.fortran_advection
 fo = K.fortran_operators
 fd = K.fortran_diag
 fm = K.fortran_multigrid
+ff = K.fortran_fluxes
 
 NH = 3
 
@@ -422,12 +424,73 @@ class Stepper(object):
         self.dx2 = np.zeros_like(state)
         self.xb = np.zeros_like(state)
         self.first = True
+        self.second = True
+        self.asselin_cst = 0.1
+        self.ab2_epsilon = 0.1
         self.fast_axpy = fast_axpy    # OpenMP axpys (same bits as numpy), CPU baseline
         self.forward = getattr(self, 'step_'+name)
 
     def step_EF(self, x, t, dt):
         self.rhs(x, t, self.dx0)
         x += dt * self.dx0
+
+    def step_AB2(self, x, t, dt):
+        self.rhs(x, t, self.dx0)
+        if self.first:
+            x += dt * self.dx0
+            self.first = False
+        else:
+            x += ((1.5+self.ab2_epsilon)*dt) * self.dx0 - ((0.5+self.ab2_epsilon)*dt)*self.dx1
+        self.dx1[:] = self.dx0
+
+    def step_AB3(self, x, t, dt):
+        self.rhs(x, t, self.dx0)
+        if self.first:
+            x += dt * self.dx0
+            self.first = False
+        elif self.second:
+            x += (1.5*dt) * self.dx0 - (0.5*dt)*self.dx1
+            self.second = False
+        else:
+            x += (23*dt/12.) * self.dx0 - (16*dt/12.)*self.dx1+(5*dt/12.)*self.dx2
+        self.dx2[:] = self.dx1
+        self.dx1[:] = self.dx0
+
+    def step_LF(self, x, t, dt):
+        self.x[:] = x
+        self.rhs(x, t, self.dx0)
+        if self.first:
+            x += dt * self.dx0
+            self.first = False
+        else:
+            x[:] = self.xb + (2*dt) * self.dx0
+            self.x += self.asselin_cst*(x+self.xb-2*self.x)
+        self.xb[:] = self.x
+
+    def step_RK3(self, x, t, dt):
+        self.kstage = 0
+        self.rhs(x, t, self.dx0)
+        self.x = x + (dt/3.) * self.dx0
+        self.kstage = 1
+        self.rhs(self.x, t+dt/3., self.dx1)
+        self.x = x + (0.5*dt)*self.dx1
+        self.kstage = 2
+        self.rhs(self.x, t+0.5*dt, self.dx2)
+        x += dt*self.dx2
+
+    def step_RK4_LS(self, x, t, dt):
+        self.kstage = 0
+        self.rhs(x, t, self.dx0)
+        self.x = x + (0.25*dt) * self.dx0
+        self.kstage = 1
+        self.rhs(self.x, t+dt*0.25, self.dx0)
+        self.x = x + (dt/3.)*self.dx0
+        self.kstage = 2
+        self.rhs(self.x, t+dt/3., self.dx0)
+        self.x = x + (dt/2.)*self.dx0
+        self.kstage = 3
+        self.rhs(self.x, t+0.5*dt, self.dx0)
+        x += dt*self.dx0
 
     def step_Heun(self, x, t, dt):
         self.kstage = 0
@@ -618,6 +681,81 @@ class BoussinesqModel(object):
         d['brms'] = np.sqrt(b2 / area-(b/area)**2)
 
 
+class Fluxes(object):
+    """core/fluxes.py: one step forward, one step with every velocity-like field reversed;
+    half sum / half difference of the time-integrated face fluxes = reversible /
+    irreversible parts"""
+
+    def __init__(self, param, grid, ope):
+        self.ope = ope
+        self.modelname = param.modelname
+        self.order = param.order
+        self.tracers = list(param.tracer_list) + ['uc', 'vc']
+        names = list(param.varname_list) + ['uc', 'vc']
+        self.nvarstate = len(names)
+        self.flx_list = ['flx_%s_%s' % (v, d) for v in self.tracers for d in 'xy']
+        self.varnames = names + self.flx_list
+        self.fullflx_list = ['%s_%s_%s' % (r, d, v) for r in ('rev', 'irr') for v in self.tracers for d in 'xy']
+        shape = [grid.nyl, grid.nxl]
+        self.x = np.zeros([len(self.varnames)]+shape)
+        self.xe = np.zeros([self.nvarstate]+shape)
+        self.xwork = np.zeros([len(self.varnames)]+shape)
+        self.flx = np.zeros([len(self.fullflx_list)]+shape)
+        self.adv = ff.adv_centered if self.order % 2 == 0 else ff.adv_upwind
+        self.cst = np.zeros(5)
+        self.cst[0], self.cst[1], self.cst[2], self.cst[4] = grid.dx, grid.dy, 0.05, param.aparab
+        self.msk, self.nh = grid.msk, grid.nh
+        self.tscheme = Stepper(param.timestepping, self.x, self.advection)
+
+    def ix(self, name):
+        return self.varnames.index(name)
+
+    def diag_fluxes(self, x, t, dt):
+        nvs = self.nvarstate
+        iu, iv, ip, iw = self.ix('u'), self.ix('v'), self.ix('psi'), self.ix('vorticity')
+        self.xe[:nvs-2] = x
+        y = 0.5*(x[iu]+np.roll(x[iu], 1, axis=1))
+        self.ope.fill_halo(y)
+        self.xe[nvs-2] = y
+        y = 0.5*(x[iv]+np.roll(x[iv], 1, axis=0))
+        self.ope.fill_halo(y)
+        self.xe[nvs-1] = y
+        self.x[:nvs] = self.xe
+        self.x[nvs:] = 0.
+        self.tscheme.forward(self.x, t, dt)
+        self.xwork[:] = self.x
+        self.x[:nvs] = self.xe
+        for k in (iu, iv, ip, iw, nvs-2, nvs-1):
+            self.x[k] *= -1
+        self.x[nvs:] = 0.
+        self.tscheme.forward(self.x, t+dt, -dt)
+        cff = 0.5/dt
+        nflx = len(self.flx_list)
+        for k in range(nflx):
+            ell = nvs+k
+            sign = -1 if (k < 2) or (k >= nflx-4) else 1
+            self.flx[k] = cff*(self.xwork[ell]+sign*self.x[ell])
+            self.flx[nflx+k] = cff*(self.xwork[ell]-sign*self.x[ell])
+
+    def advection(self, x, t, dxdt):
+        self.rhs_adv(x, t, dxdt)
+        if self.modelname == 'boussinesq':
+            self.ope.rhs_torque(x, t, dxdt)
+        self.ope.invert_vorticity(dxdt, flag='fast')
+
+    def rhs_adv(self, x, t, dxdt):
+        u, v = x[self.ix('u')], x[self.ix('v')]
+        self.cst[3] = self.ope.cst[3]
+        nvs = self.nvarstate
+        fs = self.ope.fs_method
+        for it, trac in enumerate(self.tracers):
+            k = self.ix(trac)
+            self.adv(self.msk, x[k], dxdt[k], u, v, dxdt[nvs+2*it], dxdt[nvs+2*it+1], self.cst,
+                     self.nh, fs, self.order)
+            for f in (k, nvs+2*it, nvs+2*it+1):
+                self.ope.fill_halo(dxdt[f])
+
+
 class Fluid2d(object):
     def __init__(self, param, grid, fast_axpy=False):
         self.p, self.g = param, grid
@@ -638,6 +776,9 @@ class Fluid2d(object):
             grid.island.finalize()
             self.model.ope.rhsp = grid.island.rhsp
             self.model.ope.psi = grid.island.psi
+        self.diag_fluxes = bool(getattr(param, 'diag_fluxes', False))
+        if self.diag_fluxes:
+            self.flx = Fluxes(param, grid, self.model.ope)
         self.t = 0.
         self.kt = 0
 

@@ -31,7 +31,8 @@ def _common(param, expname, datadir):
     param.tee_stdout = False   # (fluid2d_b200 extension: do not tee stdout into expdir)
 
 
-def freedecay(api, datadir, n=64, order=5, tracer=True, timestepping='RK3_SSP', ny=None, npy=1, tile=False):
+def freedecay(api, datadir, n=64, order=5, tracer=True, timestepping='RK3_SSP', ny=None, npy=1, tile=False,
+              diag_fluxes=False):
     """ny != n gives a rectangular domain with dx = dy; npy > 1 splits it in y-slabs (one
     rank per slab, like the reference run under mpirun with npx=1, npy=nranks); tile=True
     (needs ny = n*npy) repeats the n x n field in every slab instead of drawing a global one"""
@@ -53,6 +54,7 @@ def freedecay(api, datadir, n=64, order=5, tracer=True, timestepping='RK3_SSP', 
     param.forcing = False
     param.noslip = False
     param.diffusion = False
+    param.diag_fluxes = diag_fluxes
     if tracer:
         param.additional_tracer = ['tracer']
     grid = api.Grid(param)
@@ -92,23 +94,23 @@ def freedecay(api, datadir, n=64, order=5, tracer=True, timestepping='RK3_SSP', 
     return f2d
 
 
-def vortex(api, datadir, n=64, order=3, msk_config='none'):
+def vortex(api, datadir, n=64, order=3, msk_config='none', timestepping='RK3_SSP', diffusion=False, cfl=1.):
     param = api.Param('default.xml')
     param.modelname = 'euler'
-    _common(param, 'vortex_%i_%s' % (n, msk_config), datadir)
+    _common(param, 'vortex_%i_%s_%s' % (n, msk_config, timestepping), datadir)
     param.nx = n
     param.ny = n
     param.Ly = param.Lx
     param.geometry = 'closed'
-    param.cfl = 1.
+    param.cfl = cfl
     param.adaptable_dt = True
     param.dt = 0.01
     param.dtmax = 100
     param.order = order
-    param.timestepping = 'RK3_SSP'
+    param.timestepping = timestepping
     param.var_to_save = ['vorticity', 'psi', 'tracer']
     param.noslip = False
-    param.diffusion = False
+    param.diffusion = diffusion
     param.additional_tracer = ['tracer']
     grid = api.Grid(param)
     param.Kdiff = 5e-2*grid.dx
@@ -161,7 +163,7 @@ class CoolRoof(object):
         dxdt[4] *= coef
 
 
-def rb(api, datadir, nx=64):
+def rb(api, datadir, nx=64, diag_fluxes=False):
     param = api.Param('default.xml')
     param.modelname = 'boussinesq'
     _common(param, 'rb_%i' % nx, datadir)
@@ -182,6 +184,7 @@ def rb(api, datadir, nx=64):
     param.forcing_module = 'embedded'
     param.diffusion = True
     param.noslip = True
+    param.diag_fluxes = diag_fluxes
     grid = api.Grid(param)
     param.deltab = 600
     visco = .002*grid.dy
@@ -296,7 +299,18 @@ CASES = {
     'rb_64': lambda api, d: rb(api, d, 64),
     'karman_32': lambda api, d: karman(api, d, 32),
     'qg_32': lambda api, d: qg(api, d, 32),
+    # diag_fluxes=True: the fixture also holds the reversible / irreversible flux stack of
+    # core/fluxes.py at the initial state (flx0) and after the ten steps (flx10)
+    'freedecay_32_flx': lambda api, d: freedecay(api, d, 32, diag_fluxes=True),
+    'rb_32_flx': lambda api, d: rb(api, d, 32, diag_fluxes=True),
 }
+# every other stepper of core/timescheme.py:78-201, with diffusion on so that the
+# `kstage == kforcing` branch of Euler.dynamics is exercised (light fixtures: states only)
+SCHEMES = ['EF', 'LF', 'Heun', 'AB2', 'AB3', 'LFAM3', 'RK4_LS']   # ('RK3' is not in param.py's list)
+LIGHT = set()
+for _ts in SCHEMES:
+    CASES['vortex_32_%s' % _ts] = (lambda api, d, ts=_ts: vortex(api, d, 32, timestepping=ts, diffusion=True, cfl=0.25))
+    LIGHT.add('vortex_32_%s' % _ts)
 
 NSTEPS = (1, 10)
 
@@ -322,3 +336,14 @@ def run_steps(f2d, nsteps=NSTEPS):
                        float(f2d.dt),
                        {k: float(np.asarray(v).ravel()[0]) for k, v in model.diags.items()})
     return out
+
+
+def run_fluxes(f2d):
+    """The flux diagnostic the way Fluid2d.loop() triggers it before a history write
+    (fluid2d.py:204-210, 290-292): refresh maxspeed, set dt, Fluxes.diag_fluxes on the
+    model state; returns a copy of the stack [rev_x_*, rev_y_*, ..., irr_x_*, ...]."""
+    model = f2d.model
+    model.diagnostics(model.var, f2d.t)
+    f2d.set_dt(f2d.kt)
+    f2d.flx.diag_fluxes(model.var.state, f2d.t, f2d.dt)
+    return np.array(f2d.flx.flx, dtype=float, copy=True)

@@ -9,6 +9,8 @@ Operators, gmg.Gmg -- with the reference's f2py kernels replaced by the CPU orac
   state{k}, t{k}, dt{k}, diag{k}_<name>   after k = 1 and 10 iterations of the loop body
   mg_nlevs, mg_msk{l}, mg_A{l}            multigrid masks and 5-diagonal matrices
   mg_shape{l}                             (m, n) interior size per level
+  flxnames, flx0, flx10                   (diag_fluxes cases) core/fluxes.py's stack of reversible /
+                                          irreversible fluxes at the initial state and after 10 steps
   varnames, grid_msk
 
 Usage:  python tests/golden/make_golden.py [case ...]
@@ -58,11 +60,14 @@ def generate(names=None):
         out["grid_msk"] = np.array(f2d.msk if hasattr(f2d, "msk") else model.msk, copy=True)
         gmg = model.ope.gmg
         out["mg_nlevs"] = np.array(gmg.nlevs)
-        for lev in range(gmg.nlevs):
+        for lev in range(0 if name in cases.LIGHT else gmg.nlevs):
             g = gmg.grid[lev]
             out["mg_msk%i" % lev] = np.array(g.msk, dtype=np.int8, copy=True)
             out["mg_A%i" % lev] = np.array(g.A, copy=True)
             out["mg_shape%i" % lev] = np.array([g.m, g.n])
+        if getattr(f2d, "diag_fluxes", False):
+            out["flxnames"] = np.array(f2d.flx.fullflx_list)
+            out["flx0"] = cases.run_fluxes(f2d)
         res = cases.run_steps(f2d)
         for k, (state, t, dt, diags) in res.items():
             out["state%i" % k] = state
@@ -70,6 +75,8 @@ def generate(names=None):
             out["dt%i" % k] = np.array(dt)
             for dn, dv in diags.items():
                 out["diag%i_%s" % (k, dn)] = np.array(dv)
+        if getattr(f2d, "diag_fluxes", False):
+            out["flx10"] = cases.run_fluxes(f2d)
         sys.stdout = real_stdout
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **out)

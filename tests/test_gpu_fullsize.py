@@ -1,0 +1,225 @@
+"""Parity at the FULL sizes of BASELINE.json's configs (4096^2, 4096x1024, 2048x1024), where
+the CPU oracle cannot run a whole step in seconds, through size-independent properties:
+
+ * periodic tiling: every operator of the path is a local stencil on a doubly periodic
+   array, so a full-size input made of copies of a small periodic tile must give copies
+   of the ORACLE's result on that tile -- checked for the advection kernel (masked and
+   mask-free), the level-0 multigrid operators (smooth, residual, restriction,
+   interpolation) and the halo fill;
+ * shift equivariance of a whole multigrid V-cycle pair on the 11-level hierarchy;
+ * flux form: the advective tendency of a periodic field sums to zero;
+ * the inversion contracts: the full solve reaches the reference's iteration count bound and
+   its residual falls, level-0 residual of the result recomputed independently.
+
+Bit-exact on the -fmad=false build, rel L2 <= 1e-13 on the product build (per kernel)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import kernels as K  # noqa: E402
+from oracle import model as om  # noqa: E402
+
+NH = 3
+SIZES = [(4096, 4096), (1024, 4096), (1024, 2048)]     # (ny, nx) of S1, S4 (VonKarman), S3 (RB)
+TILE = 128
+
+
+@pytest.fixture(params=["strict", "product"])
+def L(request):
+    from fluid2d_b200 import _lib
+    return _lib.lib(strict=request.param == "strict"), request.param == "strict"
+
+
+@pytest.fixture(autouse=True)
+def _release_device_buffers():
+    yield
+    import torch
+    import gpu_util as g
+    torch.cuda.synchronize()
+    del g._alive[:]
+    torch.cuda.empty_cache()
+
+
+def tiled(tile_with_halo, ny, nx):
+    """full-size array with halo whose interior is the tile's interior repeated"""
+    t = tile_with_halo[NH:-NH, NH:-NH]
+    full = np.tile(t, (ny//t.shape[0], nx//t.shape[1]))
+    out = np.zeros((ny+2*NH, nx+2*NH), dtype=tile_with_halo.dtype)
+    out[NH:-NH, NH:-NH] = full
+    # periodic halo
+    out[:NH, NH:-NH] = full[-NH:, :]
+    out[-NH:, NH:-NH] = full[:NH, :]
+    out[:, :NH] = out[:, -2*NH:-NH]
+    out[:, -NH:] = out[:, NH:2*NH]
+    return out
+
+
+def check_tiles(full, tile_ref, strict, what, tol=1e-13):
+    """every tile of the device result against the oracle's tile (interior only)"""
+    ref = tile_ref[NH:-NH, NH:-NH]
+    ty, tx = ref.shape
+    inner = full[NH:-NH, NH:-NH]
+    ny, nx = inner.shape
+    blocks = inner.reshape(ny//ty, ty, nx//tx, tx).transpose(0, 2, 1, 3)
+    if strict:
+        assert np.array_equal(blocks, np.broadcast_to(ref, blocks.shape)), what
+    else:
+        err = np.linalg.norm((blocks-ref).reshape(-1, ty*tx), axis=1).max()/np.linalg.norm(ref)
+        assert err <= tol, "%s: worst tile rel L2 %.3e" % (what, err)
+    # and the halo is the periodic image of the interior
+    np.testing.assert_array_equal(full[:NH, NH:-NH], inner[-NH:, :], err_msg=what+" (south halo)")
+    np.testing.assert_array_equal(full[NH:-NH, -NH:], inner[:, :NH], err_msg=what+" (east halo)")
+
+
+@pytest.mark.parametrize("ny,nx", SIZES)
+@pytest.mark.parametrize("masked", [False, True])
+@pytest.mark.parametrize("order", [5, 3])
+def test_advection_tiled(L, ny, nx, masked, order):
+    import gpu_util as g
+    lib, strict = L
+    rng = np.random.default_rng(ny+nx+order)
+    shape = (TILE+2*NH, TILE+2*NH)
+    msk = np.ones(shape, dtype=np.int8)
+    if masked:
+        yy, xx = np.mgrid[0:shape[0], 0:shape[1]]
+        msk[(yy-50)**2+(xx-70)**2 < 15**2] = 0
+        msk[90:93, 20:100] = 0
+    fields = []
+    for _ in range(3):
+        f = rng.standard_normal(shape)
+        K.fortran_multigrid.fillhalo(f, NH)
+        fields.append(f)
+    q, u, v = fields[0], 0.3*fields[1], 0.3*fields[2]
+    cst = np.array([1./nx, 1./nx, 0.05, 1.1, 0.05])
+    ref = np.zeros(shape)
+    K.fortran_advection.adv_upwind(msk, q, ref, u, v, cst, NH, 1, order)
+    K.fortran_multigrid.fillhalo(ref, NH)
+    dq = g.dev(np.zeros((ny+2*NH, nx+2*NH)))
+    cc = (ctypes.c_double*5)(*cst)
+    dm = g.ptr(g.keep(tiled(msk, ny, nx))) if masked else None
+    lib.adv_upwind(dm, g.ptr(g.keep(tiled(q, ny, nx))), g.ptr(dq), g.ptr(g.keep(tiled(u, ny, nx))),
+                   g.ptr(g.keep(tiled(v, ny, nx))), None, None, cc, NH, 1, order, ny+2*NH, nx+2*NH, 1, g.stream())
+    out = g.host(dq)
+    check_tiles(out, ref, strict, "adv_upwind order %d %dx%d" % (order, ny, nx))
+    # flux form on a periodic domain: the tendency sums to zero (to rounding)
+    if not masked:
+        s = out[NH:-NH, NH:-NH].sum()
+        assert abs(s) <= 1e-9*np.abs(out).sum()
+
+
+@pytest.mark.parametrize("ny,nx", SIZES)
+def test_level0_operators_tiled(L, ny, nx):
+    """smooth / residual / restriction / interpolation of the finest level of the full-size
+    doubly periodic hierarchy against the oracle's on one 128^2 periodic tile (same dx)"""
+    import gpu_util as g
+    lib, strict = L
+    rng = np.random.default_rng(ny*3+nx)
+    dx = 1./nx
+    cm = np.ones((TILE+2*NH, TILE+2*NH))
+    cm[-1, :] = 0
+    cm[:, -1] = 0
+    ref = om.MG(cm, TILE, TILE, dx, dx)
+    cmf = np.ones((ny+2*NH, nx+2*NH))
+    cmf[-1, :] = 0
+    cmf[:, -1] = 0
+    h = ctypes.c_void_p()
+    s = g.stream()
+    lib.mg_create(ctypes.byref(h), g.ptr(g.keep(cmf)), ny+2*NH, nx+2*NH, dx, dx, 8./9., 1., 0., s)
+    try:
+        shape = ref.msk[0].shape
+        x = rng.standard_normal(shape)
+        b = rng.standard_normal(shape)*nx*nx
+        K.fortran_multigrid.fillhalo(x, NH)
+        K.fortran_multigrid.fillhalo(b, NH)
+        X, B = g.keep(tiled(x, ny, nx)), g.keep(tiled(b, ny, nx))
+        for nite in (1, 2):
+            xr = x.copy()
+            ref.smooth(0, xr, b, nite)
+            d = X.clone()
+            lib.mg_smooth(h, 0, g.ptr(d), g.ptr(B), nite, s)
+            check_tiles(g.host(d), xr, strict, "smooth x%d %dx%d" % (nite, ny, nx))
+        rr = np.zeros(shape)
+        ref.residual(0, x, b, rr)
+        d = g.dev(np.zeros((ny+2*NH, nx+2*NH)))
+        lib.mg_residual(h, 0, g.ptr(X), g.ptr(B), g.ptr(d), s)
+        check_tiles(g.host(d), rr, strict, "residual %dx%d" % (ny, nx))
+        cshape = ref.msk[1].shape
+        xc = np.zeros(cshape)
+        ref.down(0, x, xc)
+        d = g.dev(np.zeros((ny//2+2*NH, nx//2+2*NH)))
+        lib.mg_restrict(h, 0, g.ptr(X), g.ptr(d), s)
+        check_tiles(g.host(d), xc, strict, "restrict %dx%d" % (ny, nx))
+        c = rng.standard_normal(cshape)
+        K.fortran_multigrid.fillhalo(c, NH)
+        xf = np.zeros(shape)
+        ref.up(0, c, xf)
+        K.fortran_multigrid.fillhalo(xf, NH)
+        d = g.dev(np.zeros((ny+2*NH, nx+2*NH)))
+        lib.mg_interpolate(h, 0, g.ptr(g.keep(tiled(c, ny//2, nx//2))), g.ptr(d), 0, s)
+        out = g.host(d)
+        ref_in = xf[NH:-NH, NH:-NH]
+        blocks = out[NH:-NH, NH:-NH].reshape(ny//TILE, TILE, nx//TILE, TILE).transpose(0, 2, 1, 3)
+        if strict:
+            assert np.array_equal(blocks, np.broadcast_to(ref_in, blocks.shape)), "interpolate"
+        else:
+            assert np.abs(blocks-ref_in).max() <= 1e-13*np.abs(ref_in).max()
+    finally:
+        lib.mg_destroy(h)
+
+
+@pytest.mark.parametrize("ny,nx", SIZES)
+def test_two_vcycle_shift_equivariance(L, ny, nx):
+    """the doubly periodic hierarchy has no preferred origin at even offsets that survive
+    every coarsening: shifting rhs and first guess by a multiple of 2^(nlevels-1) cells
+    shifts the result of twoVcycle, bit for bit -- and the full solve contracts"""
+    import torch
+    import gpu_util as g
+    lib, strict = L
+    dx = 1./nx
+    cmf = np.ones((ny+2*NH, nx+2*NH))
+    cmf[-1, :] = 0
+    cmf[:, -1] = 0
+    h = ctypes.c_void_p()
+    s = g.stream()
+    lib.mg_create(ctypes.byref(h), g.ptr(g.keep(cmf)), ny+2*NH, nx+2*NH, dx, dx, 8./9., 1., 0., s)
+    try:
+        nlev = lib.mg_nlevels(h)
+        sh = 2**(nlev-1)
+        gen = torch.Generator(device="cuda").manual_seed(ny+nx)
+        rhs = torch.randn((ny, nx), dtype=torch.float64, device="cuda", generator=gen)
+        rhs -= rhs.mean()
+
+        def with_halo(t):
+            f = torch.zeros((ny+2*NH, nx+2*NH), dtype=torch.float64, device="cuda")
+            f[NH:-NH, NH:-NH] = t
+            lib.fill_halo(g.ptr(f), NH, ny+2*NH, nx+2*NH, s)
+            return f
+        outs = []
+        for shift in (0, 1):
+            r = with_halo(torch.roll(rhs, (shift*sh, shift*2*sh % nx), (0, 1)))
+            psi = torch.zeros_like(r)
+            lib.mg_two_vcycle(h, g.ptr(psi), g.ptr(r), s)
+            outs.append(psi[NH:-NH, NH:-NH].clone())
+        torch.cuda.synchronize()
+        moved = torch.roll(outs[0], (sh, 2*sh % nx), (0, 1))
+        if strict:
+            assert torch.equal(moved, outs[1])
+        else:   # rim and inner tiles are different instantiations: FMA contraction may differ
+            assert float(torch.linalg.norm(moved-outs[1])/torch.linalg.norm(outs[1])) <= 1e-13
+        # full solve: iteration count within the reference's bound, residual recomputed independently
+        r = with_halo(rhs)
+        psi = torch.zeros_like(r)
+        nite, res = ctypes.c_int(), ctypes.c_double()
+        lib.mg_solve(h, g.ptr(psi), g.ptr(r), 1e-11, 4, ctypes.byref(nite), ctypes.byref(res), s)
+        assert 1 <= nite.value <= 4
+        rr = torch.zeros_like(r)
+        lib.mg_residual(h, 0, g.ptr(psi), g.ptr(r), g.ptr(rr), s)
+        torch.cuda.synchronize()
+        mine = float(torch.linalg.norm(rr[NH:-NH, NH:-NH])/torch.linalg.norm(r[NH:-NH, NH:-NH]))
+        assert abs(mine-res.value) <= 1e-6*res.value + 1e-15
+        assert res.value < 1e-4
+    finally:
+        lib.mg_destroy(h)

@@ -251,7 +251,10 @@ class Operators(Param):
             print('-'*50)
             print(' Convergence of the vorticity inversion')
             print('-'*50)
-        lib.invert_vorticity(self.gmg.h, r.ptr(self.d_msk), r.ptr(self.d_mskp), x.rptr(iw), x.wptr(ip),
+        # all-fluid domain without island: the mask-free orthogradient (no mask traffic)
+        nomask = self.all_fluid and not island and self.nxl % 2 == 0
+        lib.invert_vorticity(self.gmg.h, None if nomask else r.ptr(self.d_msk),
+                             None if nomask else r.ptr(self.d_mskp), x.rptr(iw), x.wptr(ip),
                              x.wptr(iu), x.wptr(iv), r.ptr(self.work), rhsp, psi_island, full,
                              1 if self.geometry == 'perio' else 0, float(np.asarray(self.area).ravel()[0]),
                              self.dx, self.dy, self.nh, ctypes.byref(nite), ctypes.byref(res),

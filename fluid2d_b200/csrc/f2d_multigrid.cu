@@ -1328,7 +1328,9 @@ extern "C" int f2d_invert_vorticity(f2d_mg_t *mg, const int8_t *msk, const int8_
                                     const double *psi_island, int full, int perio, double area, double dx,
                                     double dy, int nh, int *nite, double *res, double *scratch,
                                     f2d_stream_t stream) {
-  if (!mg || !msk || !mskp || !w || !psi || !u || !v || !work) return fail(F2D_ERR_ARG, "invert_vorticity: null");
+  if (!mg || !w || !psi || !u || !v || !work) return fail(F2D_ERR_ARG, "invert_vorticity: null");
+  if ((msk == nullptr) != (mskp == nullptr) || (!msk && psi_island))
+    return fail(F2D_ERR_ARG, "invert_vorticity: msk and mskp may only be omitted together (all-fluid domain, no island)");
   if (nh != NH) return fail(F2D_ERR_NH, "invert_vorticity: nh must be 3");
   Level &l = mg->comm ? mg->S[0] : mg->L[0];
   size_t n = l.n();

@@ -92,8 +92,49 @@ __global__ void k_celltocorner(const double *__restrict__ xr, double *__restrict
   if (j > ny - 2 || i > nx - 2) return;
   xp[c] = 0.25 * (((xr[c] + xr[c + 1]) + xr[c + nx]) + xr[c + nx + 1]);
 }
+// Strip version (nx even): a thread owns two adjacent columns and marches C2C_ROWS rows
+// north; each row is read once as a 16-byte vector (+ the east neighbour from the next
+// lane), the pair sums (xr(j,i)+xr(j,i+1)) of the row are reused as the south pair of the
+// next row.  Same association as the Fortran: ((a + b) + c) + d.
+constexpr int C2C_ROWS = 16;
+__global__ void __launch_bounds__(128) k_celltocorner_strip(const double *__restrict__ xr, double *__restrict__ xp,
+                                                            int ny, int nx) {
+  const int i = (blockIdx.x * 128 + threadIdx.x) * 2;
+  const int j0 = blockIdx.y * C2C_ROWS;
+  const bool active = i < nx;
+  const unsigned lane = threadIdx.x & 31;
+  auto row = [&](int j, double2 &a, double &e) {   // xr(j,i), xr(j,i+1), xr(j,i+2)
+    a = make_double2(0., 0.);
+    if (active) a = *reinterpret_cast<const double2 *>(xr + (size_t)j * nx + i);
+    e = __shfl_down_sync(0xffffffffu, a.x, 1);
+    if (active && lane == 31) e = (i + 2 < nx) ? xr[(size_t)j * nx + i + 2] : 0.;
+  };
+  double2 a, an;
+  double e, en;
+  row(j0, a, e);
+  for (int r = 0; r < C2C_ROWS; r++) {
+    const int j = j0 + r;
+    if (j > ny - 2) break;
+    row(j + 1, an, en);
+    if (active) {
+      const size_t c = (size_t)j * nx + i;
+      double o0 = 0.25 * (((a.x + a.y) + an.x) + an.y);
+      double o1 = 0.25 * (((a.y + e) + an.y) + en);
+      if (i + 1 <= nx - 2) *reinterpret_cast<double2 *>(xp + c) = make_double2(o0, o1);
+      else xp[c] = o0;   // i + 1 is the last column, which celltocorner leaves untouched
+    }
+    a = an;
+    e = en;
+  }
+}
 extern "C" int f2d_celltocorner(const double *xr, double *xp, int ny, int nx, f2d_stream_t s) {
   if (!xr || !xp || ny < 2 || nx < 2) return fail(F2D_ERR_ARG, "celltocorner: bad args");
+  if (nx % 2 == 0 && ((reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(xp)) & 15) == 0) {
+    dim3 g(cdiv(nx, 256), cdiv(ny - 1, C2C_ROWS));
+    k_celltocorner_strip<<<g, 128, 0, S(s)>>>(xr, xp, ny, nx);
+    F2D_LAUNCHED();
+    return F2D_OK;
+  }
   dim3 b(32, 8);
   k_celltocorner<<<grid2d(ny, nx, b), b, 0, S(s)>>>(xr, xp, ny, nx);
   F2D_LAUNCHED();
@@ -153,10 +194,98 @@ __global__ void k_mask_orthogradient(const int8_t *__restrict__ msk, const int8_
   u[c] = (m0 + msk[c + 1] == 2) ? zdy * (ps - p) : 0.;
   v[c] = (m0 + msk[c + nx] == 2) ? zdx * (p - pw) : 0.;
 }
+// Strip version (nx even, so that every row start is 16-byte aligned): a thread owns two
+// adjacent columns and marches OG_ROWS rows north, keeping the masked psi of the row below
+// in registers; psi / u / v move as 16-byte vectors, the west neighbour of the pair comes
+// from the lane to the left.  ALLFLUID (msk == NULL): the cell mask is 1 everywhere and the
+// corner mask is 1 except on the last row and column, so no mask byte is read at all.
+constexpr int OG_ROWS = 16;
+template <bool ALLFLUID>
+__global__ void __launch_bounds__(128) k_mask_orthogradient_strip(const int8_t *__restrict__ msk,
+                                                                  const int8_t *__restrict__ mskp, double *psi,
+                                                                  double zdx, double zdy, double *__restrict__ u,
+                                                                  double *__restrict__ v, int ny, int nx) {
+  const int i = (blockIdx.x * 128 + threadIdx.x) * 2;
+  const int j0 = blockIdx.y * OG_ROWS;
+  const bool active = i < nx;
+  const unsigned lane = threadIdx.x & 31;
+  auto masked2 = [&](int j) -> double2 {
+    const size_t c = (size_t)j * nx + i;
+    double2 p = *reinterpret_cast<const double2 *>(psi + c);
+    double m0, m1;
+    if (ALLFLUID) {
+      m0 = (j < ny - 1) ? 1. : 0.;
+      m1 = (j < ny - 1 && i + 1 < nx - 1) ? 1. : 0.;
+    } else {
+      char2 m = *reinterpret_cast<const char2 *>(mskp + c);
+      m0 = (double)m.x;
+      m1 = (double)m.y;
+    }
+    return make_double2(__dmul_rn(p.x, m0), __dmul_rn(p.y, m1));
+  };
+  auto masked1 = [&](int j, int ii) -> double {
+    const size_t c = (size_t)j * nx + ii;
+    double m = ALLFLUID ? ((j < ny - 1 && ii < nx - 1) ? 1. : 0.) : (double)mskp[c];
+    return __dmul_rn(psi[c], m);
+  };
+  double2 ps = make_double2(0., 0.);
+  if (active && j0 > 0) ps = masked2(j0 - 1);
+  for (int r = 0; r < OG_ROWS; r++) {
+    const int j = j0 + r;
+    if (j >= ny) break;
+    double2 p = make_double2(0., 0.);
+    if (active) p = masked2(j);
+    double pw = __shfl_up_sync(0xffffffffu, p.y, 1);
+    if (active) {
+      const size_t c = (size_t)j * nx + i;
+      *reinterpret_cast<double2 *>(psi + c) = p;
+      if (j >= 1 && j <= ny - 2) {
+        if (lane == 0) pw = i > 0 ? masked1(j, i - 1) : 0.;
+        bool ue0 = true, ue1 = true, vn0 = true, vn1 = true;
+        if (!ALLFLUID) {
+          char2 m = *reinterpret_cast<const char2 *>(msk + c);
+          char2 mn = *reinterpret_cast<const char2 *>(msk + c + nx);
+          int me = (i + 2 < nx) ? msk[c + 2] : 0;
+          ue0 = m.x + m.y == 2;
+          ue1 = m.y + me == 2;
+          vn0 = m.x + mn.x == 2;
+          vn1 = m.y + mn.y == 2;
+        }
+        double2 uu, vv;
+        uu.x = ue0 ? zdy * (ps.x - p.x) : 0.;
+        uu.y = ue1 ? zdy * (ps.y - p.y) : 0.;
+        vv.x = vn0 ? zdx * (p.x - pw) : 0.;
+        vv.y = vn1 ? zdx * (p.y - p.x) : 0.;
+        if (i >= 1 && i + 1 <= nx - 2) {
+          *reinterpret_cast<double2 *>(u + c) = uu;
+          *reinterpret_cast<double2 *>(v + c) = vv;
+        } else {
+          if (i >= 1) { u[c] = uu.x; v[c] = vv.x; }
+          if (i + 1 <= nx - 2) { u[c + 1] = uu.y; v[c + 1] = vv.y; }
+        }
+      }
+    }
+    ps = p;
+  }
+}
+/* msk == NULL: all-fluid domain (cell mask 1 everywhere, corner mask 1 except on the last
+ * row and column) */
 extern "C" int f2d_mask_orthogradient(const int8_t *msk, const int8_t *mskp, double *psi, double dx, double dy,
                                       int nh, double *u, double *v, int ny, int nx, f2d_stream_t s) {
   (void)nh;
-  if (!msk || !mskp || !psi || !u || !v || ny < 3 || nx < 3) return fail(F2D_ERR_ARG, "mask_orthogradient: bad args");
+  if (!psi || !u || !v || ny < 3 || nx < 3) return fail(F2D_ERR_ARG, "mask_orthogradient: bad args");
+  if ((msk == nullptr) != (mskp == nullptr)) return fail(F2D_ERR_ARG, "mask_orthogradient: msk and mskp go together");
+  const bool vec_ok = nx % 2 == 0 && ((reinterpret_cast<uintptr_t>(psi) | reinterpret_cast<uintptr_t>(u) |
+                                       reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
+                      (!msk || ((reinterpret_cast<uintptr_t>(msk) | reinterpret_cast<uintptr_t>(mskp)) & 1) == 0);
+  if (vec_ok) {
+    dim3 g(cdiv(nx, 256), cdiv(ny, OG_ROWS));
+    if (msk) k_mask_orthogradient_strip<false><<<g, 128, 0, S(s)>>>(msk, mskp, psi, 1. / dx, 1. / dy, u, v, ny, nx);
+    else k_mask_orthogradient_strip<true><<<g, 128, 0, S(s)>>>(msk, mskp, psi, 1. / dx, 1. / dy, u, v, ny, nx);
+    F2D_LAUNCHED();
+    return F2D_OK;
+  }
+  if (!msk) return fail(F2D_ERR_ARG, "mask_orthogradient: the mask-free form needs even nx and 16-byte aligned fields");
   dim3 b(32, 8);
   k_mask_orthogradient<<<grid2d(ny, nx, b), b, 0, S(s)>>>(msk, mskp, psi, 1. / dx, 1. / dy, u, v, ny, nx);
   F2D_LAUNCHED();
@@ -297,46 +426,124 @@ static int elementwise(size_t n, cudaStream_t s, F f) {
   return F2D_OK;
 }
 
+// Streaming map out[k] = f(in0[k], ..., in{N-1}[k]) for the whole-state combinations of
+// the time schemes: 16-byte accesses, two vectors per thread and iteration with every load
+// issued before the first store (out may alias an input, so the compiler cannot hoist them
+// itself) -- 4..10 independent 16 B loads in flight per thread keep HBM3e busy.
+template <int NIN>
+struct VecIn { const double2 *p[NIN]; };
+template <int NIN, class F>
+__device__ __forceinline__ double2 vec_apply(const double2 (&a)[NIN], F f) {
+  double lo[NIN], hi[NIN];
+#pragma unroll
+  for (int q = 0; q < NIN; q++) { lo[q] = a[q].x; hi[q] = a[q].y; }
+  return make_double2(f(lo), f(hi));
+}
+template <int NIN, class F>
+__global__ void __launch_bounds__(256) k_map_vec(size_t nvec, double2 *out, VecIn<NIN> in, F f) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  for (; k + stride < nvec; k += 2 * stride) {
+    double2 a[NIN], b[NIN];
+#pragma unroll
+    for (int q = 0; q < NIN; q++) a[q] = in.p[q][k];
+#pragma unroll
+    for (int q = 0; q < NIN; q++) b[q] = in.p[q][k + stride];
+    out[k] = vec_apply<NIN>(a, f);
+    out[k + stride] = vec_apply<NIN>(b, f);
+  }
+  if (k < nvec) {
+    double2 a[NIN];
+#pragma unroll
+    for (int q = 0; q < NIN; q++) a[q] = in.p[q][k];
+    out[k] = vec_apply<NIN>(a, f);
+  }
+}
+template <int NIN, class F>
+__global__ void k_map_scalar(size_t k0, size_t n, double *out, VecIn<NIN> in, F f) {
+  for (size_t k = k0 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    double a[NIN];
+#pragma unroll
+    for (int q = 0; q < NIN; q++) a[q] = reinterpret_cast<const double *>(in.p[q])[k];
+    out[k] = f(a);
+  }
+}
+template <int NIN, class F>
+static int map_fields(size_t n, cudaStream_t s, double *out, const double *const (&inp)[NIN], F f) {
+  if (n == 0) return F2D_OK;
+  VecIn<NIN> in;
+  bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  for (int q = 0; q < NIN; q++) {
+    in.p[q] = reinterpret_cast<const double2 *>(inp[q]);
+    aligned = aligned && (reinterpret_cast<uintptr_t>(inp[q]) & 15) == 0;
+  }
+  size_t nvec = aligned ? n / 2 : 0;
+  if (nvec) {
+    long long blocks = (long long)((nvec + 511) / 512);
+    if (blocks > 148LL * 8) blocks = 148LL * 8;
+    k_map_vec<NIN><<<(int)blocks, 256, 0, s>>>(nvec, reinterpret_cast<double2 *>(out), in, f);
+    F2D_LAUNCHED();
+  }
+  if (2 * nvec < n) {   // unaligned fields, or the odd last element
+    size_t rest = n - 2 * nvec;
+    long long blocks = (long long)((rest + 255) / 256);
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    k_map_scalar<NIN><<<(int)blocks, 256, 0, s>>>(2 * nvec, n, out, in, f);
+    F2D_LAUNCHED();
+  }
+  return F2D_OK;
+}
+
 extern "C" int f2d_ts_axpy(double *y, double c, const double *a, size_t n, f2d_stream_t s) {
-  return elementwise(n, S(s), [=] __device__(size_t k) { y[k] = add_rn(y[k], mul_rn(c, a[k])); });
+  const double *const in[2] = {y, a};
+  return map_fields<2>(n, S(s), y, in, [=] __device__(const double (&v)[2]) { return add_rn(v[0], mul_rn(c, v[1])); });
 }
 extern "C" int f2d_ts_xpay(double *out, const double *x, double c, const double *a, size_t n, f2d_stream_t s) {
-  return elementwise(n, S(s), [=] __device__(size_t k) { out[k] = add_rn(x[k], mul_rn(c, a[k])); });
+  const double *const in[2] = {x, a};
+  return map_fields<2>(n, S(s), out, in, [=] __device__(const double (&v)[2]) { return add_rn(v[0], mul_rn(c, v[1])); });
 }
 extern "C" int f2d_ts_xpay2(double *out, const double *x, double c, const double *a, const double *b, size_t n,
                             f2d_stream_t s) {
-  return elementwise(n, S(s), [=] __device__(size_t k) { out[k] = add_rn(x[k], mul_rn(c, add_rn(a[k], b[k]))); });
+  const double *const in[3] = {x, a, b};
+  return map_fields<3>(n, S(s), out, in,
+                       [=] __device__(const double (&v)[3]) { return add_rn(v[0], mul_rn(c, add_rn(v[1], v[2]))); });
 }
 extern "C" int f2d_ts_rk3ssp_final(double *x, double c, const double *a, const double *b, const double *d,
                                    size_t n, f2d_stream_t s) {
-  return elementwise(n, S(s), [=] __device__(size_t k) {
-    x[k] = add_rn(x[k], mul_rn(c, add_rn(add_rn(a[k], b[k]), mul_rn(4., d[k]))));
+  const double *const in[4] = {x, a, b, d};
+  return map_fields<4>(n, S(s), x, in, [=] __device__(const double (&v)[4]) {
+    return add_rn(v[0], mul_rn(c, add_rn(add_rn(v[1], v[2]), mul_rn(4., v[3]))));
   });
 }
 extern "C" int f2d_ts_ab2(double *x, double c0, const double *a, double c1, const double *b, size_t n,
                           f2d_stream_t s) {
-  return elementwise(n, S(s), [=] __device__(size_t k) {
-    x[k] = add_rn(x[k], add_rn(mul_rn(c0, a[k]), -mul_rn(c1, b[k])));
+  const double *const in[3] = {x, a, b};
+  return map_fields<3>(n, S(s), x, in, [=] __device__(const double (&v)[3]) {
+    return add_rn(v[0], add_rn(mul_rn(c0, v[1]), -mul_rn(c1, v[2])));
   });
 }
 extern "C" int f2d_ts_ab3(double *x, double c0, const double *a, double c1, const double *b, double c2,
                           const double *d, size_t n, f2d_stream_t s) {
-  return elementwise(n, S(s), [=] __device__(size_t k) {
-    x[k] = add_rn(x[k], add_rn(add_rn(mul_rn(c0, a[k]), -mul_rn(c1, b[k])), mul_rn(c2, d[k])));
+  const double *const in[4] = {x, a, b, d};
+  return map_fields<4>(n, S(s), x, in, [=] __device__(const double (&v)[4]) {
+    return add_rn(v[0], add_rn(add_rn(mul_rn(c0, v[1]), -mul_rn(c1, v[2])), mul_rn(c2, v[3])));
   });
 }
 extern "C" int f2d_ts_set_xpay(double *x, const double *xb, double c, const double *a, size_t n, f2d_stream_t s) {
-  return elementwise(n, S(s), [=] __device__(size_t k) { x[k] = add_rn(xb[k], mul_rn(c, a[k])); });
+  const double *const in[2] = {xb, a};
+  return map_fields<2>(n, S(s), x, in, [=] __device__(const double (&v)[2]) { return add_rn(v[0], mul_rn(c, v[1])); });
 }
 extern "C" int f2d_ts_asselin(double *xs, double c, const double *x, const double *xb, size_t n, f2d_stream_t s) {
-  return elementwise(n, S(s), [=] __device__(size_t k) {
-    xs[k] = add_rn(xs[k], mul_rn(c, add_rn(add_rn(x[k], xb[k]), -mul_rn(2., xs[k]))));
+  const double *const in[3] = {xs, x, xb};
+  return map_fields<3>(n, S(s), xs, in, [=] __device__(const double (&v)[3]) {
+    return add_rn(v[0], mul_rn(c, add_rn(add_rn(v[1], v[2]), -mul_rn(2., v[0]))));
   });
 }
 extern "C" int f2d_ts_am3(double *x, const double *xs, const double *xb, size_t n, f2d_stream_t s) {
   const double w = 1. / 12.;
-  return elementwise(n, S(s), [=] __device__(size_t k) {
-    x[k] = mul_rn(w, add_rn(add_rn(mul_rn(5., x[k]), mul_rn(8., xs[k])), -xb[k]));
+  const double *const in[3] = {x, xs, xb};
+  return map_fields<3>(n, S(s), x, in, [=] __device__(const double (&v)[3]) {
+    return mul_rn(w, add_rn(add_rn(mul_rn(5., v[0]), mul_rn(8., v[1])), -v[2]));
   });
 }
 extern "C" int f2d_mul_field(double *y, const double *a, size_t n, f2d_stream_t s) {

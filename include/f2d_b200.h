@@ -87,7 +87,9 @@ int f2d_cornertocell(const double *xp, double *xr, int ny, int nx, f2d_stream_t 
 /* :2-39 computeorthogradient(msk,psi,dx,dy,nh,u,v) */
 int f2d_orthogradient(const int8_t *msk, const double *psi, double dx, double dy, int nh,
                       double *u, double *v, int ny, int nx, f2d_stream_t stream);
-/* psi = psi*mskp followed by computeorthogradient in one pass (operators.py:481,493) */
+/* psi = psi*mskp followed by computeorthogradient in one pass (operators.py:481,493).
+ * msk == mskp == NULL: all-fluid domain (cell mask 1 everywhere, corner mask 1 except on
+ * the last row and column, operators.py:59-67) -- no mask byte is read; needs even nx. */
 int f2d_mask_orthogradient(const int8_t *msk, const int8_t *mskp, double *psi, double dx,
                            double dy, int nh, double *u, double *v, int ny, int nx,
                            f2d_stream_t stream);
@@ -266,8 +268,9 @@ int f2d_mg_set_graphs(f2d_mg_t *mg, int enable);
  * work = celltocorner(w) [- rhsp]; full ? solve(psi, work, 4, 1e-11)[, psi -= mean if
  * perio] : twoVcycle(psi, work); psi *= mskp [+ psi_island]; (u,v) = orthogradient(psi).
  * w, psi, u, v, work: DEVICE fields; mskp int8 corner mask; rhsp / psi_island may be
- * NULL (island.py:21-43).  full != 0 synchronises (see f2d_mg_solve); nite/res HOST
- * outputs (may be NULL). `scratch` as for the reductions. */
+ * NULL (island.py:21-43); msk and mskp may both be NULL on an all-fluid domain without
+ * island (see f2d_mask_orthogradient).  full != 0 synchronises (see f2d_mg_solve);
+ * nite/res HOST outputs (may be NULL). `scratch` as for the reductions. */
 int f2d_invert_vorticity(f2d_mg_t *mg, const int8_t *msk, const int8_t *mskp,
                          const double *w, double *psi, double *u, double *v, double *work,
                          const double *rhsp, const double *psi_island, int full, int perio,

@@ -125,7 +125,37 @@ def test_advection_umax_zero_and_bad_nh(L):
         lib.adv_upwind(*args, 3, 1, 4, ny, nx, 0, g.stream())
 
 
-@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("shape", SHAPES + [(23, 37), (40, 518), (35, 600)])
+def test_mask_orthogradient(L, shape):
+    """psi *= mskp; computeorthogradient (operators.py:481,493) in one pass: masked form,
+    and the mask-free form (msk = mskp = NULL) of all-fluid domains"""
+    g = _gpu()
+    lib, strict = L
+    ny, nx = shape
+    rng = np.random.default_rng(11 + ny + nx)
+    fo = K.fortran_operators
+    s = g.stream()
+    for mkind in ("ones", "closed", "random"):
+        msk = rand_mask(rng, ny, nx, mkind)
+        mskp = np.zeros(shape, dtype=np.int8)
+        mskp[:-1, :-1] = msk[:-1, :-1] & msk[:-1, 1:] & msk[1:, :-1] & msk[1:, 1:]
+        psi = rng.standard_normal(shape)
+        u0, v0 = rng.standard_normal(shape), rng.standard_normal(shape)
+        pr = psi*mskp
+        ur, vr = u0.copy(), v0.copy()
+        fo.computeorthogradient(msk, pr, 0.01, 0.02, 3, ur, vr)
+        forms = [(g.ptr(g.keep(msk)), g.ptr(g.keep(mskp)))]
+        if mkind == "ones" and nx % 2 == 0:
+            forms.append((None, None))
+        for pm, pmp in forms:
+            dp, du, dv = g.dev(psi), g.dev(u0), g.dev(v0)
+            lib.mask_orthogradient(pm, pmp, g.ptr(dp), 0.01, 0.02, 3, g.ptr(du), g.ptr(dv), ny, nx, s)
+            np.testing.assert_array_equal(g.host(dp), pr)
+            g.check(g.host(du), ur, strict, what="u")
+            g.check(g.host(dv), vr, strict, what="v")
+
+
+@pytest.mark.parametrize("shape", SHAPES + [(23, 37), (35, 601)])
 def test_stencil_operators(L, shape):
     g = _gpu()
     lib, strict = L

@@ -51,6 +51,19 @@ def timeit(f, reps=10):
     return e0.elapsed_time(e1)/reps
 
 
+if os.environ.get("F2D_PROF_RANGE"):
+    # under `ncu --profile-from-start off`: capture exactly one pass of the chosen cycle
+    f = {"vcycle": lambda: L.mg_two_vcycle(h, ptr(x), ptr(b), s),
+         "fcycle": lambda: L.mg_fcycle(h, 0, s),
+         "smooth": lambda: L.mg_smooth(h, 0, ptr(x), ptr(b), 2, s)}[what]
+    f()
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()
+    f()
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+    L.mg_destroy(h)
+    sys.exit(0)
 if what in ("smooth", "all"):
     ms = timeit(lambda: L.mg_smooth(h, 0, ptr(x), ptr(b), 2, s))/2
     print("smooth2 level0: %.4f ms  -> %.0f GB/s at 24 B/cell" % (ms, 24.*n*n/ms/1e6))

@@ -49,49 +49,71 @@ def measured_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons during the timed region"""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled every few ms DURING the timed region, through
+    NVML (nvidia_ml_py; nvidia-smi's own loop is too coarse for a 0.2 s region)"""
+    NAMES = [("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+             ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+             ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+             ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap")]
 
     def __init__(self, index=0):
-        self.proc = None
-        self.lines = []
+        self.sm, self.reasons, self.err = [], set(), None
+        self.mx = None
+        self._stop = False
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
+            import pynvml as N
+            N.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    index = int(vis.split(",")[index])
+                except ValueError:
+                    pass
+            self.N = N
+            self.h = N.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM))
+            self.bits = []
+            for name, a, b in self.NAMES:
+                v = getattr(N, a, None)
+                if v is None:
+                    v = getattr(N, b, None)
+                if v is not None:
+                    self.bits.append((name, v))
+            self._sample()
+            self.sm = []
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
+        except Exception as ex:
+            self.err = repr(ex)
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _sample(self):
+        N = self.N
+        self.sm.append(float(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)))
+        try:
+            r = N.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = N.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in self.bits:
+            if r & bit:
+                self.reasons.add(name)
+
+    def _loop(self):
+        while not self._stop:
+            try:
+                self._sample()
+            except Exception as ex:
+                self.err = repr(ex)
+                return
+            time.sleep(0.004)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm)//2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.err and not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.mx, "samples": 0, "reasons": ["nvml unavailable: " + self.err]}
+        self._stop = True
+        self.t.join(timeout=1.)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm)//2] if sm else None, "sm_max_mhz": self.mx, "samples": len(sm),
+                "reasons": sorted(self.reasons)}
 
 
 def build_case(api, n, tracers, datadir, world=1):

@@ -152,6 +152,64 @@ __device__ __forceinline__ void fill_zero(double *x, int n) {
   __syncthreads();
 }
 
+// Coarsest level of an all-fluid doubly periodic hierarchy (constant-stencil class): every
+// halo cell is a periodic image, so the m x n interior values are the only unknowns, and the
+// value smoothtwicewithA computes on the ring around the interior is, bit for bit, the image
+// of an interior value (same expression, same operands).  The ndeepest double sweeps
+// (hierarchy.py:114-116, x = 0 first) therefore run in ONE warp on two m*n arrays with
+// periodic indexing and __syncwarp() -- no block barrier, no halo fill -- and the result is
+// expanded to the full array (interior + images) at the end.  u: scratch of >= 2*m*n doubles.
+constexpr int MAXU = 64;   // unknowns handled (two per lane)
+__device__ __forceinline__ bool coarsest_periodic_ok(const fused::LevelK &L) {
+  return (L.ny - 2 * NH) * (L.nx - 2 * NH) <= MAXU && L.ny * L.nx >= 2 * (L.ny - 2 * NH) * (L.nx - 2 * NH);
+}
+template <int NTHREADS>
+__device__ void coarsest_periodic(const fused::LevelK &L, double *x, const double *b, double *u, int ndeepest) {
+  const int ny = L.ny, nx = L.nx, m = ny - 2 * NH, n = nx - 2 * NH, U = m * n;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    fused::Coefs<false, false> kc;
+    kc.load(L, 0, nullptr, 0);
+    double *src = u, *dst = u + U;
+    int nb[2][8];
+    double bq[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int p = lane + 32 * q;
+      bq[q] = 0.;
+      if (p < U) {
+        const int pj = p / n, pi = p - pj * n;
+        const int jm = (pj + m - 1) % m, jp = (pj + 1) % m, im = (pi + n - 1) % n, ip = (pi + 1) % n;
+        nb[q][0] = jm * n + im; nb[q][1] = jm * n + pi; nb[q][2] = jm * n + ip;
+        nb[q][3] = pj * n + im;                         nb[q][4] = pj * n + ip;
+        nb[q][5] = jp * n + im; nb[q][6] = jp * n + pi; nb[q][7] = jp * n + ip;
+        bq[q] = b[(pj + NH) * nx + pi + NH];
+        src[p] = 0.;
+      }
+    }
+    __syncwarp();
+    for (int s = 0; s < 2 * ndeepest; s++) {
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const int p = lane + 32 * q;
+        if (p < U)
+          dst[p] = fused::jacobi_val<false, false>(L, kc, src[nb[q][0]], src[nb[q][1]], src[nb[q][2]], src[nb[q][3]],
+                                                   src[p], src[nb[q][4]], src[nb[q][5]], src[nb[q][6]], src[nb[q][7]],
+                                                   bq[q]);
+      }
+      __syncwarp();
+      double *tmp = src; src = dst; dst = tmp;
+    }
+    // 2*ndeepest sweeps: the result is back in u[0..U)
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < ny * nx; c += NTHREADS) {
+    const int j = c / nx, i = c - j * nx;
+    x[c] = u[((j - NH + 4 * m) % m) * n + (i - NH + 4 * n) % n];
+  }
+  __syncthreads();
+}
+
 // V-cycle of the tail levels [l1, nlev-1]; x of level l1 is whatever the shared array holds
 template <bool MASKED, bool STORED>
 __device__ void vcycle(const Params &P, double *X, double *B, double *T, int l1) {
@@ -167,8 +225,12 @@ __device__ void vcycle(const Params &P, double *X, double *B, double *T, int l1)
   {
     const fused::LevelK &L = P.lv[last];
     double *x = X + P.off[last], *b = B + P.off[last], *t = T + P.off[last];
-    fill_zero(x, L.ny * L.nx);
-    for (int k = 0; k < P.ndeepest; k++) smooth2<MASKED, STORED>(L, x, b, t, false);
+    if (!MASKED && !STORED && coarsest_periodic_ok(L)) {
+      coarsest_periodic<NT>(L, x, b, t, P.ndeepest);
+    } else {
+      fill_zero(x, L.ny * L.nx);
+      for (int k = 0; k < P.ndeepest; k++) smooth2<MASKED, STORED>(L, x, b, t, false);
+    }
   }
   for (int l = last - 1; l >= l1; l--) {
     const fused::LevelK &L = P.lv[l];
@@ -199,8 +261,12 @@ __global__ void __launch_bounds__(NT, 1) k_mg_tail(const __grid_constant__ Param
     {
       const fused::LevelK &L = P.lv[last];
       double *x = X + P.off[last];
-      fill_zero(x, L.ny * L.nx);
-      for (int k = 0; k < P.ndeepest; k++) smooth2<MASKED, STORED>(L, x, B + P.off[last], T + P.off[last], false);
+      if (!MASKED && !STORED && coarsest_periodic_ok(L)) {
+        coarsest_periodic<NT>(L, x, B + P.off[last], T + P.off[last], P.ndeepest);
+      } else {
+        fill_zero(x, L.ny * L.nx);
+        for (int k = 0; k < P.ndeepest; k++) smooth2<MASKED, STORED>(L, x, B + P.off[last], T + P.off[last], false);
+      }
     }
     for (int l = last - 1; l >= 0; l--) {
       interpolate<MASKED>(P.lv[l], P.lv[l + 1], X + P.off[l + 1], X + P.off[l], false);

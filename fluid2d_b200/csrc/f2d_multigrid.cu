@@ -15,6 +15,7 @@
 #include "f2d_tma.cuh"
 #include "f2d_mg_fused.cuh"
 #include "f2d_mg_tail.cuh"
+#include "f2d_mg_ctail.cuh"
 
 using namespace f2d;
 
@@ -49,6 +50,10 @@ struct f2d_mg {
   int tail0 = -1;             // first level of the shared-memory tail (-1: no tail kernel)
   bool tail_const = false;    // every tail level is in the constant-stencil class
   size_t tail_smem = 0;
+  bool ctail = false;         // the tail runs on a thread-block cluster (f2d_mg_ctail.cuh), from 128^2 down
+  ctail::Params ctp;          // its level table (pointers / program filled per launch)
+  long long *trace = nullptr; // f2d_mg_set_trace
+  int trace_cap = 0;
   struct G { cudaGraphExec_t exec; long long kernels; };
   std::map<std::tuple<int, int, const void *, const void *, const void *>, G> cache;
   // Gmg.solve as ONE graph: norms, a device-side WHILE node around (F-cycle, residual,
@@ -609,6 +614,31 @@ int coarsest_enqueue(f2d_mg *mg, double *X, const double *B, cudaStream_t s) {
 // 2 = F-cycle of the levels tail0..last; rhs b_in, result x_out (both of level tail0)
 int tail_launch(f2d_mg *mg, int program, const double *b_in, const double *x_in, double *x_out, cudaStream_t s,
                 double *acc = nullptr) {
+  if (mg->ctail) {
+    ctail::Params P = mg->ctp;
+    P.b_in = b_in;
+    P.x_in = x_in;
+    P.x_out = x_out;
+    P.acc = acc;
+    P.trace = mg->trace;
+    P.trace_cap = mg->trace_cap;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctail::NC);
+    cfg.blockDim = dim3(ctail::NT);
+    cfg.dynamicSmemBytes = mg->tail_smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = ctail::NC;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (mg->tail_const) F2D_CUDA(cudaLaunchKernelEx(&cfg, ctail::k_mg_ctail<false, false>, P, program));
+    else F2D_CUDA(cudaLaunchKernelEx(&cfg, ctail::k_mg_ctail<true, true>, P, program));
+    F2D_LAUNCHED();
+    return F2D_OK;
+  }
   tail::Params P;
   int n = (int)mg->L.size() - mg->tail0;
   P.nlev = n;
@@ -1070,6 +1100,53 @@ int finish_setup(f2d_mg *mg, double Rd, cudaStream_t s) {
                                (int)mg->tail_smem));
     }
   }
+  // cluster tail: the deepest levels whose interior is at most 128 wide, on 8 SMs
+  {
+    // Opt-in (F2D_MG_CTAIL=1): measured on B200 it is not yet faster than the one-CTA tail plus
+    // the per-level kernels of the 128^2 level (55 us against 49 us per V-cycle of a 128^2
+    // hierarchy) -- its per-point passes go through the row-address table.
+    const char *notail = getenv("F2D_MG_NO_TAIL"), *noct = getenv("F2D_MG_NO_CTAIL"), *ct = getenv("F2D_MG_CTAIL");
+    int t0 = (int)mg->L.size();
+    while (t0 > 0) {
+      Level &l = mg->L[t0 - 1];
+      if (l.ny - 2 * NH > ctail::MAXN || l.nx - 2 * NH > ctail::MAXN) break;
+      if ((int)mg->L.size() - (t0 - 1) > ctail::MAXL) break;
+      t0--;
+    }
+    const bool off = (notail && notail[0] == '1') || (noct && noct[0] == '1') || !(ct && ct[0] == '1');
+    if (!off && t0 < (int)mg->L.size() && mg->L[t0].n() > (size_t)ctail::REPL_CELLS) {
+      ctail::Params &P = mg->ctp;
+      P = ctail::Params{};
+      P.nlev = (int)mg->L.size() - t0;
+      int o = 0, rp = 0;
+      bool all_const = true;
+      for (int k = 0; k < P.nlev; k++) {
+        Level &l = mg->L[t0 + k];
+        P.lv[k] = level_k(mg, t0 + k);
+        P.dist[k] = l.n() > (size_t)ctail::REPL_CELLS ? 1 : 0;
+        P.rows[k] = (l.ny + ctail::NC - 1) / ctail::NC;
+        P.off[k] = o;
+        P.rp[k] = rp;
+        o += P.dist[k] ? P.rows[k] * l.nx : l.ny * l.nx;
+        if (P.dist[k]) rp += l.ny;
+        if (l.mode != 1) all_const = false;
+      }
+      P.total = o + (o & 1);
+      P.rptotal = rp;
+      P.ndeepest = mg->ndeepest;
+      size_t smem = 3 * (size_t)P.total * sizeof(double) + 3 * (size_t)rp * sizeof(double *);
+      if (smem <= 220 * 1024) {
+        mg->ctail = true;
+        mg->tail0 = t0;
+        mg->tail_smem = smem;
+        mg->tail_const = all_const;
+        MGC(cudaFuncSetAttribute(ctail::k_mg_ctail<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+        MGC(cudaFuncSetAttribute(ctail::k_mg_ctail<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+      }
+    }
+  }
   MGC(cudaStreamSynchronize(s));
   MGC(cudaGetLastError());
   return F2D_OK;
@@ -1323,6 +1400,17 @@ extern "C" int f2d_mg_solve(f2d_mg_t *mg, double *psi, const double *rhs, double
 }
 
 // operators.py:421-498
+extern "C" int f2d_mg_set_trace(f2d_mg_t *mg, long long *buf, int cap) {
+  if (!mg) return fail(F2D_ERR_ARG, "mg_set_trace: null handle");
+  mg->trace = cap > 1 ? buf : nullptr;
+  mg->trace_cap = cap;
+  for (auto &kv : mg->cache) cudaGraphExecDestroy(kv.second.exec);   // graphs captured the old pointer
+  mg->cache.clear();
+  for (auto &kv : mg->solve_cache) cudaGraphExecDestroy(kv.second.exec);
+  mg->solve_cache.clear();
+  return F2D_OK;
+}
+
 extern "C" int f2d_invert_vorticity(f2d_mg_t *mg, const int8_t *msk, const int8_t *mskp, const double *w,
                                     double *psi, double *u, double *v, double *work, const double *rhsp,
                                     const double *psi_island, int full, int perio, double area, double dx,

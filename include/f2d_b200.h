@@ -263,6 +263,9 @@ int f2d_mg_solve(f2d_mg_t *mg, double *psi, const double *rhs, double tol, int m
                  int *nite, double *res, f2d_stream_t stream);
 /* use CUDA graphs for the cycles (default 1) */
 int f2d_mg_set_graphs(f2d_mg_t *mg, int enable);
+/* diagnostics: the cluster tail kernel appends one SM clock stamp per barrier of its rank-0
+ * CTA to the DEVICE buffer buf (buf[0] = count, zero it first; cap entries); NULL turns it off */
+int f2d_mg_set_trace(f2d_mg_t *mg, long long *buf, int cap);
 
 /* ---- Operators.invert_vorticity (operators.py:421-498) as one call:
  * work = celltocorner(w) [- rhsp]; full ? solve(psi, work, 4, 1e-11)[, psi -= mean if

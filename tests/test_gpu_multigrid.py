@@ -40,7 +40,7 @@ def cell_mask(kind, ny, nx, rng):
 
 
 CASES = [("perio", 64, 64), ("closed", 64, 64), ("obstacle", 64, 128), ("xchannel", 32, 128),
-         ("perio", 16, 8), ("obstacle", 128, 128), ("perio", 256, 128)]
+         ("perio", 16, 8), ("obstacle", 128, 128), ("perio", 256, 128), ("closed", 256, 256)]
 
 
 @pytest.fixture(params=["strict", "product"])
@@ -49,11 +49,13 @@ def L(request):
     return _lib.lib(strict=request.param == "strict"), request.param == "strict"
 
 
-def make(lib, kind, ny, nx, Rd=0., force_stored=False, notail=False):
+def make(lib, kind, ny, nx, Rd=0., force_stored=False, notail=False, noctail=False):
     import os
     import gpu_util as g
     os.environ["F2D_MG_FORCE_STORED"] = "1" if force_stored else "0"
     os.environ["F2D_MG_NO_TAIL"] = "1" if notail else "0"
+    os.environ["F2D_MG_NO_CTAIL"] = "1" if noctail else "0"
+    os.environ["F2D_MG_CTAIL"] = "0" if noctail else "1"   # the cluster tail is opt-in
     rng = np.random.default_rng(ny + nx)
     msk = cell_mask(kind, ny, nx, rng)
     cm = corner_mask(msk)
@@ -156,14 +158,16 @@ def test_matrix_classes(L):
 
 
 @pytest.mark.parametrize("kind,ny,nx", CASES)
-@pytest.mark.parametrize("graphs,force_stored,notail",
-                         [(0, False, False), (1, False, False), (1, True, False), (1, False, True)])
-def test_cycles_and_solve(L, kind, ny, nx, graphs, force_stored, notail):
-    """graphs on/off; matrix class forced to 'stored'; with and without the shared-memory
-    tail kernel (levels <= 64^2 in one launch)"""
+@pytest.mark.parametrize("graphs,force_stored,notail,noctail",
+                         [(0, False, False, False), (1, False, False, False), (1, True, False, False),
+                          (1, False, True, False), (1, False, False, True), (1, True, False, True)])
+def test_cycles_and_solve(L, kind, ny, nx, graphs, force_stored, notail, noctail):
+    """graphs on/off; matrix class forced to 'stored'; coarse levels by the cluster tail
+    kernel (<= 128^2, 8 CTAs over distributed shared memory), by the one-CTA tail kernel
+    (<= 64^2), or by the per-level kernels"""
     import gpu_util as g
     lib, strict = L
-    ref, h, rng = make(lib, kind, ny, nx, force_stored=force_stored, notail=notail)
+    ref, h, rng = make(lib, kind, ny, nx, force_stored=force_stored, notail=notail, noctail=noctail)
     s = g.stream()
     lib.mg_set_graphs(h, graphs)
     tol_cycle = 1e-12

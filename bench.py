@@ -48,72 +48,81 @@ def measured_peaks():
     return 6650., "fallback (B200_PROFILING.md)"
 
 
+_SAMPLER_SRC = r"""
+import sys, time
+import pynvml as N
+N.nvmlInit()
+h = N.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+names = [("hw_slowdown", "HwSlowdown"), ("hw_thermal_slowdown", "HwThermalSlowdown"),
+         ("sw_thermal_slowdown", "SwThermalSlowdown"), ("sw_power_cap", "SwPowerCap")]
+bits = []
+for nm, suffix in names:
+    v = getattr(N, "nvmlClocksEventReason" + suffix, None)
+    if v is None:
+        v = getattr(N, "nvmlClocksThrottleReason" + suffix, None)
+    if v is not None:
+        bits.append((nm, v))
+print("max", N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM), flush=True)
+while True:
+    try:
+        r = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+    except Exception:
+        r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+    print("s", repr(time.time()), N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM),
+          ",".join(nm for nm, b in bits if r & b), flush=True)
+    time.sleep(0.005)
+"""
+
+
 class ClockSampler(object):
-    """SM clock and throttle reasons sampled every few ms DURING the timed region, through
-    NVML (nvidia_ml_py; nvidia-smi's own loop is too coarse for a 0.2 s region)"""
-    NAMES = [("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
-             ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
-             ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
-             ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap")]
+    """SM clock and throttle reasons sampled every 5 ms through NVML (nvidia_ml_py) by a CHILD
+    process, so that the sampling costs the benchmark's host thread nothing (a sampling thread
+    in this process was measured to cost 5 % at 4 GPUs through the GIL).  start() before the
+    warm-up; window(t0, t1) keeps the samples taken during the timed region."""
 
     def __init__(self, index=0):
-        self.sm, self.reasons, self.err = [], set(), None
-        self.mx = None
-        self._stop = False
-        try:
-            import pynvml as N
-            N.nvmlInit()
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            if vis:
-                try:
-                    index = int(vis.split(",")[index])
-                except ValueError:
-                    pass
-            self.N = N
-            self.h = N.nvmlDeviceGetHandleByIndex(index)
-            self.mx = float(N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM))
-            self.bits = []
-            for name, a, b in self.NAMES:
-                v = getattr(N, a, None)
-                if v is None:
-                    v = getattr(N, b, None)
-                if v is not None:
-                    self.bits.append((name, v))
-            self._sample()
-            self.sm = []
-            self.t = threading.Thread(target=self._loop, daemon=True)
-            self.t.start()
-        except Exception as ex:
-            self.err = repr(ex)
-
-    def _sample(self):
-        N = self.N
-        self.sm.append(float(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)))
-        try:
-            r = N.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-        except Exception:
-            r = N.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-        for name, bit in self.bits:
-            if r & bit:
-                self.reasons.add(name)
-
-    def _loop(self):
-        while not self._stop:
+        self.proc = None
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
             try:
-                self._sample()
-            except Exception as ex:
-                self.err = repr(ex)
-                return
-            time.sleep(0.004)
+                index = int(vis.split(",")[index])
+            except (ValueError, IndexError):
+                pass
+        try:
+            # the child writes to a file: nothing in this process wakes up while the bench runs
+            self.out = tempfile.NamedTemporaryFile("w+", suffix=".clocks")
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(index)], stdout=self.out,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
 
-    def stop(self):
-        if self.err and not self.sm:
-            return {"sm_mhz": None, "sm_max_mhz": self.mx, "samples": 0, "reasons": ["nvml unavailable: " + self.err]}
-        self._stop = True
-        self.t.join(timeout=1.)
-        sm = sorted(self.sm)
-        return {"sm_mhz": sm[len(sm)//2] if sm else None, "sm_max_mhz": self.mx, "samples": len(sm),
-                "reasons": sorted(self.reasons)}
+    def wait_ready(self, timeout=10.):
+        """block until the child has delivered its first sample (NVML start-up takes a while)"""
+        t_end = time.time()+timeout
+        while self.proc is not None and time.time() < t_end:
+            if os.path.getsize(self.out.name) > 40:
+                return
+            time.sleep(0.05)
+
+    def window(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml sampler unavailable"]}
+        time.sleep(0.02)
+        self.proc.terminate()
+        self.proc.wait()
+        self.out.seek(0)
+        sm, mx, reasons = [], None, set()
+        for ln in self.out.read().splitlines():
+            f = ln.split()
+            if f and f[0] == "max":
+                mx = float(f[1])
+            elif f and f[0] == "s" and t0 <= float(f[1]) <= t1:
+                sm.append(float(f[2]))
+                if len(f) > 3:
+                    reasons.update(x for x in f[3].split(",") if x)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm)//2] if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
 
 
 def build_case(api, n, tracers, datadir, world=1):
@@ -194,10 +203,15 @@ def gpu_main(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # native libraries (NCCL's version banner) write to file descriptor 1 directly: point it at
+    # stderr until the JSON line is due, so that stdout carries that one line only
+    sys.stdout.flush()
+    saved_fd1 = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if args.replicas:
         os.environ.pop("RANK", None)     # N independent single-GPU replicas (debug aid)
     import fluid2d_b200
@@ -207,6 +221,7 @@ def gpu_main(args):
     lib = r.lib
     real_stdout = sys.stdout
     sys.stdout = sys.stderr
+    sampler = ClockSampler(local) if rank == 0 else None     # child process, started well before the timed region
     n, T = args.n, args.tracers
     t0 = time.time()
     slabs = world > 1 and not args.replicas
@@ -223,21 +238,24 @@ def gpu_main(args):
 
     for _ in range(args.warmup):
         loop_body(f2d)
+    if sampler:
+        sampler.wait_ready()
     barrier()
     # ---- timed region: K steps, device timers, inputs (134 MB fields) exceed the 126 MB L2
-    sampler = ClockSampler(local) if rank == 0 else None
     lib.launch_count_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nites = []
+    wall0 = time.time()
     e0.record()
     for _ in range(args.steps):
         loop_body(f2d)
         nites.append(model.ope.last_solve[0])
     e1.record()
     barrier()
+    wall1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = int(lib.launch_count())
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.window(wall0, wall1) if sampler else None
     if world > 1:
         tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -309,7 +327,13 @@ def gpu_main(args):
            "h2d_bytes_per_step": (ds.h2d_bytes-h2d0)//ke, "d2h_bytes_per_step": (ds.d2h_bytes-d2h0)//ke,
            "ms_per_step": e2e_ms/ke, "steps": ke}
 
+    sys.stderr.flush()
+    os.dup2(saved_fd1, 1)
+    os.close(saved_fd1)
     sys.stdout = real_stdout
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     cpu = None

@@ -227,7 +227,7 @@ __device__ void coarsest(const Params &P, const Ctx &C) {
   const fused::LevelK &L = P.lv[last];
   if (!MASKED && !STORED && !P.dist[last] && tail::coarsest_periodic_ok(L)) {
     // one warp, periodic indexing on the m x n unknowns (see f2d_mg_tail.cuh)
-    tail::coarsest_periodic<NT>(L, C.A[AX] + P.off[last], C.A[AB] + P.off[last], C.A[AT] + P.off[last], P.ndeepest);
+    tail::coarsest_periodic(L, C.A[AX] + P.off[last], C.A[AB] + P.off[last], C.A[AT] + P.off[last], P.ndeepest);
     return;
   }
   fill_zero(P, C, last);

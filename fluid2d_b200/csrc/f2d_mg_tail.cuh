@@ -17,7 +17,7 @@
 namespace tail {
 
 constexpr int NH = 3;
-constexpr int NT = 1024;
+constexpr int NT = 1024;      // upper bound of the block size (the launch picks blockDim.x)
 constexpr int MAXL = 8;       // levels 64,32,16,8,4 at most in practice
 constexpr int MAXN = 64;      // largest interior size handled
 
@@ -42,7 +42,8 @@ struct Ctx {
 template <class F>
 __device__ __forceinline__ void for_cells(int ny, int nx, int jlo, int jhi, int ilo, int ihi, F f) {
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int j = jlo + warp; j <= jhi; j += NT / 32)
+  const int nw = blockDim.x >> 5;
+  for (int j = jlo + warp; j <= jhi; j += nw)
     for (int i = ilo + lane; i <= ihi; i += 32) f(j, i);
 }
 
@@ -148,7 +149,7 @@ __device__ void interpolate(const fused::LevelK &Lf, const fused::LevelK &Lc, co
 }
 
 __device__ __forceinline__ void fill_zero(double *x, int n) {
-  for (int p = threadIdx.x; p < n; p += NT) x[p] = 0.;
+  for (int p = threadIdx.x; p < n; p += blockDim.x) x[p] = 0.;
   __syncthreads();
 }
 
@@ -163,8 +164,7 @@ constexpr int MAXU = 64;   // unknowns handled (two per lane)
 __device__ __forceinline__ bool coarsest_periodic_ok(const fused::LevelK &L) {
   return (L.ny - 2 * NH) * (L.nx - 2 * NH) <= MAXU && L.ny * L.nx >= 2 * (L.ny - 2 * NH) * (L.nx - 2 * NH);
 }
-template <int NTHREADS>
-__device__ void coarsest_periodic(const fused::LevelK &L, double *x, const double *b, double *u, int ndeepest) {
+__device__ inline void coarsest_periodic(const fused::LevelK &L, double *x, const double *b, double *u, int ndeepest) {
   const int ny = L.ny, nx = L.nx, m = ny - 2 * NH, n = nx - 2 * NH, U = m * n;
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
@@ -203,7 +203,7 @@ __device__ void coarsest_periodic(const fused::LevelK &L, double *x, const doubl
     // 2*ndeepest sweeps: the result is back in u[0..U)
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < ny * nx; c += NTHREADS) {
+  for (int c = threadIdx.x; c < ny * nx; c += blockDim.x) {
     const int j = c / nx, i = c - j * nx;
     x[c] = u[((j - NH + 4 * m) % m) * n + (i - NH + 4 * n) % n];
   }
@@ -226,7 +226,7 @@ __device__ void vcycle(const Params &P, double *X, double *B, double *T, int l1)
     const fused::LevelK &L = P.lv[last];
     double *x = X + P.off[last], *b = B + P.off[last], *t = T + P.off[last];
     if (!MASKED && !STORED && coarsest_periodic_ok(L)) {
-      coarsest_periodic<NT>(L, x, b, t, P.ndeepest);
+      coarsest_periodic(L, x, b, t, P.ndeepest);
     } else {
       fill_zero(x, L.ny * L.nx);
       for (int k = 0; k < P.ndeepest; k++) smooth2<MASKED, STORED>(L, x, b, t, false);
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(NT, 1) k_mg_tail(const __grid_constant__ Param
   double *B = X + P.total;
   double *T = B + P.total;
   const int n0 = P.lv[0].ny * P.lv[0].nx;
-  for (int p = threadIdx.x; p < n0; p += NT) {
+  for (int p = threadIdx.x; p < n0; p += blockDim.x) {
     B[p] = P.b_in[p];
     X[p] = (program == 1) ? P.x_in[p] : 0.;
   }
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(NT, 1) k_mg_tail(const __grid_constant__ Param
       const fused::LevelK &L = P.lv[last];
       double *x = X + P.off[last];
       if (!MASKED && !STORED && coarsest_periodic_ok(L)) {
-        coarsest_periodic<NT>(L, x, B + P.off[last], T + P.off[last], P.ndeepest);
+        coarsest_periodic(L, x, B + P.off[last], T + P.off[last], P.ndeepest);
       } else {
         fill_zero(x, L.ny * L.nx);
         for (int k = 0; k < P.ndeepest; k++) smooth2<MASKED, STORED>(L, x, B + P.off[last], T + P.off[last], false);
@@ -276,9 +276,9 @@ __global__ void __launch_bounds__(NT, 1) k_mg_tail(const __grid_constant__ Param
     vcycle<MASKED, STORED>(P, X, B, T, 0);
   }
   if (P.acc)
-    for (int p = threadIdx.x; p < n0; p += NT) P.acc[p] = P.acc[p] + X[p];
+    for (int p = threadIdx.x; p < n0; p += blockDim.x) P.acc[p] = P.acc[p] + X[p];
   else
-    for (int p = threadIdx.x; p < n0; p += NT) P.x_out[p] = X[p];
+    for (int p = threadIdx.x; p < n0; p += blockDim.x) P.x_out[p] = X[p];
 }
 
 }  // namespace tail

@@ -50,6 +50,7 @@ struct f2d_mg {
   int tail0 = -1;             // first level of the shared-memory tail (-1: no tail kernel)
   bool tail_const = false;    // every tail level is in the constant-stencil class
   size_t tail_smem = 0;
+  int tail_nt = tail::NT;     // threads of the one-CTA tail kernel (F2D_TAIL_NT)
   bool ctail = false;         // the tail runs on a thread-block cluster (f2d_mg_ctail.cuh), from 128^2 down
   ctail::Params ctp;          // its level table (pointers / program filled per launch)
   long long *trace = nullptr; // f2d_mg_set_trace
@@ -655,9 +656,9 @@ int tail_launch(f2d_mg *mg, int program, const double *b_in, const double *x_in,
   P.x_out = x_out;
   P.acc = acc;
   if (mg->tail_const)
-    tail::k_mg_tail<false, false><<<1, tail::NT, mg->tail_smem, s>>>(P, program);
+    tail::k_mg_tail<false, false><<<1, mg->tail_nt, mg->tail_smem, s>>>(P, program);
   else
-    tail::k_mg_tail<true, true><<<1, tail::NT, mg->tail_smem, s>>>(P, program);
+    tail::k_mg_tail<true, true><<<1, mg->tail_nt, mg->tail_smem, s>>>(P, program);
   F2D_LAUNCHED();
   return F2D_OK;
 }
@@ -1090,6 +1091,10 @@ int finish_setup(f2d_mg *mg, double Rd, cudaStream_t s) {
     const char *notail = getenv("F2D_MG_NO_TAIL");
     if (t0 < (int)mg->L.size() && !(notail && notail[0] == '1')) {
       mg->tail0 = t0;
+      if (const char *nt = getenv("F2D_TAIL_NT")) {
+        int v = atoi(nt);
+        if (v >= 32 && v <= tail::NT && v % 32 == 0) mg->tail_nt = v;
+      }
       mg->tail_smem = 3 * cells * sizeof(double);
       mg->tail_const = true;
       for (size_t lev = t0; lev < mg->L.size(); lev++)

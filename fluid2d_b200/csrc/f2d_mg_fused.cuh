@@ -20,6 +20,7 @@
 // Arithmetic: each value is computed by the same expression, in the same order, as the
 // Fortran; only the traversal is different.
 #pragma once
+#include <cstddef>
 
 namespace fused {
 
@@ -115,12 +116,20 @@ constexpr int XP = XW + 2, CP = CW + 2;
 struct Smooth2Smem {
   alignas(128) double xs[XH][XP];   // TMA destinations: 128-byte aligned, dense boxes
   alignas(128) double bs[YH][YW];
-  alignas(128) double cs[CH][CP];
-  double y1[YH][YW];
+  // the coarse tile is dead once the interpolation pass has folded it into xs (a block
+  // barrier later sweep 1 starts writing y1): the two share their storage
+  union {
+    alignas(128) double y1[YH][YW];
+    double cs[CH][CP];
+  };
+  alignas(8) uint64_t bar;          // mbarrier of the TMA loads
+  // mask tiles last: the mask-free instantiations are launched with SMOOTH2_SMEM_NOMASK
+  // bytes only (56 KB -> 4 CTAs per SM instead of 3)
   int8_t ms[XH][XW];
   int8_t cm[CH][CW];
-  alignas(8) uint64_t bar;          // mbarrier of the TMA loads
 };
+static_assert(sizeof(double[CH][CP]) <= sizeof(double[YH][YW]), "coarse tile must fit in the y1 tile");
+constexpr size_t SMOOTH2_SMEM_NOMASK = offsetof(Smooth2Smem, ms);
 static_assert(XP % 2 == 0 && YW % 2 == 0 && CP % 2 == 0, "TMA boxes need an even number of doubles per row");
 
 // ---- asynchronous tile loader -----------------------------------------------------

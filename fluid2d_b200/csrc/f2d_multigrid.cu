@@ -419,7 +419,7 @@ int launch_smooth2(f2d_mg *mg, Level &l, Level *cl, const double *xin, const dou
                    const double *xc, cudaStream_t s, double *acc) {
   fused::LevelK k = level_k(mg, l);
   dim3 grid(cdiv(l.nx - 2 * NH, fused::TX), cdiv(l.ny - 2 * NH, fused::TY));
-  size_t sm = sizeof(fused::Smooth2Smem);
+  const size_t sm = l.mode == 1 ? fused::SMOOTH2_SMEM_NOMASK : sizeof(fused::Smooth2Smem);
   const int8_t *mskc = nullptr;
   int nxc = 0, nyc = 0;
   if (INPUT >= 2) {

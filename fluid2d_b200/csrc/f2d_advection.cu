@@ -11,6 +11,7 @@
 //
 // The running mask sums of the Fortran (mx5/mx3, my5/my3; :62-70,96-97,132-133) are
 // window sums here -- the same integers.
+#include <cstddef>
 #include "f2d_common.cuh"
 
 using namespace f2d;
@@ -118,8 +119,10 @@ struct AdvSmem {
   int8_t m[SH][SW];       // mask tile (MASKED only)
 };
 
+// mask-free instantiations: launched without the mask tile (54.8 KB) and compiled for 4 CTAs
+// per SM (<= 64 registers)
 template <bool UPW, int ORDER, bool MASKED>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, MASKED ? 3 : 4)
 k_adv(const int8_t *__restrict__ msk, const double *__restrict__ q, double *__restrict__ dq,
       const double *__restrict__ u, const double *__restrict__ v, double *__restrict__ xflx,
       double *__restrict__ yflx, AdvC k, int ny, int nx, int fill) {
@@ -222,7 +225,8 @@ int launch_adv_m(const int8_t *msk, const double *q, double *dq, const double *u
     attr_set = true;
   }
   dim3 grid(cdiv(nx - 2 * NH, TX), cdiv(ny - 2 * NH, TY));
-  k_adv<UPW, ORDER, MASKED><<<grid, NT, sizeof(AdvSmem), s>>>(msk, q, dq, u, v, xflx, yflx, k, ny, nx, fill);
+  const size_t sm = MASKED ? sizeof(AdvSmem) : offsetof(AdvSmem, m);
+  k_adv<UPW, ORDER, MASKED><<<grid, NT, sm, s>>>(msk, q, dq, u, v, xflx, yflx, k, ny, nx, fill);
   F2D_LAUNCHED();
   return F2D_OK;
 }

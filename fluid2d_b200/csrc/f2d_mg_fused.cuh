@@ -414,11 +414,13 @@ __device__ __noinline__ double resid_global(const LevelK &L, const double *__res
 constexpr int RXP = RXW + 1, RBP = RW + 1;         // row pitches of the x / b tiles (even: TMA boxes)
 struct ResidSmem {
   alignas(128) double xs[RXH][RXP];
+  // b tile, overwritten IN PLACE by the residual: the thread that computes r(j,i) is the only
+  // reader of b(j,i), so r(r,q) takes the place of b at bs[r][q + 1] (row pitch RBP)
   alignas(128) double bs[RH][RBP];
-  double rs[RH][RW];
-  int8_t ms[RXH][RXW];
   alignas(8) uint64_t bar;
+  int8_t ms[RXH][RXW];     // last: not allocated for the mask-free instantiations
 };
+constexpr size_t RESID_SMEM_NOMASK = offsetof(ResidSmem, ms);
 
 // column strip of the residual tile (same register-window scheme as jacobi_strip)
 template <bool MASKED, bool STORED, bool GUARD, int NR>
@@ -448,7 +450,7 @@ __device__ __forceinline__ void resid_strip(const LevelK &L, const Coefs<MASKED,
         double cdiag = STORED ? L.A[4 * (size_t)ny * nx + g + (size_t)k * nx] : L.c[4];
         val = resid_val<MASKED, STORED>(L, kk, cdiag, a0, a1, a2, m0, m1, m2, h0, h1, h2, bp[k * RBP]);
       }
-      rp[k * RW] = val;
+      rp[k * RBP] = val;
       a0 = m0; a1 = m1; a2 = m2;
       m0 = h0; m1 = h1; m2 = h2;
     }
@@ -456,7 +458,7 @@ __device__ __forceinline__ void resid_strip(const LevelK &L, const Coefs<MASKED,
 }
 
 template <bool MASKED, bool STORED, bool PEER>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, MASKED ? 4 : 5)
 k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ bc,
                  const int8_t *__restrict__ mskc, int nyc, int nxc, f2d::Peer P, int use_tma,
                  const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmb) {
@@ -507,13 +509,13 @@ k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restric
     const int r0 = tg * 8 + (tg < 1 ? 0 : 1), nr = tg < 1 ? 9 : 8;
     if (inner)
       resid_strip<MASKED, STORED, false, 9>(L, kc, &S.xs[r0 + 1][tx + 1], &S.bs[r0][tx + 1], &S.ms[r0 + 1][tx + 1],
-                                            &S.rs[r0][tx], nr, fj0 + r0, fi0 + tx, x, b);
+                                            &S.bs[r0][tx + 1], nr, fj0 + r0, fi0 + tx, x, b);
     else
       resid_strip<MASKED, STORED, true, 9>(L, kc, &S.xs[r0 + 1][tx + 1], &S.bs[r0][tx + 1], &S.ms[r0 + 1][tx + 1],
-                                           &S.rs[r0][tx], nr, fj0 + r0, fi0 + tx, x, b);
+                                           &S.bs[r0][tx + 1], nr, fj0 + r0, fi0 + tx, x, b);
     if (t < RH) {
       const int r = t, q = RW - 1;
-      resid_strip<MASKED, STORED, true, 1>(L, kc, &S.xs[r + 1][q + 1], &S.bs[r][q + 1], &S.ms[r + 1][q + 1], &S.rs[r][q], 1,
+      resid_strip<MASKED, STORED, true, 1>(L, kc, &S.xs[r + 1][q + 1], &S.bs[r][q + 1], &S.ms[r + 1][q + 1], &S.bs[r][q + 1], 1,
                                            fj0 + r, fi0 + q, x, b);
     }
   }
@@ -528,9 +530,9 @@ k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restric
     size_t g = (size_t)j * nxc + i;
     double val = 0.;
     if (!MASKED || mskc[g] != 0) {
-      const double *c = &S.rs[2 * r + 1][2 * q + 1];  // centre in the residual tile
-      val = 0.25 * c[0] + 0.125 * (((c[-1] + c[1]) + c[-RW]) + c[RW]) +
-            0.0625 * (((c[-RW - 1] + c[-RW + 1]) + c[RW - 1]) + c[RW + 1]);
+      const double *c = &S.bs[2 * r + 1][2 * q + 2];  // centre in the residual tile (column offset 1)
+      val = 0.25 * c[0] + 0.125 * (((c[-1] + c[1]) + c[-RBP]) + c[RBP]) +
+            0.0625 * (((c[-RBP - 1] + c[-RBP + 1]) + c[RBP - 1]) + c[RBP + 1]);
     }
     bc[g] = val;
     if (rim)

@@ -559,7 +559,7 @@ int op_resid_restrict_L(f2d_mg *mg, Level &l, Level &c, const double *x, const d
                         cudaStream_t s) {
   fused::LevelK k = level_k(mg, l);
   dim3 grid(cdiv(c.nx - 2 * NH, fused::RTX), cdiv(c.ny - 2 * NH, fused::RTY));
-  size_t sm = sizeof(fused::ResidSmem);
+  const size_t sm = l.mode == 1 ? fused::RESID_SMEM_NOMASK : sizeof(fused::ResidSmem);
   const bool peer = mg->comm != nullptr && l.ywrap == 0;
   f2d::Peer P = comm_peer(peer ? mg->comm : nullptr);
   if (peer && !comm_owns(mg->comm, bc))

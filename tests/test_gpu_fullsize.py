@@ -223,3 +223,52 @@ def test_two_vcycle_shift_equivariance(L, ny, nx):
         assert res.value < 1e-4
     finally:
         lib.mg_destroy(h)
+
+
+@pytest.mark.parametrize("ny,nx,kind", [(1024, 4096, "obstacle"), (1024, 2048, "xchannel")])
+def test_masked_hierarchy_classes_agree_at_full_size(L, ny, nx, kind):
+    """VonKarman- / RayleighBenard-sized domains with walls: the kernels that rebuild the
+    coefficients from the 1-byte masks (class 2) and from constant stencils must give, bit for
+    bit, the fields of the kernels that read the stored Galerkin matrices (class 0, the
+    reference's own data layout) -- through twoVcycle and a full solve on the whole hierarchy."""
+    import os
+    import torch
+    import gpu_util as g
+    lib, strict = L
+    msk = np.ones((ny+2*NH, nx+2*NH), dtype=np.int8)
+    msk[:NH, :] = 0
+    msk[-NH:, :] = 0
+    if kind == "obstacle":
+        yy, xx = np.mgrid[0:ny+2*NH, 0:nx+2*NH]
+        msk[(yy-0.5*ny)**2+(xx-0.5*ny)**2 < (0.08*ny)**2] = 0
+    cm = np.zeros(msk.shape)
+    K.fortran_operators.celltocorner(msk*1., cm)
+    cm[cm < 1.] = 0.
+    s = g.stream()
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    dmask = g.keep(cm)
+    rhs = torch.randn(msk.shape, dtype=torch.float64, device="cuda", generator=gen)*dmask
+    out = {}
+    for stored in ("0", "1"):
+        os.environ["F2D_MG_FORCE_STORED"] = stored
+        h = ctypes.c_void_p()
+        lib.mg_create(ctypes.byref(h), g.ptr(dmask), ny+2*NH, nx+2*NH, 1./ny, 1./ny, 8./9., 1., 0., s)
+        try:
+            modes = [lib.mg_level_matrix_mode(h, lev) for lev in range(lib.mg_nlevels(h))]
+            assert (set(modes) == {0}) == (stored == "1")
+            assert stored == "1" or modes[0] == 2
+            psi = torch.zeros_like(rhs)
+            lib.mg_two_vcycle(h, g.ptr(psi), g.ptr(rhs), s)
+            v = psi.clone()
+            nite, res = ctypes.c_int(), ctypes.c_double()
+            lib.mg_solve(h, g.ptr(psi), g.ptr(rhs), 1e-11, 4, ctypes.byref(nite), ctypes.byref(res), s)
+            torch.cuda.synchronize()
+            out[stored] = (v, psi.clone(), nite.value, res.value)
+        finally:
+            lib.mg_destroy(h)
+    os.environ["F2D_MG_FORCE_STORED"] = "0"
+    assert torch.equal(out["0"][0], out["1"][0]), "twoVcycle differs between coefficient classes"
+    assert torch.equal(out["0"][1], out["1"][1]), "solve differs between coefficient classes"
+    assert out["0"][2] == out["1"][2]
+    assert out["0"][3] < 1e-3 and abs(out["0"][3]-out["1"][3]) <= 1e-9*out["1"][3]
+    assert float(out["0"][1].abs().max()) > 0.

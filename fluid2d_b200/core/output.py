@@ -67,12 +67,22 @@ class Output(object):
             nh = self.nh
             self.his_t.append(t)
             for v in self.var_to_save:
-                field = var.get(v)     # D2H of that field only
-                self.his[v].append(np.array(field[nh:-nh, nh:-nh], dtype=np.float32))
+                self.his[v].append(self._snapshot(var.dstate, var.index(v)))
             if self.flxlist:
-                stack = data['flx'].flx     # D2H of the flux stack (output.py:94-95)
+                fstate = data['flx']._flx     # the flux stack (output.py:94-95)
                 for k, v in enumerate(self.flxlist):
-                    self.flx[v].append(np.array(stack[k][nh:-nh, nh:-nh], dtype=np.float32))
+                    self.flx[v].append(self._snapshot(fstate, k))
+
+    def _snapshot(self, dstate, k):
+        """interior of field k of a DeviceState as float32: cast and packed on the device
+        (f2d_pack_interior_f32), one D2H copy of half the fp64 bytes"""
+        import torch
+        from runtime import rt
+        r = rt()
+        nh, ny, nx = self.nh, dstate.ny, dstate.nx
+        dev = torch.empty((ny-2*nh, nx-2*nh), dtype=torch.float32, device=r.device)
+        r.lib.pack_interior_f32(dstate.rptr(k), r.ptr(dev), nh, ny, nx, r.stream)
+        return dev.cpu().numpy()
 
     def dump_diag(self):
         self._write_diag()

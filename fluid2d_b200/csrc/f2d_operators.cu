@@ -600,6 +600,25 @@ extern "C" int f2d_flx_split(double *rev, double *irr, const double *fwd, const 
     irr[k] = mul_rn(cff, add_rn(fwd[k], -sb));
   });
 }
+// history snapshot (output.py:90-95, NcfileIO.write): the interior of a field, cast to
+// float32 on the device, packed [ny-2nh][nx-2nh] -- half the bytes cross PCIe
+__global__ void k_pack_interior_f32(const double *__restrict__ x, float *__restrict__ out, int nh, int ny, int nx) {
+  const int mi = nx - 2 * nh, mj = ny - 2 * nh;
+  const size_t n = (size_t)mi * mj;
+  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(p / mi), i = (int)(p - (size_t)j * mi);
+    out[p] = (float)x[(size_t)(j + nh) * nx + i + nh];
+  }
+}
+extern "C" int f2d_pack_interior_f32(const double *x, float *out, int nh, int ny, int nx, f2d_stream_t s) {
+  if (!x || !out || nh < 0 || ny <= 2 * nh || nx <= 2 * nh) return fail(F2D_ERR_ARG, "pack_interior_f32: bad args");
+  const size_t n = (size_t)(ny - 2 * nh) * (nx - 2 * nh);
+  long long blocks = (long long)((n + 255) / 256);
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  k_pack_interior_f32<<<(int)blocks, 256, 0, S(s)>>>(x, out, nh, ny, nx);
+  F2D_LAUNCHED();
+  return F2D_OK;
+}
 extern "C" int f2d_div_scalar(double *y, double d, size_t n, f2d_stream_t s) {
   return elementwise(n, S(s), [=] __device__(size_t k) { y[k] = __ddiv_rn(y[k], d); });
 }

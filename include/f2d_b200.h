@@ -215,6 +215,11 @@ int f2d_flx_cellvel(const double *u, const double *v, double *uc, double *vc, in
 int f2d_flx_split(double *rev, double *irr, const double *fwd, const double *bwd, double cff,
                   double sign, size_t n, f2d_stream_t stream);
 
+/* ---- core/output.py:90-95 (history files are float32): interior of a field cast to
+ * float32 and packed [ny-2nh][nx-2nh] on the device, ready for one D2H copy */
+int f2d_pack_interior_f32(const double *x, float *out, int nh, int ny, int nx,
+                          f2d_stream_t stream);
+
 /* ---- core/gmg: hierarchy.Gmg (hierarchy.py:21-218) + level.Grid (level.py:120-496)
  * + the kernels of gmg/fortran_multigrid.f90.
  * f2d_mg_create builds the whole hierarchy on the device: Gridinfo (level.py:24-117,

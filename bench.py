@@ -359,8 +359,9 @@ def gpu_main(args):
         "roofline": {"bound": "hbm", "kernel": "k_smooth2<0,0,0> (Grid.smooth = double Jacobi sweep + halo fill, level 0)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 4096^2, from
-                     # profiles/r01_ncu_full_smooth2_level0_v2.csv (269 MB + 107 MB; algorithmic 420 MB)
-                     "traffic": 3.76e8 if n == 4096 else None,
+                     # profiles/r01_ncu_full_v10_two_vcycle_kernels.csv (269.1 MB + 104.2 MB; algorithmic
+                     # 420 MB: the mask-free level reads x and b, writes x; halo re-reads hit L2)
+                     "traffic": 3.733e8 if n == 4096 else None,
                      "peak_source": peak_src, "ms_per_launch": smooth_ms,
                      "algorithmic_bytes_per_cell": SMOOTH_BYTES_PER_CELL},
         "step_hbm": {"b_alg_bytes_per_cell": balg, "achieved_gbs": balg*value/world/1e9,

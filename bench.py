@@ -152,8 +152,16 @@ def loop_body(f2d):
 # ---------------------------------------------------------------------------
 def cpu_arm(n, tracers, steps, warmup):
     import types
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host
+    # thread (the OpenMP runtime reads the variable when the oracle library is loaded, below)
+    under_torchrun = os.environ.get("OMP_NUM_THREADS") == "1" and (
+        "TORCHELASTIC_RUN_ID" in os.environ or "RANK" in os.environ)
+    if under_torchrun:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from oracle import model as om, kernels as K
     K.lib().f2d_oracle_set_reduce_mode(1)     # row-partial reductions (parallel)
+    if under_torchrun:
+        K.lib().f2d_oracle_set_num_threads(os.cpu_count() or 1)
     cores = K.lib().f2d_oracle_num_threads()
 
     class F(om.Fluid2d):

@@ -205,11 +205,10 @@ def rb(api, datadir, nx=64, diag_fluxes=False):
     return f2d
 
 
-def karman(api, datadir, ny=32):
+def karman(api, datadir, ny=32, ratio=2):
     param = api.Param('default.xml')
     param.modelname = 'euler'
     _common(param, 'karman_%i' % ny, datadir)
-    ratio = 2
     param.ny = ny
     param.nx = param.ny*ratio
     param.Ly = 1.

@@ -24,10 +24,15 @@ world = int(os.environ.get("WORLD_SIZE", "1"))
 api = fluid2d_b200.api()
 so = sys.stdout
 sys.stdout = sys.stderr
-try:
+case = os.environ.get("F2D_PROF_CASE", "freedecay")   # rb: RayleighBenard n x n/2; karman: VonKarman 4n x n
+if case == "rb":
+    import cases
+    f2d = cases.rb(api, tempfile.mkdtemp(), n)
+elif case == "karman":
+    import cases
+    f2d = cases.karman(api, tempfile.mkdtemp(), n, ratio=4)
+else:
     f2d = bench.build_case(api, n, 1, tempfile.mkdtemp(), world)
-except TypeError:
-    f2d = bench.build_case(api, n, 1, tempfile.mkdtemp())
 f2d.model.diagnostics(f2d.model.var, 0.)
 for _ in range(4):
     bench.loop_body(f2d)

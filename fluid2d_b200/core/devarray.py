@@ -50,7 +50,52 @@ class TrackedArray(np.ndarray):
         np.ndarray.__setitem__(self, key, value)
         self._after_write()
 
+    def _device_inplace(self, ufunc, method, inputs, out, kwargs):
+        """`view += a`, `view -= a`, `view *= a` on a WHOLE field whose device copy is current
+        (the idiom of user forcing hooks, e.g. `dxdt[4] += self.forc; dxdt[4] *= coef`): done
+        by one kernel on the device instead of pulling the field to the host, doing the
+        arithmetic there and pushing it back.  Same IEEE result as numpy (one rounding per
+        element).  Returns False when the pattern does not apply."""
+        if method != '__call__' or kwargs or out is None or len(out) != 1 or out[0] is not self:
+            return False
+        if ufunc not in (np.add, np.subtract, np.multiply) or len(inputs) != 2 or inputs[0] is not self:
+            return False
+        own = self._own
+        if own is None or own[1] is None:
+            return False
+        st, k = own
+        if self.shape != (st.ny, st.nx) or not st.dev_fresh[k] or st.device.type != 'cuda':
+            return False
+        if not self.flags['C_CONTIGUOUS'] or self.ctypes.data != st._host[k].ctypes.data:
+            return False      # a reversed / strided view of the field: host path
+        other = inputs[1]
+        from runtime import rt
+        r = rt()
+        n = st.ny*st.nx
+        if isinstance(other, (int, float, np.floating, np.integer)):
+            c = float(other)
+            if ufunc is np.multiply:
+                r.lib.scale(st.wptr(k), c, n, r.stream)
+            else:
+                return False
+            return True
+        if isinstance(other, TrackedArray) or not isinstance(other, np.ndarray):
+            return False
+        if other.shape != self.shape or other.dtype != np.float64:
+            return False
+        d = torch.from_numpy(np.ascontiguousarray(other)).to(st.device)
+        if ufunc is np.add:
+            r.lib.add_scaled(st.wptr(k), 1., r.ptr(d), n, r.stream)
+        elif ufunc is np.subtract:
+            r.lib.add_scaled(st.wptr(k), -1., r.ptr(d), n, r.stream)
+        else:
+            r.lib.mul_field(st.wptr(k), r.ptr(d), n, r.stream)
+        torch.cuda.current_stream().synchronize()   # `d` may be freed once we return
+        return True
+
     def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kwargs):
+        if self._device_inplace(ufunc, method, inputs, out, kwargs):
+            return self
         plain = []
         for x in inputs:
             if isinstance(x, TrackedArray):

@@ -68,3 +68,40 @@ def test_pack_interior_f32_matches_numpy():
         out = torch.zeros((ny-6, nx-6), dtype=torch.float32, device="cuda")
         lib.pack_interior_f32(g.ptr(g.keep(x)), ctypes.c_void_p(out.data_ptr()), 3, ny, nx, g.stream())
         np.testing.assert_array_equal(g.host(out), x[3:-3, 3:-3].astype(np.float32))
+
+
+def test_inplace_ops_on_field_views_run_on_the_device_and_match_numpy():
+    """the forcing-hook idiom `dxdt[k] += f; dxdt[k] *= c` (boussinesq.py:110, user scripts)"""
+    import torch
+    from fluid2d_b200 import activate
+    activate()
+    from devarray import DeviceState
+    rng = np.random.default_rng(1)
+    ny, nx = 38, 70
+    st = DeviceState(3, ny, nx)
+    a0 = rng.standard_normal((3, ny, nx))
+    st.upload_all_from(a0)
+    f = rng.standard_normal((ny, nx))
+    ref = a0.copy()
+    v = st[1]                 # host view; the device copy is current
+    d2h = st.d2h_bytes
+    v += f
+    v *= 0.37
+    v -= 2.*f
+    v *= f
+    ref[1] += f
+    ref[1] *= 0.37
+    ref[1] -= 2.*f
+    ref[1] *= f
+    assert st.d2h_bytes == d2h, "the field must not have crossed PCIe"
+    assert not st.host_fresh[1]
+    np.testing.assert_array_equal(st.numpy(), ref)
+    # patterns that do not qualify take the host path and still give numpy's answer
+    w = st[2]
+    w[3:-3, :] += 1.5
+    ref[2][3:-3, :] += 1.5
+    r = st[0][::-1]
+    r += f
+    ref[0][::-1] += f
+    np.testing.assert_array_equal(st.numpy(), ref)
+    torch.cuda.synchronize()

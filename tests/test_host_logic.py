@@ -139,3 +139,30 @@ def test_gridinfo_levels():
     assert len(level_sizes(128, 128)) == 6
     assert level_sizes(2048, 1024)[-1] == (4, 8)
     assert level_sizes(4096, 1024)[-1] == (4, 16)
+
+
+def test_inplace_ops_on_field_views_host_path():
+    """TrackedArray in-place arithmetic (the forcing-hook idiom) on a CPU DeviceState takes the
+    host path and must equal numpy; the device fast path is covered by the GPU tests"""
+    import numpy as np
+    import torch
+    import fluid2d_b200
+    fluid2d_b200.activate()
+    from devarray import DeviceState
+    rng = np.random.default_rng(4)
+    st = DeviceState(2, 12, 14, device=torch.device("cpu"))
+    a0 = rng.standard_normal((2, 12, 14))
+    st.upload_all_from(a0)
+    f = rng.standard_normal((12, 14))
+    ref = a0.copy()
+    v = st[1]
+    v += f
+    v *= 0.25
+    v -= f
+    ref[1] += f
+    ref[1] *= 0.25
+    ref[1] -= f
+    w = st[0]
+    w[2:5, :] *= 3.
+    ref[0][2:5, :] *= 3.
+    np.testing.assert_array_equal(st.numpy(), ref)

@@ -243,3 +243,92 @@ def test_diagnostics_on_uniform_fields():
     msk[5, 5] = 0
     z, z2 = fd.computesumandnorm(msk, w, NH)
     assert z == 2.*(ncell-1)
+
+
+def test_diffusion_is_the_masked_five_point_laplacian():
+    """fortran_operators.f90:125-156: dtrac += K/dx^2 * sum of (neighbour - centre) over FLUID
+    neighbours (homogeneous Neumann at walls), fluid cells of rows/cols 2..m-1 only"""
+    ny, nx, dx, K0 = 18, 22, 0.25, 0.3
+    xx, yy = grid(ny, nx, dx)
+    t = xx**2+2.*yy**2                          # Laplacian = 2 + 4 = 6 exactly for the 5-point formula
+    msk = np.ones((ny, nx), dtype=np.int8)
+    d = np.full((ny, nx), 0.5)
+    fo.add_diffusion(msk, t, dx, NH, K0, d)
+    np.testing.assert_allclose(d[1:-1, 1:-1], 0.5+6.*K0, rtol=1e-12)
+    assert (d[0] == 0.5).all() and (d[:, 0] == 0.5).all() and (d[-1] == 0.5).all() and (d[:, -1] == 0.5).all()
+    # a wall on the east side removes that neighbour's contribution (no flux through the wall)
+    msk[:, 12] = 0
+    d[:] = 0.
+    fo.add_diffusion(msk, t, dx, NH, K0, d)
+    j, i = 8, 11
+    east = t[j, i+1]-t[j, i]
+    np.testing.assert_allclose(d[j, i], K0/dx**2*(6.*dx**2-east), rtol=1e-12)
+    assert not d[:, 12].any()                   # solid cells get no tendency
+
+
+def test_torque_is_the_centred_x_derivative_of_buoyancy():
+    """fortran_operators.f90:330-381: domega += g/(2dx)*(b(i+1)-b(i-1)) on interior cells whose
+    two x-neighbour pairs are all fluid"""
+    ny, nx, dx, g = 14, 20, 0.2, 9.81
+    xx, yy = grid(ny, nx, dx)
+    b = 3.*xx-yy+0.5*xx*yy                      # db/dx = 3 + 0.5 y
+    msk = np.ones((ny, nx), dtype=np.int8)
+    dw = np.zeros((ny, nx))
+    fo.add_torque(msk, b, dx, NH, g, dw)
+    np.testing.assert_allclose(dw[NH:-NH, NH:-NH], (g*(3.+0.5*yy))[NH:-NH, NH:-NH], rtol=1e-12)
+    assert not dw[:NH].any() and not dw[:, :NH].any()
+    msk[:, 9] = 0
+    dw[:] = 0.
+    fo.add_torque(msk, b, dx, NH, g, dw)
+    assert not dw[NH:-NH, 8:11].any()           # the wall column and both cells next to it
+    np.testing.assert_allclose(dw[NH:-NH, 11], (g*(3.+0.5*yy))[NH:-NH, 11], rtol=1e-12)
+
+
+def test_noslip_source_is_the_tangential_velocity_along_walls():
+    """fortran_operators.f90:221-277: psi at corners; at a wall face the cell-averaged
+    tangential velocity / (grid step) enters the FLUID cell next to the wall, with the sign
+    of the vorticity that would cancel it"""
+    ny, nx, dx, dy = 16, 18, 0.1, 0.1
+    x = (np.arange(nx)-NH+1.)*dx                # corner coordinates
+    y = (np.arange(ny)-NH+1.)*dy
+    xx, yy = np.meshgrid(x, y)
+    msk = np.ones((ny, nx), dtype=np.int8)
+    msk[:NH, :] = 0                             # a wall below row NH (south wall)
+    # uniform flow u = U along x: psi = -U*y  (u = -dpsi/dy)
+    U = 0.7
+    psi = -U*yy
+    src = np.full((ny, nx), np.nan)
+    fo.computenoslipsourceterm(msk, psi, src, dx, dy, NH)
+    # first fluid row j = NH: the south face is a wall; u along it gives a vortex sheet of
+    # strength u/dy, spread on the cell:  y(j,i) += u with u = -(psi(j,i)+psi(j,i-1)-psi(j-2,i)-psi(j-2,i-1))/(2dxdy)
+    expect = -(psi[NH, 5]+psi[NH, 4]-psi[NH-2, 5]-psi[NH-2, 4])/(2*dx*dy)
+    np.testing.assert_allclose(src[NH, NH:-NH], expect, rtol=1e-12)
+    np.testing.assert_allclose(expect, 2.*U/dx, rtol=1e-12)   # two corner pairs, two rows apart: 4 U dy / (2 dx dy)
+    assert not src[NH+1:-NH, NH:-NH].any()      # no wall, no source
+    # the gather form the CUDA kernel uses gives the same field (scatter in the Fortran)
+    tot = 0.
+    for i in range(NH, nx-NH+1):
+        tot += src[NH, i]
+    assert tot != 0.
+
+
+def test_remaining_reductions():
+    ny, nx = 16, 20
+    rng = np.random.default_rng(2)
+    msk = (rng.random((ny, nx)) > 0.2).astype(np.int8)
+    a, b = rng.standard_normal((ny, nx)), rng.standard_normal((ny, nx))
+    inner = (slice(NH, -NH), slice(NH, -NH))
+    m = msk[inner] != 0
+    np.testing.assert_allclose(fd.computedotprod(msk, a, b, NH), (a[inner]*b[inner])[m].sum(), rtol=1e-13)
+    np.testing.assert_allclose(fd.computesum(msk, a, NH), a[inner][m].sum(), rtol=1e-13)
+    z, z2 = fd.computesumandnorm(msk, a, NH)
+    np.testing.assert_allclose([z, z2], [a[inner][m].sum(), (a[inner][m]**2).sum()], rtol=1e-13)
+    # multigrid norm: sum of squares over the interior where the mask is fluid
+    np.testing.assert_allclose(fm.computenorm(msk, a, NH), (a[inner][m]**2).sum(), rtol=1e-13)
+    # ke: quarter sum of the four face contributions of each cell, maxu from cell-centred speeds
+    u, v = a, b
+    ke, maxu = fd.computekemaxu(np.ones((ny, nx), dtype=np.int8), u, v, NH)
+    ui, um = u[inner], u[NH:-NH, NH-1:-NH-1]
+    vi, vm = v[inner], v[NH-1:-NH-1, NH:-NH]
+    np.testing.assert_allclose(ke, 0.25*(ui**2+um**2+vi**2+vm**2).sum(), rtol=1e-13)
+    np.testing.assert_allclose(maxu, 0.5*(np.abs(ui+um)+np.abs(vi+vm)).max(), rtol=1e-13)

@@ -2,31 +2,27 @@
 Same interface: var, ope, tscheme, diags, step, dynamics, add_noslip,
 set_psi_from_vorticity, diagnostics, forc / extrastep hooks."""
 import numpy as np
-from importlib import import_module
+import torch
 
+from modelbase import adopt, declare_state, user_object, EMBEDDED_FORCING_NOTE
 from operators import Operators
 from variables import Var
 from timescheme import Timescheme
 from runtime import rt
-import torch
+
+FROM_PARAM = ('timestepping', 'forcing', 'forcing_module', 'diffusion', 'Kdiff', 'noslip', 'gravity',
+              'customized', 'custom_module', 'additional_tracer', 'isisland', 'myrank')
+FROM_GRID = ('nh', 'Lx', 'msk', 'area', 'xr', 'yr', 'mpitools')
 
 
 class Boussinesq(object):
     def __init__(self, param, grid):
-        self.list_param = ['forcing', 'noslip', 'timestepping', 'diffusion', 'Kdiff', 'myrank',
-                           'forcing_module', 'gravity', 'isisland', 'customized', 'custom_module',
-                           'additional_tracer']
-        param.copy(self, self.list_param)
-        self.list_param = ['xr', 'yr', 'nh', 'Lx', 'msk', 'area', 'mpitools']
-        grid.copy(self, self.list_param)
-        param.varname_list = ['vorticity', 'psi', 'u', 'v', 'buoyancy', 'banom']
-        param.tracer_list = ['vorticity', 'buoyancy']
-        param.whosetspsi = ('vorticity')
-        if hasattr(self, 'additional_tracer'):
-            for trac in self.additional_tracer:
-                param.varname_list.append(trac)
-                param.tracer_list.append(trac)
-        param.sizevar = [grid.nyl, grid.nxl]
+        adopt(self, param, FROM_PARAM)
+        adopt(self, grid, FROM_GRID)
+        # vorticity and buoyancy are advected; 'banom' is the diagnosed anomaly b - bref
+        declare_state(param, grid, ['vorticity', 'psi', 'u', 'v', 'buoyancy', 'banom'],
+                      ['vorticity', 'buoyancy'], 'vorticity',
+                      more_tracers=getattr(self, 'additional_tracer', ()))
         self.var = Var(param)
         r = rt()
         self.rt = r
@@ -41,21 +37,12 @@ class Boussinesq(object):
         self.tscheme.set(self.dynamics, self.timestepping)
         if self.forcing:
             if self.forcing_module == 'embedded':
-                self.msg_forcing = ('To make Fluid2d aware of your embedded forcing\n'
-                                    'you need to add in the user script \n'
-                                    'model.forc = Forcing(param, grid)\n'
-                                    'right below the line: model = f2d.model')
+                self.msg_forcing = EMBEDDED_FORCING_NOTE
             else:
-                try:
-                    f = import_module(self.forcing_module)
-                except ImportError:
-                    raise ImportError('module %s for forcing cannot be found; make sure file **%s.py** exists'
-                                      % (self.forcing_module, self.forcing_module))
-                self.forc = f.Forcing(param, grid)
+                self.forc = user_object(self.forcing_module, 'Forcing', param, grid, 'forcing')
         self.diags = {}
         if self.customized:
-            f = import_module(self.custom_module)
-            self.extrastep = f.Step(param, grid)
+            self.extrastep = user_object(self.custom_module, 'Step', param, grid, 'customized step')
 
     def step(self, t, dt):
         r, lib = self.rt, self.rt.lib

@@ -7,37 +7,30 @@ state and the tendency buffers are DeviceState objects; user hooks see them thro
 host views (devarray.py).
 """
 import numpy as np
-from importlib import import_module
 
+from modelbase import adopt, declare_state, user_object, EMBEDDED_FORCING_NOTE
 from operators import Operators
 from variables import Var
 from timescheme import Timescheme
 from timers import Timers
 from runtime import rt
 
+FROM_PARAM = ('timestepping', 'forcing', 'forcing_module', 'diffusion', 'Kdiff', 'noslip', 'spongelayer',
+              'customized', 'custom_module', 'additional_tracer', 'var_to_save', 'enforce_momentum')
+FROM_GRID = ('nh', 'ny', 'dx', 'Lx', 'msk', 'area', 'xr', 'yr', 'r2', 'x0', 'y0', 'x2', 'y2', 'isisland',
+             'mpitools')
+
 
 class Euler(object):
     def __init__(self, param, grid):
-        self.list_param = ['forcing', 'noslip', 'timestepping', 'diffusion', 'Kdiff', 'forcing_module',
-                           'additional_tracer', 'enforce_momentum', 'var_to_save', 'customized',
-                           'custom_module', 'spongelayer']
-        param.copy(self, self.list_param)
-        self.list_param = ['yr', 'nh', 'msk', 'area', 'mpitools', 'dx', 'xr', 'yr', 'r2', 'x0', 'y0', 'x2',
-                           'y2', 'isisland', 'Lx', 'ny']
-        grid.copy(self, self.list_param)
-
-        param.varname_list = ['vorticity', 'psi', 'u', 'v', 'source']
-        param.tracer_list = ['vorticity']
-        param.whosetspsi = ('vorticity')
-        if 'tauw' in self.var_to_save:
-            param.varname_list.append('tauw')
-        if 'wshear' in self.var_to_save:
-            param.varname_list.append('wshear')
-        if hasattr(self, 'additional_tracer'):
-            for trac in self.additional_tracer:
-                param.varname_list.append(trac)
-                param.tracer_list.append(trac)
-        param.sizevar = [grid.nyl, grid.nxl]
+        adopt(self, param, FROM_PARAM)
+        adopt(self, grid, FROM_GRID)
+        # state: the four dynamical fields, the no-slip source, optional wall diagnostics,
+        # then the passive tracers the user asked for
+        fields = ['vorticity', 'psi', 'u', 'v', 'source']
+        fields += [name for name in ('tauw', 'wshear') if name in self.var_to_save]
+        declare_state(param, grid, fields, ['vorticity'], 'vorticity',
+                      more_tracers=getattr(self, 'additional_tracer', ()))
         self.var = Var(param)
         self.timers = Timers(param)
         self.ope = Operators(param, grid)
@@ -59,31 +52,18 @@ class Euler(object):
         self.d_xr = r.to_device(self.xr, dtype=np.float64)
         self.d_yr = r.to_device(self.yr, dtype=np.float64)
         self.ncell = grid.nyl*grid.nxl
-
         if self.forcing:
             if self.forcing_module == 'embedded':
-                print('Warning: check that you have indeed added the forcing to the model')
-                print('Right below the line    : model = f2d.model')
-                print('you should have the line: model.forc = Forcing(param, grid)')
+                print(EMBEDDED_FORCING_NOTE)
             else:
-                try:
-                    f = import_module(self.forcing_module)
-                except ImportError:
-                    raise ImportError('module %s for forcing cannot be found; make sure file **%s.py** exists'
-                                      % (self.forcing_module, self.forcing_module))
-                self.forc = f.Forcing(param, grid)
+                self.forc = user_object(self.forcing_module, 'Forcing', param, grid, 'forcing')
         if self.spongelayer:
-            # [0 = full sponge, 1 = no sponge]
+            # damping factor towards the east end of the domain: 1 = untouched, 0 = fully damped
             self.spongemsk = (1-(1+np.tanh((self.xr - self.Lx)/0.1))*0.5)
             self.d_spongemsk = r.to_device(self.spongemsk, dtype=np.float64)
         self.diags = {}
         if self.customized:
-            try:
-                f = import_module(self.custom_module)
-            except ImportError:
-                raise ImportError('module %s cannot be found; make sure file **%s.py** exists'
-                                  % (self.custom_module, self.custom_module))
-            self.extrastep = f.Step(param, grid)
+            self.extrastep = user_object(self.custom_module, 'Step', param, grid, 'customized step')
 
     def step(self, t, dt):
         r, lib = self.rt, self.rt.lib

@@ -2,48 +2,43 @@
 The elliptic operator is the Helmholtz operator (Laplacian - 1/Rd^2), built by the
 device multigrid when param.qgoperator is set (hierarchy.py:80-84)."""
 import numpy as np
-from importlib import import_module
 import torch
 
+from modelbase import adopt, declare_state, user_object
 from operators import Operators
 from variables import Var
 from timescheme import Timescheme
 from runtime import rt
 
+FROM_PARAM = ('timestepping', 'forcing', 'forcing_module', 'diffusion', 'Kdiff', 'noslip', 'beta', 'Rd',
+              'ageostrophic', 'bottom_torque')
+FROM_GRID = ('nh', 'msk', 'area', 'yr', 'isisland', 'mpitools')
+
 
 class QG(object):
     def __init__(self, param, grid):
-        self.list_param = ['forcing', 'diffusion', 'Kdiff', 'noslip', 'timestepping', 'beta', 'Rd',
-                           'ageostrophic', 'bottom_torque', 'forcing_module']
-        param.copy(self, self.list_param)
-        self.list_param = ['yr', 'nh', 'msk', 'area', 'mpitools', 'isisland']
-        grid.copy(self, self.list_param)
+        adopt(self, param, FROM_PARAM)
+        adopt(self, grid, FROM_GRID)
         if param.bottom_torque or param.ageostrophic:
             raise NotImplementedError('QG: bottom_torque / ageostrophic diagnostics are not built yet')
-        param.varname_list = ['pv', 'psi', 'u', 'v', 'pvanom', 'vorticity']
-        param.sizevar = [grid.nyl, grid.nxl]
+        # the full PV is advected; the inversion reads its anomaly w.r.t. the background beta*y
+        declare_state(param, grid, ['pv', 'psi', 'u', 'v', 'pvanom', 'vorticity'], ['pv'], 'pvanom')
         self.var = Var(param)
         r = rt()
         self.rt = r
         self.ncell = grid.nyl*grid.nxl
         self.source = torch.zeros((grid.nyl, grid.nxl), dtype=torch.float64, device=r.device)
-        self.ipva = self.var.index('pvanom')
-        self.ipv = self.var.index('pv')
-        self.ivor = self.var.index('vorticity')
-        self.ipsi = self.var.index('psi')
+        ix = self.var.index
+        self.ipv, self.ipsi, self.ipva, self.ivor = ix('pv'), ix('psi'), ix('pvanom'), ix('vorticity')
         self.pvback = self.beta*(grid.yr-grid.Ly*.5)*grid.msk
         self.d_pvback = r.to_device(self.pvback, dtype=np.float64)
-        param.tracer_list = ['pv']
-        param.whosetspsi = ('pvanom')
-        param.qgoperator = True
+        param.qgoperator = True      # Helmholtz operator in the multigrid (hierarchy.py:80-84)
         self.ope = Operators(param, grid)
         self.tscheme = Timescheme(param, self.var.dstate)
         self.dx0 = self.tscheme.dx0
         self.kt = 0
-        if self.forcing:
-            if self.forcing_module != 'embedded':
-                f = import_module(self.forcing_module)
-                self.forc = f.Forcing(param, grid)
+        if self.forcing and self.forcing_module != 'embedded':
+            self.forc = user_object(self.forcing_module, 'Forcing', param, grid, 'forcing')
         self.diags = {}
         self.tscheme.set(self.dynamics, self.timestepping)
 

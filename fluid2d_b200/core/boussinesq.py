@@ -94,13 +94,9 @@ class Boussinesq(object):
         lib.computedotprod(msk, s.rptr(ix('buoyancy')), r.ptr(self.d_yr), nh, ny, nx, slot(6), sc, r.stream)
         ke, maxu, z, z2, b, b2, by = r.read_out(7)
         pe = - self.gravity * by
-        cst = self.mpitools.local_to_global([(maxu, 'max'), (ke, 'sum'), (z, 'sum'), (z2, 'sum'),
+        glo = self.mpitools.local_to_global([(maxu, 'max'), (ke, 'sum'), (z, 'sum'), (z2, 'sum'),
                                              (pe, 'sum'), (b, 'sum'), (b2, 'sum')])
-        self.diags['maxspeed'] = cst[0]
-        self.diags['ke'] = cst[1] / self.area
-        self.diags['pe'] = cst[4] / self.area
-        self.diags['energy'] = (cst[1]+cst[4]) / self.area
-        self.diags['vorticity'] = cst[2] / self.area
-        self.diags['enstrophy'] = 0.5*cst[3] / self.area
-        self.diags['buoyancy'] = cst[5] / self.area
-        self.diags['brms'] = np.sqrt(cst[6] / self.area-(cst[5]/self.area)**2)
+        # domain means (maxspeed is a maximum, not a mean)
+        maxu, ke, z, z2, pe, b, b2 = [glo[0]]+[v/self.area for v in glo[1:]]
+        self.diags.update(maxspeed=maxu, ke=ke, pe=pe, energy=(glo[1]+glo[4])/self.area, vorticity=z, enstrophy=0.5*z2,
+                          buoyancy=b, brms=np.sqrt(b2-b**2))

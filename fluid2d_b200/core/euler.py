@@ -137,15 +137,11 @@ class Euler(object):
         lib.diag_euler(r.ptr(self.ope.d_msk), s.rptr(ix('u')), s.rptr(ix('v')), s.rptr(ix('vorticity')),
                        s.rptr(ix('psi')), s.rptr(ix('source')), r.ptr(self.d_xr), r.ptr(self.d_yr),
                        self.nh, s.ny, s.nx, r.ptr(r.out), r.ptr(r.scratch), r.stream)
-        maxu, ke, z, z2, px, py, angmom, sce = r.read_out(8)
-        cst = self.mpitools.local_to_global([(maxu, 'max'), (ke, 'sum'), (z, 'sum'), (z2, 'sum'),
-                                             (px, 'sum'), (py, 'sum'), (angmom, 'sum'), (sce, 'sum')])
-        self.diags['maxspeed'] = cst[0]
-        self.diags['ke'] = cst[1] / self.area
-        self.diags['vorticity'] = cst[2] / self.area
-        self.diags['enstrophy'] = 0.5*cst[3] / self.area
-        self.diags['px'] = cst[4] / self.area
-        self.diags['py'] = cst[5] / self.area
-        self.diags['angmom'] = cst[6] / self.area
-        self.diags['source'] = cst[7] / self.area
+        names = ('maxspeed', 'ke', 'vorticity', 'enstrophy', 'px', 'py', 'angmom', 'source')
+        local = r.read_out(8)
+        glo = self.mpitools.local_to_global([(local[0], 'max')]+[(v, 'sum') for v in local[1:]])
+        # domain means, except the maximum speed; enstrophy = half the mean square vorticity
+        for k, name in enumerate(names):
+            self.diags[name] = glo[k] if k == 0 else glo[k]/self.area
+        self.diags['enstrophy'] = 0.5*self.diags['enstrophy']
         self.timers.toc('diag')

@@ -13,6 +13,7 @@ import os
 import sys
 import tempfile
 
+import numpy as np
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -79,7 +80,11 @@ def record(name):
         sys.stdout = so
         mock_device.uninstall()
     # (mg_destroy comes from Gmg.__del__, i.e. whenever the garbage collector runs)
-    return [c for c in list(fake.lib.calls) if c[0] != "mg_destroy"]
+    calls = [c for c in list(fake.lib.calls) if c[0] != "mg_destroy"]
+    # the integral diagnostics the host derived from the (mock) reductions, and the clock
+    diags = sorted((k, float("%.12g" % float(np.ravel(v)[0]))) for k, v in f2d.model.diags.items())
+    calls.append(["<diags>", diags, float("%.12g" % f2d.t), float("%.12g" % f2d.dt), f2d.kt])
+    return calls
 
 
 def load():

@@ -19,18 +19,20 @@ class Island(Param):
         self.nbisland += 1
 
     def finalize(self, mskp_model=None):
+        """per island: psi = psi0 on every corner that touches it, and on the fluid corners next
+        to it the right-hand-side correction (number of island neighbours) * psi0 / (dx dy)"""
         print('found %i islands' % self.nbisland)
         shape = (self.nyl, self.nxl)
-        for isl in self.data:
-            cells = np.ones(shape, dtype=np.int8)
-            cells[isl['idx']] = 0
-            # corner is fluid iff its four cells are (celltocorner(mask) == 1)
-            fluid = np.zeros(shape, dtype=np.int8)
-            fluid[:-1, :-1] = cells[:-1, :-1] & cells[:-1, 1:] & cells[1:, :-1] & cells[1:, 1:]
-            inside = (1-fluid).astype(np.int8)
-            nb = (np.roll(inside, -1, axis=1)+np.roll(inside, -1, axis=0)
-                  + np.roll(inside, +1, axis=1)+np.roll(inside, +1, axis=0))
-            z = nb*isl['psi0']/(self.dx*self.dy)
-            self.rhsp[nb > 0] = z[nb > 0]
-            self.psi[inside == 1] = isl['psi0']
+        cell_area = self.dx*self.dy
+        for island in self.data:
+            psi0 = island['psi0']
+            solid = np.zeros(shape, dtype=bool)
+            solid[island['idx']] = True
+            # a corner belongs to the island unless its four cells are all outside it
+            touches = np.ones(shape, dtype=np.int8)
+            touches[:-1, :-1] = (solid[:-1, :-1] | solid[:-1, 1:] | solid[1:, :-1] | solid[1:, 1:])
+            neighbours = sum(np.roll(touches, shift, axis=axis) for axis in (0, 1) for shift in (-1, 1))
+            near = neighbours > 0
+            self.rhsp[near] = (neighbours*psi0/cell_area)[near]
+            self.psi[touches == 1] = psi0
         print('island are ok')

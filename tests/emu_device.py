@@ -1,0 +1,518 @@
+"""CPU emulation of the C ABI for tests of the HOST layer's numerics.  TEST INFRASTRUCTURE.
+
+`tests/mock_device.py` records which entry points the Python host layer (fluid2d_b200/core)
+calls; this module goes one step further and *executes* every call on CPU memory with the
+oracle's kernels (oracle/kernels.py, oracle/model.py:MG), one entry point at a time, with the
+argument meaning include/f2d_b200.h documents.  Swapping it in for the runtime singleton lets
+the `-m "not gpu"` suite run the product's host layer -- models, operators, time schemes,
+fluxes driver, diagnostics, dt control -- end to end and compare the fields with the fixtures
+frozen from the reference's own Python (tests/golden/*.npz): what is verified is that the host
+layer asks for the right operations on the right buffers in the right order, with arithmetic
+attached.  It says nothing about the CUDA kernels (the -m gpu tests compare those with the
+same oracle through the real library), and nothing under fluid2d_b200/ can reach this module:
+the product has no CPU path.
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+from oracle import kernels as K          # noqa: E402
+from oracle import model as om           # noqa: E402
+
+fa, ff, fo, fd, fm = (K.fortran_advection, K.fortran_fluxes, K.fortran_operators, K.fortran_diag,
+                      K.fortran_multigrid)
+
+
+def _addr(p):
+    if p is None:
+        return 0
+    if isinstance(p, ctypes.c_void_p):
+        return p.value or 0
+    return int(p)
+
+
+def f64(p, *shape):
+    """numpy view of the doubles at address p (None for a NULL pointer)"""
+    a = _addr(p)
+    if not a:
+        return None
+    n = int(np.prod(shape))
+    return np.ctypeslib.as_array((ctypes.c_double*n).from_address(a)).reshape(shape)
+
+
+def i8(p, *shape):
+    a = _addr(p)
+    if not a:
+        return None
+    n = int(np.prod(shape))
+    return np.ctypeslib.as_array((ctypes.c_int8*n).from_address(a)).reshape(shape)
+
+
+def _ones_msk(ny, nx):
+    return np.ones((ny, nx), dtype=np.int8)
+
+
+def _corner_of_all_fluid(ny, nx):
+    """corner mask of an all-fluid domain: 1 except on the last row and column"""
+    m = np.ones((ny, nx), dtype=np.int8)
+    m[-1, :] = 0
+    m[:, -1] = 0
+    return m
+
+
+class _Handle(object):
+    """what an f2d_mg_t* stands for here: the oracle's hierarchy"""
+
+    def __init__(self, mg):
+        self.mg = mg
+        self.Aplanes = {}
+
+
+class EmuLib(object):
+    """one method per entry point of include/f2d_b200.h that the host layer reaches
+    (names without the f2d_ prefix, as fluid2d_b200/_lib.py exposes them)"""
+
+    def __init__(self):
+        self.handles = {}
+        self.count = 0
+        self.called = set()
+
+    def __getattribute__(self, name):
+        v = object.__getattribute__(self, name)
+        if callable(v) and not name.startswith("_"):
+            object.__getattribute__(self, "called").add(name)
+        return v
+
+    # ---- bookkeeping
+    def abi_version(self):
+        return 1
+
+    def last_error(self):
+        return b""
+
+    def launch_count(self):
+        return self.count
+
+    def launch_count_reset(self):
+        self.count = 0
+
+    def reduce_scratch_len(self):
+        return 64
+
+    # ---- copies, halo
+    def copy(self, dst, src, nbytes, stream):
+        ctypes.memmove(_addr(dst), _addr(src), int(nbytes))
+        return 0
+
+    def zero(self, dst, nbytes, stream):
+        ctypes.memset(_addr(dst), 0, int(nbytes))
+        return 0
+
+    def fill_halo(self, x, nh, ny, nx, stream):
+        fm.fillhalo(f64(x, ny, nx), nh)
+        return 0
+
+    def fill_halo_i8(self, x, nh, ny, nx, stream):
+        a = i8(x, ny, nx)
+        t = a.astype(np.float64)
+        fm.fillhalo(t, nh)
+        a[...] = t.astype(np.int8)
+        return 0
+
+    def _fill(self, a, nh, mode):
+        if mode == 1:
+            fm.fillhalo(a, nh)
+        elif mode:
+            raise NotImplementedError("emulator: one rank (fill mode %d)" % mode)
+
+    # ---- advection
+    def _adv(self, upwind, msk, q, dq, u, v, xflx, yflx, cst5, nh, method, order, ny, nx, fill):
+        if nh != 3:
+            return 1
+        m = i8(msk, ny, nx)
+        if m is None:
+            m = _ones_msk(ny, nx)
+        cst = np.array([cst5[k] for k in range(5)])
+        Q, DQ, U, V = f64(q, ny, nx), f64(dq, ny, nx), f64(u, ny, nx), f64(v, ny, nx)
+        XF, YF = f64(xflx, ny, nx), f64(yflx, ny, nx)
+        if XF is None:
+            (fa.adv_upwind if upwind else fa.adv_centered)(m, Q, DQ, U, V, cst, nh, method, order)
+        else:
+            (ff.adv_upwind if upwind else ff.adv_centered)(m, Q, DQ, U, V, XF, YF, cst, nh, method, order)
+        self._fill(DQ, nh, fill)
+        return 0
+
+    def adv_upwind(self, *a):
+        return self._adv(True, *a[:-1])
+
+    def adv_centered(self, *a):
+        return self._adv(False, *a[:-1])
+
+    # ---- operators
+    def celltocorner(self, xr, xp, ny, nx, stream):
+        fo.celltocorner(f64(xr, ny, nx), f64(xp, ny, nx))
+        return 0
+
+    def cornertocell(self, xp, xr, ny, nx, stream):
+        fo.cornertocell(f64(xp, ny, nx), f64(xr, ny, nx))
+        return 0
+
+    def orthogradient(self, msk, psi, dx, dy, nh, u, v, ny, nx, stream):
+        fo.computeorthogradient(i8(msk, ny, nx), f64(psi, ny, nx), dx, dy, nh, f64(u, ny, nx), f64(v, ny, nx))
+        return 0
+
+    def mask_orthogradient(self, msk, mskp, psi, dx, dy, nh, u, v, ny, nx, stream):
+        m, mp = i8(msk, ny, nx), i8(mskp, ny, nx)
+        if m is None:
+            m, mp = _ones_msk(ny, nx), _corner_of_all_fluid(ny, nx)
+        P = f64(psi, ny, nx)
+        P *= mp
+        fo.computeorthogradient(m, P, dx, dy, nh, f64(u, ny, nx), f64(v, ny, nx))
+        return 0
+
+    def add_diffusion(self, msk, trac, dx, nh, Kdiff, dtrac, ny, nx, fill, stream):
+        D = f64(dtrac, ny, nx)
+        fo.add_diffusion(i8(msk, ny, nx), f64(trac, ny, nx), dx, nh, Kdiff, D)
+        self._fill(D, nh, fill)
+        return 0
+
+    def add_torque(self, msk, buoy, dx, nh, gravity, domega, ny, nx, premask, fill, stream):
+        m, D = i8(msk, ny, nx), f64(domega, ny, nx)
+        if premask:
+            D *= m
+        fo.add_torque(m, f64(buoy, ny, nx), dx, nh, gravity, D)
+        self._fill(D, nh, fill)
+        return 0
+
+    def noslip_source(self, msknoslip, psi, y, dx, dy, nh, ny, nx, stream):
+        fo.computenoslipsourceterm(i8(msknoslip, ny, nx), f64(psi, ny, nx), f64(y, ny, nx), dx, dy, nh)
+        return 0
+
+    # ---- reductions (sequential sums: the Fortran's own order)
+    def computedotprod(self, msk, x, y, nh, ny, nx, out, scratch, stream):
+        f64(out, 1)[0] = fd.computedotprod(i8(msk, ny, nx), f64(x, ny, nx), f64(y, ny, nx), nh)
+        return 0
+
+    def computemax(self, msk, x, nh, ny, nx, out, scratch, stream):
+        f64(out, 1)[0] = fd.computemax(i8(msk, ny, nx), f64(x, ny, nx), nh)
+        return 0
+
+    def computesum(self, msk, x, nh, ny, nx, out, scratch, stream):
+        f64(out, 1)[0] = fd.computesum(i8(msk, ny, nx), f64(x, ny, nx), nh)
+        return 0
+
+    def computesumandnorm(self, msk, x, nh, ny, nx, out, scratch, stream):
+        f64(out, 2)[:] = fd.computesumandnorm(i8(msk, ny, nx), f64(x, ny, nx), nh)
+        return 0
+
+    def computekemaxu(self, msk, u, v, nh, ny, nx, out, scratch, stream):
+        f64(out, 2)[:] = fd.computekemaxu(i8(msk, ny, nx), f64(u, ny, nx), f64(v, ny, nx), nh)
+        return 0
+
+    def computenorm(self, msk, x, nh, ny, nx, out, scratch, stream):
+        f64(out, 1)[0] = fm.computenorm(i8(msk, ny, nx), f64(x, ny, nx), nh)
+        return 0
+
+    def domain_sum(self, x, nh, ny, nx, out, scratch, stream):
+        f64(out, 1)[0] = np.sum(f64(x, ny, nx)[nh:-nh, nh:-nh])
+        return 0
+
+    def diag_euler(self, msk, u, v, w, psi, source, xr, yr, nh, ny, nx, out, scratch, stream):
+        m = i8(msk, ny, nx)
+        W = f64(w, ny, nx)
+        o = f64(out, 8)
+        ke, maxu = fd.computekemaxu(m, f64(u, ny, nx), f64(v, ny, nx), nh)
+        z, z2 = fd.computesumandnorm(m, W, nh)
+        o[0], o[1], o[2], o[3] = maxu, ke, z, z2
+        o[4] = fd.computedotprod(m, W, f64(xr, ny, nx), nh)
+        o[5] = fd.computedotprod(m, W, f64(yr, ny, nx), nh)
+        o[6] = fd.computesum(m, f64(psi, ny, nx), nh)
+        o[7] = fd.computedotprod(m, W, f64(source, ny, nx), nh)
+        return 0
+
+    # ---- time-scheme combinations: the numpy expressions of timescheme.py
+    def ts_axpy(self, y, c, a, n, stream):
+        Y = f64(y, n)
+        Y += c*f64(a, n)
+        return 0
+
+    def ts_xpay(self, out, x, c, a, n, stream):
+        f64(out, n)[:] = f64(x, n) + c*f64(a, n)
+        return 0
+
+    def ts_xpay2(self, out, x, c, a, b, n, stream):
+        f64(out, n)[:] = f64(x, n) + c*(f64(a, n)+f64(b, n))
+        return 0
+
+    def ts_rk3ssp_final(self, x, c, a, b, d, n, stream):
+        X = f64(x, n)
+        X += c*(f64(a, n)+f64(b, n)+4*f64(d, n))
+        return 0
+
+    def ts_ab2(self, x, c0, a, c1, b, n, stream):
+        X = f64(x, n)
+        X += c0*f64(a, n) - c1*f64(b, n)
+        return 0
+
+    def ts_ab3(self, x, c0, a, c1, b, c2, d, n, stream):
+        X = f64(x, n)
+        X += c0*f64(a, n) - c1*f64(b, n) + c2*f64(d, n)
+        return 0
+
+    def ts_set_xpay(self, x, xb, c, a, n, stream):
+        f64(x, n)[:] = f64(xb, n) + c*f64(a, n)
+        return 0
+
+    def ts_asselin(self, xs, c, x, xb, n, stream):
+        XS = f64(xs, n)
+        XS += c*(f64(x, n)+f64(xb, n)-2*XS)
+        return 0
+
+    def ts_am3(self, x, xs, xb, n, stream):
+        X = f64(x, n)
+        X[:] = (1./12.)*(5.*X + 8.*f64(xs, n)-f64(xb, n))
+        return 0
+
+    # ---- elementwise glue
+    def mul_field(self, y, a, n, stream):
+        Y = f64(y, n)
+        Y *= f64(a, n)
+        return 0
+
+    def mul_mask(self, y, a, n, stream):
+        Y = f64(y, n)
+        Y *= i8(a, n)
+        return 0
+
+    def scale(self, y, alpha, n, stream):
+        Y = f64(y, n)
+        Y *= alpha
+        return 0
+
+    def add_scaled(self, y, alpha, a, n, stream):
+        Y = f64(y, n)
+        Y += alpha*f64(a, n)
+        return 0
+
+    def add_scaled_mask(self, y, alpha, a, n, stream):
+        Y = f64(y, n)
+        Y += alpha*i8(a, n)
+        return 0
+
+    def set_sum(self, y, a, alpha, b, n, stream):
+        f64(y, n)[:] = f64(a, n) + alpha*f64(b, n)
+        return 0
+
+    def div_scalar(self, y, d, n, stream):
+        Y = f64(y, n)
+        Y /= d
+        return 0
+
+    def sub_lin2_mask(self, y, pa, a, pb, b, mask, n, stream):
+        Y = f64(y, n)
+        Y -= (pa*f64(a, n)+pb*f64(b, n))*i8(mask, n)
+        return 0
+
+    def sub_lin2(self, y, pa, a, pb, b, n, stream):
+        Y = f64(y, n)
+        Y -= (f64(a, n)*pa+f64(b, n)*pb)
+        return 0
+
+    def sub_devscalar(self, y, dev_scalar, denom, n, stream):
+        Y = f64(y, n)
+        Y -= f64(dev_scalar, 1)[0]/denom
+        return 0
+
+    def sub_devscalar_mask(self, y, dev_scalar, denom, a, n, stream):
+        Y = f64(y, n)
+        Y -= (f64(dev_scalar, 1)[0]/denom)*i8(a, n)
+        return 0
+
+    # ---- fluxes driver, output
+    def flx_cellvel(self, u, v, uc, vc, nh, ny, nx, fill, stream):
+        U, V, UC, VC = f64(u, ny, nx), f64(v, ny, nx), f64(uc, ny, nx), f64(vc, ny, nx)
+        UC[nh:-nh, nh:-nh] = (0.5*(U+np.roll(U, 1, axis=1)))[nh:-nh, nh:-nh]
+        VC[nh:-nh, nh:-nh] = (0.5*(V+np.roll(V, 1, axis=0)))[nh:-nh, nh:-nh]
+        self._fill(UC, nh, fill)
+        self._fill(VC, nh, fill)
+        return 0
+
+    def flx_split(self, rev, irr, fwd, bwd, cff, sign, n, stream):
+        F, B = f64(fwd, n), f64(bwd, n)
+        sb = sign*B
+        r = cff*(F+sb)
+        i = cff*(F-sb)
+        f64(rev, n)[:] = r
+        f64(irr, n)[:] = i
+        return 0
+
+    def pack_interior_f32(self, x, out, nh, ny, nx, stream):
+        m, n = ny-2*nh, nx-2*nh
+        o = np.ctypeslib.as_array((ctypes.c_float*(m*n)).from_address(_addr(out))).reshape(m, n)
+        o[...] = f64(x, ny, nx)[nh:-nh, nh:-nh].astype(np.float32)
+        return 0
+
+    # ---- multigrid
+    def mg_create(self, h, cornermask, ny, nx, dx, dy, omega, hydroepsilon, Rd, stream):
+        cm = f64(cornermask, ny, nx).copy()
+        mg = om.MG(cm, nx-6, ny-6, dx, dy, omega=omega, hydroepsilon=hydroepsilon, Rd=(Rd if Rd > 0 else None))
+        key = len(self.handles)+1
+        self.handles[key] = _Handle(mg)
+        h._obj.value = key
+        return 0
+
+    def mg_create_slab(self, *a):
+        raise NotImplementedError("emulator: one rank")
+
+    def _h(self, h):
+        return self.handles[_addr(h)]
+
+    def mg_destroy(self, h):
+        self.handles.pop(_addr(h), None)
+        return 0
+
+    def mg_slab_levels(self, h):
+        return 0
+
+    def mg_nlevels(self, h):
+        return self._h(h).mg.nlevs
+
+    def mg_level_shape(self, h, lev, ny, nx):
+        m, n = self._h(h).mg.sizes[lev]
+        ny._obj.value, nx._obj.value = m+6, n+6
+        return 0
+
+    def mg_level_matrix_mode(self, h, lev):
+        return 0
+
+    def mg_level_ptr(self, h, lev, which):
+        H = self._h(h)
+        mg = H.mg
+        if which == 0:
+            return mg.msk[lev].ctypes.data
+        if which == 1:     # 5 planes [5][ny][nx]
+            if lev not in H.Aplanes:
+                H.Aplanes[lev] = np.ascontiguousarray(np.moveaxis(mg.A[lev], 2, 0))
+            return H.Aplanes[lev].ctypes.data
+        return (mg.x, mg.b, mg.r)[which-2][lev].ctypes.data
+
+    def mg_set_graphs(self, h, enable):
+        return 0
+
+    def mg_vcycle(self, h, lev1, stream):
+        self._h(h).mg.vcycle(lev1)
+        return 0
+
+    def mg_fcycle(self, h, lev1, stream):
+        self._h(h).mg.fcycle(lev1)
+        return 0
+
+    def mg_two_vcycle(self, h, psi, rhs, stream):
+        mg = self._h(h).mg
+        shape = mg.x[0].shape
+        mg.two_vcycle(f64(psi, *shape), f64(rhs, *shape))
+        return 0
+
+    def mg_solve(self, h, psi, rhs, tol, maxite, nite, res, stream):
+        mg = self._h(h).mg
+        shape = mg.x[0].shape
+        try:
+            n, r = mg.solve(f64(psi, *shape), f64(rhs, *shape), maxite=maxite, tol=tol)
+        except RuntimeError:
+            return 4
+        if nite is not None:
+            nite._obj.value = int(n)
+        if res is not None:
+            res._obj.value = float(r)
+        return 0
+
+    def invert_vorticity(self, h, msk, mskp, w, psi, u, v, work, rhsp, psi_island, full, perio, area, dx, dy,
+                         nh, nite, res, scratch, stream):
+        mg = self._h(h).mg
+        ny, nx = mg.x[0].shape
+        n = ny*nx
+        self.celltocorner(w, work, ny, nx, stream)
+        if _addr(rhsp):
+            self.add_scaled(work, -1., rhsp, n, stream)
+        if full:
+            err = self.mg_solve(h, psi, work, 1e-11, 4, nite, res, stream)
+            if err:
+                return err
+            if perio:
+                P = f64(psi, ny, nx)
+                P -= np.sum(P[nh:-nh, nh:-nh])/area
+        else:
+            self.mg_two_vcycle(h, psi, work, stream)
+            if nite is not None:
+                nite._obj.value = 1
+            if res is not None:
+                res._obj.value = 0.
+        if not _addr(psi_island):
+            return self.mask_orthogradient(msk, mskp, psi, dx, dy, nh, u, v, ny, nx, stream)
+        self.mul_mask(psi, mskp, n, stream)
+        self.add_scaled(psi, 1., psi_island, n, stream)
+        return self.orthogradient(msk, psi, dx, dy, nh, u, v, ny, nx, stream)
+
+    # ---- one rank: the multi-GPU entry points degenerate
+    def comm_barrier(self, comm, stream):
+        return 0
+
+
+class EmuRuntime(object):
+    """stands where runtime.Runtime stands; state lives in CPU tensors"""
+
+    def __init__(self):
+        self.lib = EmuLib()
+        self.device = torch.device("cpu")
+        self.scratch = torch.zeros(64, dtype=torch.float64)
+        self.out = torch.zeros(16, dtype=torch.float64)
+        self.out_host = torch.zeros(16, dtype=torch.float64)
+        self.comm = None
+        self.nranks = 1
+        self.rank = 0
+
+    def ensure_comm(self, nranks, fieldbytes):
+        if nranks != 1:
+            raise NotImplementedError("emulator: one rank")
+
+    def alloc(self, shape, dtype=torch.float64):
+        return torch.zeros(shape, dtype=dtype)
+
+    @property
+    def stream(self):
+        return None
+
+    def ptr(self, t):
+        return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+    def to_device(self, a, dtype=None):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype).copy())
+
+    def read_out(self, n):
+        return self.out[:n].tolist()
+
+
+def install():
+    """activate the host layer on top of the emulated library; returns (api, runtime)"""
+    import fluid2d_b200
+    api = fluid2d_b200.api()
+    import runtime
+    import devarray
+    import mock_device
+    emu = EmuRuntime()
+    runtime._rt = emu
+    del mock_device._REGISTRY[:]
+    mock_device.patch_devicestate(devarray)
+    return api, emu
+
+
+def uninstall():
+    import mock_device
+    mock_device.uninstall()

@@ -155,6 +155,19 @@ def install():
     import devarray
     fake = FakeRuntime()
     runtime._rt = fake
+    patch_devicestate(devarray)
+    return api, fake
+
+
+class _NoStream(object):
+    cuda_stream = 0
+
+    def synchronize(self):
+        pass
+
+
+def patch_devicestate(devarray):
+    """DeviceState blocks live in CPU tensors (shared with tests/emu_device.py)"""
     if not getattr(devarray.DeviceState, "_mock_patched", False):
         real_init = devarray.DeviceState.__init__
 
@@ -162,12 +175,19 @@ def install():
             real_init(self, nvar, ny, nx, device=torch.device("cpu"))
             register(self.dev, "S", ny*nx*8)
         devarray.DeviceState.__init__ = init
-        devarray.DeviceState._mock_patched = True
+        devarray.DeviceState._mock_patched = real_init
     if not torch.cuda.is_available():
         torch.cuda.synchronize = lambda *a, **k: None
-    return api, fake
+        torch.cuda.current_stream = lambda *a, **k: _NoStream()
 
 
 def uninstall():
+    """back to the real runtime (a GPU test that follows in the same process must get
+    device-resident state again)"""
     import runtime
+    import devarray
     runtime._rt = None
+    real_init = getattr(devarray.DeviceState, "_mock_patched", False)
+    if real_init:
+        devarray.DeviceState.__init__ = real_init
+        devarray.DeviceState._mock_patched = False

@@ -9,6 +9,7 @@ from operators import Operators
 from variables import Var
 from timescheme import Timescheme
 from runtime import rt
+from devarray import HostField
 
 FROM_PARAM = ('timestepping', 'forcing', 'forcing_module', 'diffusion', 'Kdiff', 'noslip', 'gravity',
               'customized', 'custom_module', 'additional_tracer', 'isisland', 'myrank')
@@ -27,9 +28,9 @@ class Boussinesq(object):
         r = rt()
         self.rt = r
         self.ncell = grid.nyl*grid.nxl
-        # reference buoyancy: the buoyancy field at construction time (zeros)
-        self.bref = self.var.get('buoyancy').copy()
-        self.d_bref = r.to_device(self.bref, dtype=np.float64)
+        # reference buoyancy: the buoyancy field at construction time (zeros); scripts set it
+        # afterwards in place (model.bref[:, :] = buoy), hence a HostField
+        self.bref = HostField(self.var.get('buoyancy'))
         self.source = torch.zeros((grid.nyl, grid.nxl), dtype=torch.float64, device=r.device)
         self.d_yr = r.to_device(self.yr, dtype=np.float64)
         self.ope = Operators(param, grid)
@@ -53,7 +54,9 @@ class Boussinesq(object):
         if self.customized:
             self.extrastep.do(self.var, t, dt)
         ib, ia = self.var.index('buoyancy'), self.var.index('banom')
-        lib.set_sum(state.wptr(ia), state.rptr(ib), -1., r.ptr(self.d_bref), self.ncell, r.stream)
+        if not isinstance(self.bref, HostField):
+            self.bref = HostField(self.bref)        # the script replaced the attribute
+        lib.set_sum(state.wptr(ia), state.rptr(ib), -1., self.bref.device_ptr(), self.ncell, r.stream)
 
     def dynamics(self, x, t, dxdt):
         self.ope.rhs_adv(x, t, dxdt)

@@ -130,6 +130,63 @@ class TrackedArray(np.ndarray):
         return np.array(self.view(np.ndarray), order=order, copy=True)
 
 
+class HostField(np.ndarray):
+    """Host array with a device twin that is uploaded on demand.
+
+    For model constants the reference keeps as plain numpy attributes and experiment scripts
+    edit in place after the model is built (`model.bref[:, :] = buoy`, Internal_IVP /
+    KelvinHelmholtz / Leewave).  Any write through the array or a view of it marks the root
+    stale; `device_ptr()` uploads again before handing out the device address."""
+
+    _root = None
+    _stale = True
+    _dev = None
+
+    def __new__(cls, array):
+        obj = np.array(array, dtype=np.float64, order='C', copy=True).view(cls)
+        obj._root = None
+        obj._stale = True
+        obj._dev = None
+        return obj
+
+    def __array_finalize__(self, obj):
+        if isinstance(obj, HostField):
+            self._root = obj if obj._root is None else obj._root
+
+    def _touch(self):
+        (self if self._root is None else self._root)._stale = True
+
+    def __setitem__(self, key, value):
+        np.ndarray.__setitem__(self, key, value)
+        self._touch()
+
+    def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kwargs):
+        plain = [x.view(np.ndarray) if isinstance(x, HostField) else x for x in inputs]
+        if out is not None:
+            for o in out:
+                if isinstance(o, HostField):
+                    o._touch()
+            kwargs['out'] = tuple(o.view(np.ndarray) if isinstance(o, HostField) else o for o in out)
+        res = getattr(ufunc, method)(*plain, **kwargs)
+        if out is not None:
+            return out[0] if len(out) == 1 else out
+        return res
+
+    def fill(self, value):
+        np.ndarray.fill(self, value)
+        self._touch()
+
+    def device_ptr(self):
+        """device address of the twin, uploaded first if the host side was written"""
+        from runtime import rt
+        r = rt()
+        root = self if self._root is None else self._root
+        if root._stale or root._dev is None:
+            root._dev = r.to_device(root.view(np.ndarray), dtype=np.float64)
+            root._stale = False
+        return r.ptr(root._dev)
+
+
 class DeviceState(object):
     """[nvar, ny, nx] float64 in HBM (torch owns the allocation) + pinned host mirror"""
 

@@ -19,10 +19,11 @@ class QG(object):
     def __init__(self, param, grid):
         adopt(self, param, FROM_PARAM)
         adopt(self, grid, FROM_GRID)
-        if param.bottom_torque or param.ageostrophic:
-            raise NotImplementedError('QG: bottom_torque / ageostrophic diagnostics are not built yet')
-        # the full PV is advected; the inversion reads its anomaly w.r.t. the background beta*y
-        declare_state(param, grid, ['pv', 'psi', 'u', 'v', 'pvanom', 'vorticity'], ['pv'], 'pvanom')
+        # the full PV is advected; the inversion reads its anomaly w.r.t. the background beta*y.
+        # Optional diagnosed fields ride along as advected tracers (quasigeostrophic.py:34-58):
+        # 'btorque' (bottom torque) and 'ua', 'va' (ageostrophic velocity)
+        extra = (['btorque'] if param.bottom_torque else []) + (['ua', 'va'] if param.ageostrophic else [])
+        declare_state(param, grid, ['pv', 'psi', 'u', 'v', 'pvanom', 'vorticity'] + extra, ['pv'] + extra, 'pvanom')
         self.var = Var(param)
         r = rt()
         self.rt = r
@@ -37,6 +38,7 @@ class QG(object):
         self.tscheme = Timescheme(param, self.var.dstate)
         self.dx0 = self.tscheme.dx0
         self.kt = 0
+        self._ageo = None
         if self.forcing and self.forcing_module != 'embedded':
             self.forc = user_object(self.forcing_module, 'Forcing', param, grid, 'forcing')
         self.diags = {}
@@ -45,13 +47,46 @@ class QG(object):
     def step(self, t, dt):
         r, lib = self.rt, self.rt.lib
         s = self.var.dstate
+        n, nbytes = self.ncell, self.ncell*8
+        ix = self.var.index
+        if self.bottom_torque:
+            # the background PV is transported for one step; what it has changed by is the
+            # torque -J(psi, htopo) (quasigeostrophic.py:96-98, 124-131)
+            ibt = ix('btorque')
+            lib.copy(s.wptr(ibt), r.ptr(self.d_pvback), nbytes, r.stream)
+        if self.ageostrophic:
+            iu, iv, iua, iva = ix('u'), ix('v'), ix('ua'), ix('va')
+            lib.copy(s.wptr(iua), s.rptr(iu), nbytes, r.stream)
+            lib.copy(s.wptr(iva), s.rptr(iv), nbytes, r.stream)
         self.dt = dt
         self.tscheme.forward(s, t, dt)
         if self.noslip:
             self.add_noslip(s)
         self.set_psi_from_pv()
-        lib.set_sum(s.wptr(self.ipva), s.rptr(self.ipv), -1., r.ptr(self.d_pvback), self.ncell, r.stream)
-        lib.set_sum(s.wptr(self.ivor), s.rptr(self.ipva), -(self.Rd**-2), s.rptr(self.ipsi), self.ncell, r.stream)
+        lib.set_sum(s.wptr(self.ipva), s.rptr(self.ipv), -1., r.ptr(self.d_pvback), n, r.stream)
+        lib.set_sum(s.wptr(self.ivor), s.rptr(self.ipva), -(self.Rd**-2), s.rptr(self.ipsi), n, r.stream)
+        if self.bottom_torque:
+            lib.set_sum(s.wptr(ibt), s.rptr(ibt), -1., r.ptr(self.d_pvback), n, r.stream)
+            lib.div_scalar(s.wptr(ibt), dt, n, r.stream)
+        if self.ageostrophic:
+            # ua = -(vg - va')/dt - pvback*ug ;  va = +(ug - ua')/dt - pvback*vg   with ua', va' the
+            # transported copies of (u, v)  (quasigeostrophic.py:133-153)
+            if self._ageo is None:
+                self._ageo = r.alloc((s.ny, s.nx))
+            wa, wb, wc = r.ptr(self.ope.work), r.ptr(self.ope.work2), r.ptr(self._ageo)
+            lib.set_sum(wa, s.rptr(iv), -1., s.rptr(iva), n, r.stream)
+            lib.div_scalar(wa, dt, n, r.stream)
+            lib.scale(wa, -1., n, r.stream)
+            lib.copy(wc, s.rptr(iu), nbytes, r.stream)
+            lib.mul_field(wc, r.ptr(self.d_pvback), n, r.stream)
+            lib.add_scaled(wa, -1., wc, n, r.stream)
+            lib.set_sum(wb, s.rptr(iu), -1., s.rptr(iua), n, r.stream)
+            lib.div_scalar(wb, dt, n, r.stream)
+            lib.copy(wc, s.rptr(iv), nbytes, r.stream)
+            lib.mul_field(wc, r.ptr(self.d_pvback), n, r.stream)
+            lib.add_scaled(wb, -1., wc, n, r.stream)
+            lib.copy(s.wptr(iva), wb, nbytes, r.stream)
+            lib.copy(s.wptr(iua), wa, nbytes, r.stream)
 
     def dynamics(self, x, t, dxdt):
         r, lib = self.rt, self.rt.lib

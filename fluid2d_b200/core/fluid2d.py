@@ -23,8 +23,9 @@ from output import Output
 # modelname -> (module, class); the models that need an FFT or the line relaxation are not
 # on the device path
 MODELS = {'euler': ('euler', 'Euler'), 'advection': ('advection', 'Advection'),
-          'boussinesq': ('boussinesq', 'Boussinesq'), 'quasigeostrophic': ('quasigeostrophic', 'QG')}
-NOT_ON_DEVICE = ('boussinesqTS', 'sqg', 'thermalwind')
+          'boussinesq': ('boussinesq', 'Boussinesq'), 'quasigeostrophic': ('quasigeostrophic', 'QG'),
+          'boussinesqTS': ('boussinesqTS', 'BoussinesqTS')}
+NOT_ON_DEVICE = ('sqg', 'thermalwind')
 PV_MODELS = ('quasigeostrophic', 'sqg')
 
 FROM_PARAM = ('modelname', 'tend', 'dt', 'adaptable_dt', 'cfl', 'dtmax', 'exacthistime', 'rescaledtime',

@@ -64,6 +64,14 @@ class Gmg(object):
         else:
             # y-slabs: (ny, nx) is the local slab; coarse levels are gathered and replicated
             self.lib.mg_create_slab(ctypes.byref(self.h), comm, *args)
+        # line relaxation (level.py:153-163): asked for, or implied by flat cells
+        self.relaxation = param.get('relaxation', 'default')
+        if float(param.get('hydroepsilon', 1.))*float(param['dy'])/float(param['dx']) <= .2:
+            self.relaxation = 'tridiagonal'
+        if self.relaxation == 'tridiagonal':
+            if comm is not None:
+                raise ValueError('Small aspect ratio experiment requires param.npy = 1')
+            self.lib.mg_set_relaxation(self.h, 1)
         self.slab_levels = self.lib.mg_slab_levels(self.h)
         self.nlevs = self.lib.mg_nlevels(self.h)
         self.nglo, self.mglo = param['n'], param['m']

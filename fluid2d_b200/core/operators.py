@@ -203,6 +203,15 @@ class Operators(Param):
                        self.nyl, self.nxl, 1, self.fillmode, r.stream)
         self._xch(dxdt.wptr(iw))
 
+    def rhs_torque_density(self, x, t, dxdt):
+        """the torque of the BoussinesqTS model reads the density: same kernel with -g and
+        without the mask product on the tendency (operators.py:316-328)"""
+        r, lib = self.rt, self.lib
+        ib, iw = self.ix('density'), self.ix('vorticity')
+        lib.add_torque(r.ptr(self.d_msk), x.rptr(ib), self.dx, self.nh, -self.gravity, dxdt.wptr(iw),
+                       self.nyl, self.nxl, 0, self.fillmode, r.stream)
+        self._xch(dxdt.wptr(iw))
+
     def rhs_noslip(self, x, source):
         """vorticity source along the walls that cancels the tangential velocity
         (operators.py:245-290); `source` is (DeviceState, field index) or a device tensor"""

@@ -7,6 +7,7 @@
 // halo fill (level.py:365,384,493); here the fill is fused into the producing kernel
 // (threads owning rim cells also store the halo images).
 #include <stdlib.h>
+#include <algorithm>
 #include <vector>
 #include <map>
 #include <tuple>
@@ -39,6 +40,7 @@ struct f2d_mg {
   std::vector<Level> L;
   double omega = 8. / 9.;
   int npre = 1, npost = 1, ndeepest = 16, nvcyc = 1;  // hierarchy.py:29-32
+  int relax = 0;              // 0 damped Jacobi (smoothtwicewithA), 1 line relaxation (smoothtridiag)
   double *scratch = nullptr;  // reductions
   double *dscal = nullptr;    // device scalars [4]
   double *hscal = nullptr;    // pinned host mirror [4]
@@ -235,6 +237,61 @@ __global__ void k_interpolate(const int8_t *__restrict__ msk1, const int8_t *__r
 }
 
 // ---- set-up kernels ---------------------------------------------------------
+// Line relaxation (fortran_multigrid.f90:215-317 smoothtridiag + tridiag): for each column
+// i = 2..n-1 whose first interior corner is fluid, x(4:m-4, i) := V^{-1} (b - H x), V the
+// vertical part of the operator (diagonal A5, off-diagonal A2), H the six other neighbours.
+// The columns are swept west to east IN PLACE, so column i reads the new values of column
+// i-1: a Gauss-Seidel order that leaves no parallelism across columns if the result is to be
+// the reference's.  ONE CTA: the right-hand side and the two diagonals of a column are
+// evaluated by all threads into shared memory, one thread runs the Thomas recurrences
+// (forward elimination with the pivots, back substitution), all threads store the column.
+// Shared memory: 4 arrays of ny doubles (rhs/solution, d, ud, gam).
+__global__ void __launch_bounds__(256)
+k_smooth_tridiag(const int8_t *__restrict__ msk, const double *__restrict__ A, double *x,
+                 const double *__restrict__ b, int ny, int nx) {
+  extern __shared__ double tri_smem[];
+  double *y = tri_smem, *d = y + ny, *ud = d + ny, *gam = ud + ny;
+  const size_t pl = (size_t)ny * nx;
+  const double *A1 = A, *A2 = A + pl, *A3 = A + 2 * pl, *A4 = A + 3 * pl, *A5 = A + 4 * pl;
+  const int k0 = NH, k1 = ny - 5;          // Fortran rows 4 .. m-4
+  for (int i = 1; i <= nx - 2; i++) {      // Fortran columns 2 .. n-1
+    if (msk[(size_t)NH * nx + i] == 0) continue;   // uniform over the block
+    for (int j = k0 + (int)threadIdx.x; j <= k1; j += (int)blockDim.x) {
+      size_t c = (size_t)j * nx + i;
+      double r = b[c] - A1[c] * x[c - nx - 1];
+      r = r - A3[c] * x[c - nx + 1];
+      r = r - A4[c] * x[c - 1];
+      r = r - A4[c + 1] * x[c + 1];
+      r = r - A3[c + nx - 1] * x[c + nx - 1];
+      r = r - A1[c + nx + 1] * x[c + nx + 1];
+      y[j] = r;
+      d[j] = A5[c];
+      ud[j] = A2[c + nx];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && k1 >= k0) {
+      double bet = 1. / d[k0];
+      double prev = y[k0] * bet;
+      y[k0] = prev;
+      for (int k = k0 + 1; k <= k1; k++) {
+        double dd = ud[k - 1];
+        double g = dd * bet;
+        gam[k] = g;
+        bet = 1. / (d[k] - dd * g);
+        prev = (y[k] - dd * prev) * bet;
+        y[k] = prev;
+      }
+      for (int k = k1 - 1; k >= k0; k--) {
+        prev = y[k] - gam[k + 1] * prev;
+        y[k] = prev;
+      }
+    }
+    __syncthreads();
+    for (int j = k0 + (int)threadIdx.x; j <= k1; j += (int)blockDim.x) x[(size_t)j * nx + i] = y[j];
+    __syncthreads();   // the next column reads this one from global memory
+  }
+}
+
 __global__ void k_mask_from_double(const double *__restrict__ a, int8_t *__restrict__ m, size_t n) {
   for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
     m[k] = (int8_t)a[k];
@@ -501,6 +558,17 @@ cudaError_t set_smem_all() {
 // Grid.smooth: nite x (double sweep + fill); ping-pong through the level scratch t
 int op_smooth(f2d_mg *mg, int lev, double *x, const double *b, int nite, cudaStream_t s) {
   Level &l = mg->L[lev];
+  if (mg->relax == 1) {
+    // level.py:340-349: three line relaxations (+ halo fill) per requested iteration
+    const size_t sm = 4 * (size_t)l.ny * sizeof(double);
+    for (int k = 0; k < 3 * nite; k++) {
+      k_smooth_tridiag<<<1, 256, sm, s>>>(l.msk, l.A, x, b, l.ny, l.nx);
+      F2D_LAUNCHED();
+      int rc = f2d_fill_halo(x, NH, l.ny, l.nx, (f2d_stream_t)s);
+      if (rc != F2D_OK) return rc;
+    }
+    return F2D_OK;
+  }
   double *cur = x, *other = l.t;
   for (int k = 0; k < nite; k++) {
     int rc = smooth2(mg, lev, 0, cur, b, other, nullptr, s);
@@ -602,6 +670,10 @@ int op_interpolate(f2d_mg *mg, int lev, const double *xc, double *xf, int add, c
 int coarsest_enqueue(f2d_mg *mg, double *X, const double *B, cudaStream_t s) {
   int last = (int)mg->L.size() - 1;
   Level &l = mg->L[last];
+  if (mg->relax == 1) {
+    F2D_CUDA(cudaMemsetAsync(X, 0, l.n() * sizeof(double), s));
+    return op_smooth(mg, last, X, B, mg->ndeepest, s);
+  }
   double *cur = X, *other = l.t;
   for (int k = 0; k < mg->ndeepest; k++) {
     TRY(smooth2(mg, last, k == 0 ? 1 : 0, cur, B, other, nullptr, s));
@@ -674,6 +746,29 @@ int vcycle_enqueue(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s,
   int last = (int)mg->L.size() - 1;
   auto X = [&](int lev) { return lev == lev1 ? x0 : mg->L[lev].x; };
   auto B = [&](int lev) { return lev == lev1 ? b0 : mg->L[lev].b; };
+  if (mg->relax == 1) {
+    // line relaxation: the operators one by one, as hierarchy.py:98-127 lists them (the fused
+    // kernels below are built around the Jacobi double sweep)
+    if (first_input == 1) F2D_CUDA(cudaMemsetAsync(X(lev1), 0, mg->L[lev1].n() * sizeof(double), s));
+    if (first_input == 2) TRY(op_interpolate(mg, lev1, X(lev1 + 1), X(lev1), 0, s));
+    for (int lev = lev1; lev < last; lev++) {
+      Level &l = mg->L[lev];
+      if (lev > lev1) F2D_CUDA(cudaMemsetAsync(X(lev), 0, l.n() * sizeof(double), s));
+      TRY(op_smooth(mg, lev, X(lev), B(lev), mg->npre, s));
+      TRY(op_residual(mg, lev, X(lev), B(lev), l.r, s));
+      TRY(op_restrict(mg, lev, l.r, B(lev + 1), s));
+    }
+    TRY(coarsest_enqueue(mg, X(last), B(last), s));
+    for (int lev = last - 1; lev >= lev1; lev--) {
+      TRY(op_interpolate(mg, lev, X(lev + 1), X(lev), 1, s));
+      TRY(op_smooth(mg, lev, X(lev), B(lev), mg->npost, s));
+    }
+    if (acc) {
+      k_add_inplace<<<nblocks1d(mg->L[lev1].n()), 256, 0, s>>>(acc, X(lev1), mg->L[lev1].n());
+      F2D_LAUNCHED();
+    }
+    return F2D_OK;
+  }
   const int t0 = mg->tail0;
   if (t0 >= 0 && lev1 == t0 && first_input == 0) return tail_launch(mg, 1, b0, x0, x0, s);
   if (t0 >= 0 && lev1 == t0 && first_input == 1) return tail_launch(mg, 0, b0, nullptr, x0, s);
@@ -1184,6 +1279,7 @@ int common_init(f2d_mg *mg) {
 }  // namespace
 
 extern "C" int f2d_mg_destroy(f2d_mg_t *mg);
+extern "C" int f2d_mg_set_relaxation(f2d_mg_t *mg, int mode);
 
 extern "C" int f2d_mg_create(f2d_mg_t **out, const double *cornermask, int ny, int nx, double dx, double dy,
                              double omega, double hydroepsilon, double Rd, f2d_stream_t stream) {
@@ -1191,8 +1287,6 @@ extern "C" int f2d_mg_create(f2d_mg_t **out, const double *cornermask, int ny, i
   int m = ny - 2 * NH, n = nx - 2 * NH;
   if (m < 4 || n < 4) return fail(F2D_ERR_ARG, "mg_create: grid too small");
   if ((m & (m - 1)) || (n & (n - 1))) return fail(F2D_ERR_ARG, "mg_create: nx, ny must be powers of two");
-  if (hydroepsilon * dy / dx <= 0.2)
-    return fail(F2D_ERR_ARG, "mg_create: small aspect ratio needs the tridiagonal relaxation (not built yet)");
   cudaStream_t s = S(stream);
   f2d_mg *mg = new f2d_mg();
   mg->omega = omega;
@@ -1222,6 +1316,8 @@ extern "C" int f2d_mg_create(f2d_mg_t **out, const double *cornermask, int ny, i
     if ((rc = f2d_fill_halo(A9 + k * l0.n(), NH, l0.ny, l0.nx, stream)) != F2D_OK) { cudaFree(A9); return bail(rc); }
   if ((rc = build_replicated(mg, A9, true, s)) != F2D_OK) return bail(rc);
   if ((rc = finish_setup(mg, Rd, s)) != F2D_OK) return bail(rc);
+  // level.py:153-163: flat cells take the line relaxation
+  if (hydroepsilon * dy / dx <= 0.2 && (rc = f2d_mg_set_relaxation(mg, 1)) != F2D_OK) return bail(rc);
   *out = mg;
   return F2D_OK;
 }
@@ -1313,6 +1409,33 @@ extern "C" int f2d_mg_level_matrix_mode(const f2d_mg_t *mg, int lev) {
 }
 /* number of distributed (slab) levels of a handle made by f2d_mg_create_slab */
 extern "C" int f2d_mg_slab_levels(const f2d_mg_t *mg) { return mg ? mg->lg : 0; }
+extern "C" int f2d_mg_set_relaxation(f2d_mg_t *mg, int mode) {
+  if (!mg || (mode != 0 && mode != 1)) return fail(F2D_ERR_ARG, "mg_set_relaxation: bad handle / mode");
+  if (mode == mg->relax) return F2D_OK;
+  if (mode == 1) {
+    if (mg->comm) return fail(F2D_ERR_ARG, "mg_set_relaxation: the line relaxation needs npy = 1 (level.py:155-157)");
+    size_t need = 0;
+    for (auto &l : mg->L) need = std::max(need, 4 * (size_t)l.ny * sizeof(double));
+    if (need > 200 * 1024) return fail(F2D_ERR_ARG, "mg_set_relaxation: columns longer than 6400 rows do not fit the line kernel");
+    if (need > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(k_smooth_tridiag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_smooth_tridiag)");
+    }
+    // the shared-memory tail kernels and the constant-stencil classes belong to the Jacobi
+    // path: every level goes through the per-operator kernels on the stored coefficients
+    mg->tail0 = -1;
+    mg->ctail = false;
+    for (auto &l : mg->L) l.mode = 0;
+  } else {
+    return fail(F2D_ERR_ARG, "mg_set_relaxation: a hierarchy switched to the line relaxation cannot be switched back");
+  }
+  mg->relax = mode;
+  for (auto &kv : mg->cache) cudaGraphExecDestroy(kv.second.exec);   // graphs captured the Jacobi kernels
+  mg->cache.clear();
+  for (auto &kv : mg->solve_cache) cudaGraphExecDestroy(kv.second.exec);
+  mg->solve_cache.clear();
+  return F2D_OK;
+}
 extern "C" int f2d_mg_set_graphs(f2d_mg_t *mg, int enable) {
   if (!mg) return fail(F2D_ERR_ARG, "mg_set_graphs: null");
   mg->graphs = enable != 0;
@@ -1368,7 +1491,9 @@ extern "C" int f2d_mg_solve(f2d_mg_t *mg, double *psi, const double *rhs, double
                             double *res_out, f2d_stream_t stream) {
   if (!mg || !psi || !rhs) return fail(F2D_ERR_ARG, "mg_solve: null");
   cudaStream_t s = S(stream);
-  if (mg->graphs && !(mg->comm && mg->lg == 0)) return solve_graph(mg, psi, rhs, tol, maxite, nite_out, res_out, s);
+  // (line relaxation: the host-driven loop below; its F-cycle is still one captured graph)
+  if (mg->graphs && !(mg->comm && mg->lg == 0) && mg->relax == 0)
+    return solve_graph(mg, psi, rhs, tol, maxite, nite_out, res_out, s);
   // host-driven loop (graphs disabled): same operations, one host round trip per F-cycle
   if (mg->comm) return slab_solve(mg, psi, rhs, tol, maxite, nite_out, res_out, s);
   Level &l = mg->L[0];

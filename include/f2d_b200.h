@@ -266,6 +266,13 @@ int f2d_mg_two_vcycle(f2d_mg_t *mg, double *psi, const double *rhs, f2d_stream_t
  * HOST outputs.  Returns F2D_ERR_DIVERGE where the reference would exit(0). */
 int f2d_mg_solve(f2d_mg_t *mg, double *psi, const double *rhs, double tol, int maxite,
                  int *nite, double *res, f2d_stream_t stream);
+/* relaxation of Grid.smooth (level.py:153-163, 340-349): 0 = two damped-Jacobi sweeps per
+ * application (smoothtwicewithA, the default), 1 = line relaxation -- THREE applications of
+ * smoothtridiag (fortran_multigrid.f90:215-317: per column a tridiagonal solve in y, columns
+ * swept west to east in place) + halo fill per requested iteration.  f2d_mg_create selects 1
+ * by itself when hydroepsilon*dy/dx <= 0.2; param.relaxation = 'tridiagonal' asks for it.
+ * Single-GPU hierarchies only (the reference also refuses it with npy > 1, level.py:155-157). */
+int f2d_mg_set_relaxation(f2d_mg_t *mg, int mode);
 /* use CUDA graphs for the cycles (default 1) */
 int f2d_mg_set_graphs(f2d_mg_t *mg, int enable);
 /* diagnostics: the cluster tail kernel appends one SM clock stamp per barrier of its rank-0

@@ -160,9 +160,12 @@ class MG(object):
     ndeepest = 16
     nvcyc = 1
 
-    def __init__(self, cornermask, n, m, dx, dy, omega=8./9., hydroepsilon=1., Rd=None):
+    def __init__(self, cornermask, n, m, dx, dy, omega=8./9., hydroepsilon=1., Rd=None, relaxation='default'):
         self.nh = NH
         self.omega = omega
+        # level.py:153-163: the line (tridiagonal) relaxation is taken when asked for
+        # (param.relaxation) or when the cells are flat (hydroepsilon*dy/dx <= 0.2)
+        self.relaxation = 'tridiagonal' if hydroepsilon*dy/dx <= .2 else relaxation
         self.sizes = level_sizes(n, m)
         self.nlevs = len(self.sizes)
         self.msk, self.A, self.x, self.b, self.r = [], [], [], [], []
@@ -217,6 +220,11 @@ class MG(object):
 
     # -- per-level operators (level.py:340-496) -----------------------------
     def smooth(self, lev, x, b, nite):
+        if self.relaxation == 'tridiagonal':     # level.py:340-349
+            for _ in range(3*nite):
+                fm.smoothtridiag(self.msk[lev], self.A[lev], x, b)
+                fm.fillhalo(x, self.nh)
+            return
         for _ in range(nite):
             fm.smoothtwicewitha(self.msk[lev], self.A[lev], x, b, self.omega)
             fm.fillhalo(x, self.nh)
@@ -314,7 +322,8 @@ class Ops(object):
         self.mskp = self.msk*0
         self.mskp[self.work == 1.] = 1
         self.gmg = MG(self.work, param.nx, param.ny, grid.dx, grid.dy,
-                      hydroepsilon=param.hydroepsilon, Rd=(param.Rd if qg else None))
+                      hydroepsilon=param.hydroepsilon, Rd=(param.Rd if qg else None),
+                      relaxation=getattr(param, 'relaxation', 'default'))
         self.fill_halo = grid.fill_halo
         # boundary mask of the no-slip source (operators.py:157-186)
         ns = grid.msknoslip

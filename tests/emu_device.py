@@ -368,6 +368,10 @@ class EmuLib(object):
         h._obj.value = key
         return 0
 
+    def mg_set_relaxation(self, h, mode):
+        self._h(h).mg.relaxation = 'tridiagonal' if mode else 'default'
+        return 0
+
     def mg_create_slab(self, *a):
         raise NotImplementedError("emulator: one rank")
 

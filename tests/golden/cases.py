@@ -205,6 +205,73 @@ def rb(api, datadir, nx=64, diag_fluxes=False):
     return f2d
 
 
+class SaltFingerFluxes:
+    """embedded forcing of experiments/doublediffusion/doublediffusion.py:70-112: constant
+    temperature / salinity fluxes through the bottom and top rows of the channel"""
+
+    def __init__(self, param, grid):
+        self.nh = grid.nh
+        dz = grid.dy
+        self.FluxT = param.Kdiff['T']*param.dTdz/dz
+        self.FluxS = param.Kdiff['S']*param.dSdz/dz
+
+    def add_forcing(self, x, t, dxdt, coef=1.):
+        dxdt[6][-self.nh-1, :] += self.FluxT
+        dxdt[7][-self.nh-1, :] += self.FluxS
+        dxdt[6][self.nh, :] -= self.FluxT
+        dxdt[7][self.nh, :] -= self.FluxS
+
+
+def dbldiff(api, datadir, nx=32, relaxation='default'):
+    """experiments/doublediffusion/doublediffusion.py: the BoussinesqTS model (temperature +
+    salinity, density diagnosed), tall channel, per-tracer diffusivities, flux forcing.  The
+    script asks for relaxation='tridiagonal' (the line smoother of the multigrid)."""
+    param = api.Param('default.xml')
+    param.modelname = 'boussinesqTS'
+    _common(param, 'dbldiff_%i' % nx, datadir)
+    param.nx = nx
+    param.ny = param.nx*2
+    param.Lx = 1.
+    param.Ly = param.Lx*2
+    param.geometry = 'xchannel'
+    param.cfl = 1.
+    param.adaptable_dt = True
+    param.dt = 0.01
+    param.dtmax = 1e-2
+    param.order = 5
+    param.relaxation = relaxation
+    param.var_to_save = ['vorticity', 'density', 'T', 'S', 'psi']
+    param.gravity = 1.
+    param.forcing = True
+    param.forcing_module = 'embedded'
+    param.diffusion = True
+    param.noslip = False
+    param.alphaT = 1.
+    param.betaS = 1.
+    grid = api.Grid(param)
+    K0 = 2e-2*grid.dx
+    param.Kdiff = {'vorticity': K0*7., 'T': K0, 'S': K0/50.}
+    param.dTdz = 50.
+    param.dSdz = 50.
+    f2d = api.Fluid2d(param, grid)
+    model = f2d.model
+    model.forc = SaltFingerFluxes(param, grid)
+    z = grid.yr0
+    temp = model.var.get('T')
+    salt = model.var.get('S')
+    vor = model.var.get('vorticity')
+    temp[:, :] = param.dTdz*z
+    salt[:, :] = param.dSdz*z
+    np.random.seed(42)
+    noise = np.random.normal(size=np.shape(grid.yr), scale=1.)*grid.msk
+    noise -= grid.domain_integration(noise)*grid.msk/grid.area
+    grid.fill_halo(noise)
+    vor[:, :] = 1e-2*noise
+    model.set_density()
+    model.set_psi_from_vorticity()
+    return f2d
+
+
 def karman(api, datadir, ny=32, ratio=2):
     param = api.Param('default.xml')
     param.modelname = 'euler'
@@ -259,10 +326,14 @@ def karman(api, datadir, ny=32, ratio=2):
     return f2d
 
 
-def qg(api, datadir, n=64, timestepping='LFAM3'):
+def qg(api, datadir, n=64, timestepping='LFAM3', diagnosed=False):
+    """diagnosed=True: with the bottom-torque and ageostrophic-velocity diagnostics
+    (quasigeostrophic.py:96-153; experiments/QGbasic/vortex_betaplane_v2.py)"""
     param = api.Param('default.xml')
     param.modelname = 'quasigeostrophic'
     _common(param, 'qg_%i' % n, datadir)
+    param.bottom_torque = diagnosed
+    param.ageostrophic = diagnosed
     param.nx = n
     param.ny = n
     param.geometry = 'closed'
@@ -302,7 +373,15 @@ CASES = {
     # core/fluxes.py at the initial state (flx0) and after the ten steps (flx10)
     'freedecay_32_flx': lambda api, d: freedecay(api, d, 32, diag_fluxes=True),
     'rb_32_flx': lambda api, d: rb(api, d, 32, diag_fluxes=True),
+    # BoussinesqTS (temperature + salinity), damped-Jacobi and line (tridiagonal) relaxation
+    'dbldiff_32': lambda api, d: dbldiff(api, d, 32),
+    'dbldiff_32_tridiag': lambda api, d: dbldiff(api, d, 32, relaxation='tridiagonal'),
+    'qg_32_diagnosed': lambda api, d: qg(api, d, 32, timestepping='RK3_SSP', diagnosed=True),
 }
+# cases added after the last GPU session of round 1: their GPU parity test sits in
+# tests/test_gpu_zz_late.py so that it runs after every test that has already been green on a
+# B200 (the host layer is pinned on the CPU by tests/test_host_emulated.py)
+LATE = {'dbldiff_32', 'dbldiff_32_tridiag', 'qg_32_diagnosed'}
 # every other stepper of core/timescheme.py:78-201, with diffusion on so that the
 # `kstage == kforcing` branch of Euler.dynamics is exercised (light fixtures: states only)
 SCHEMES = ['EF', 'LF', 'Heun', 'AB2', 'AB3', 'LFAM3', 'RK4_LS']   # ('RK3' is not in param.py's list)

@@ -43,7 +43,7 @@ def check_fluxes(f2d, gold, key, tol, report):
         assert e <= tol, "%s %s: rel L2 %.3e > %.0e" % (key, nm, e, tol)
 
 
-@pytest.mark.parametrize("name", sorted(cases.CASES))
+@pytest.mark.parametrize("name", sorted(set(cases.CASES)-cases.LATE))
 def test_case_matches_reference_run(name):
     import fluid2d_b200
     api = fluid2d_b200.api()

@@ -9,6 +9,7 @@ step plus the end-of-step full solve, diagnostics -- on the freedecay initial st
 diagnostics.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--n 4096] [--tracers 1]
+    python bench.py --strong --n 16384 --gpus N --no-cpu     # SURVEY.md 8d case S5 (not the driver's line)
     python bench.py --impl reference ...     # the CPU arm (oracle port on the host cores)
 
 One JSON line on stdout (rank 0); everything else goes to stderr.
@@ -125,12 +126,18 @@ class ClockSampler(object):
                 "reasons": sorted(reasons)}
 
 
-def build_case(api, n, tracers, datadir, world=1):
+def build_case(api, n, tracers, datadir, world=1, strong=False):
     """world > 1: weak scaling -- the global domain is n x (n*world), split in `world`
     y-slabs of n x n cells (npx = 1, npy = world); the n x n freedecay field is repeated in
     every slab (periodic tiling), so each GPU carries the single-GPU workload plus the halo
-    exchange with its neighbours"""
+    exchange with its neighbours.
+    strong=True (--strong, SURVEY.md 8d case S5): the global domain is n x n whatever the
+    number of GPUs, split in `world` y-slabs of n/world rows; the field is a 4096^2 freedecay
+    tile repeated over the domain"""
     import cases
+    if strong:
+        return cases.freedecay(api, datadir, n, order=5, tracer=(tracers > 1), ny=n, npy=world,
+                               tile=min(n, 4096))
     if world == 1:
         return cases.freedecay(api, datadir, n, order=5, tracer=(tracers > 1))
     return cases.freedecay(api, datadir, n, order=5, tracer=(tracers > 1), ny=n*world, npy=world, tile=True)
@@ -233,7 +240,12 @@ def gpu_main(args):
     n, T = args.n, args.tracers
     t0 = time.time()
     slabs = world > 1 and not args.replicas
-    f2d = build_case(api, n, T, tempfile.mkdtemp(), world if slabs else 1)
+    strong = bool(args.strong)
+    if strong and (args.replicas or n % world):
+        raise SystemExit("--strong: n must be a multiple of the number of GPUs (and no --replicas)")
+    rows = n//world if strong else n          # rows of this rank's slab
+    total_cells = n*n if strong else world*n*n
+    f2d = build_case(api, n, T, tempfile.mkdtemp(), world if slabs else 1, strong)
     model = f2d.model
     model.diagnostics(model.var, 0.)
     torch.cuda.synchronize()
@@ -269,23 +281,23 @@ def gpu_main(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms = float(tmax.item())
     ms_step = ms/args.steps
-    value = world*n*n*args.steps/(ms*1e-3)
+    value = total_cells*args.steps/(ms*1e-3)
     n_F = float(np.mean(nites))
 
     # ---- dominant kernel: the level-0 double Jacobi sweep (Grid.smooth), timed alone
     peak, peak_src = measured_peaks()
     if slabs:
         # kernel-level numbers come from a single-GPU hierarchy of the slab's size on this rank
-        cm = torch.ones((n+6, n+6), dtype=torch.float64, device="cuda")
+        cm = torch.ones((rows+6, n+6), dtype=torch.float64, device="cuda")
         cm[-1, :] = 0
         cm[:, -1] = 0
         import ctypes
         mgh = ctypes.c_void_p()
-        lib.mg_create(ctypes.byref(mgh), r.ptr(cm), n+6, n+6, 1./n, 1./n, 8./9., 1., 0., r.stream)
+        lib.mg_create(ctypes.byref(mgh), r.ptr(cm), rows+6, n+6, 1./n, 1./n, 8./9., 1., 0., r.stream)
     else:
         mgh = model.ope.gmg.h
-    x0 = torch.zeros((n+6, n+6), dtype=torch.float64, device="cuda")
-    b0 = torch.randn((n+6, n+6), dtype=torch.float64, device="cuda")
+    x0 = torch.zeros((rows+6, n+6), dtype=torch.float64, device="cuda")
+    b0 = torch.randn((rows+6, n+6), dtype=torch.float64, device="cuda")
     reps = 10
     for _ in range(3):
         lib.mg_smooth(mgh, 0, r.ptr(x0), r.ptr(b0), 2, r.stream)
@@ -297,7 +309,7 @@ def gpu_main(args):
     s1.record()
     torch.cuda.synchronize()
     smooth_ms = s0.elapsed_time(s1)/(2*reps)
-    achieved = SMOOTH_BYTES_PER_CELL*n*n/(smooth_ms*1e-3)/1e9
+    achieved = SMOOTH_BYTES_PER_CELL*rows*n/(smooth_ms*1e-3)/1e9
     # ---- V-cycle (metric part 2): one Vcycle(0) through its CUDA graph
     lib.mg_vcycle(mgh, 0, r.stream)
     torch.cuda.synchronize()
@@ -331,7 +343,7 @@ def gpu_main(args):
         tmax = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_ms = float(tmax.item())
-    e2e = {"value": world*n*n*ke/(e2e_ms*1e-3), "unit": "cell-updates/s",
+    e2e = {"value": total_cells*ke/(e2e_ms*1e-3), "unit": "cell-updates/s",
            "h2d_bytes_per_step": (ds.h2d_bytes-h2d0)//ke, "d2h_bytes_per_step": (ds.d2h_bytes-d2h0)//ke,
            "ms_per_step": e2e_ms/ke, "steps": ke}
 
@@ -345,7 +357,7 @@ def gpu_main(args):
     if rank != 0:
         return
     cpu = None
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and not strong:
         try:
             cpu = cpu_arm(n, T, 2, 1)
         except Exception as ex:   # the baseline is a report, never a reason to lose the GPU line
@@ -354,28 +366,28 @@ def gpu_main(args):
     line = {
         "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Euler freedecay %dx%d perio per GPU (experiments/Twodim_turbulence), RK3_SSP, "
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Euler freedecay %dx%d perio %s (experiments/Twodim_turbulence), RK3_SSP, "
                                "upwind5 + parabolic splitting, 2 truncated MG inversions + full solve per step, "
-                               "T=%d advected tracer(s)" % (n, n, T),
+                               "T=%d advected tracer(s)" % (n, n, "in total" if strong else "per GPU", T),
                    "grid": [n, n], "tracers": T, "n_F_mean": n_F,
                    "parallelism": "single GPU" if world == 1 else (
                        "%d y-slabs of %dx%d (global %dx%d), peer halo exchange over NVLink, coarse levels gathered"
-                       % (world, n, n, n, n*world) if slabs else "%d independent replicas" % world),
+                       % (world, n, rows, n, rows*world) if slabs else "%d independent replicas" % world),
                    "mg_slab_levels": getattr(model.ope.gmg, "slab_levels", 0),
-                   "cache": "working set %.1f GB >> 126 MB L2 (no flush needed)" % (40*(n+6)**2*8/1e9)},
+                   "cache": "working set %.1f GB >> 126 MB L2 (no flush needed)" % (40*(n+6)*(rows+6)*8/1e9)},
         "roofline": {"bound": "hbm", "kernel": "k_smooth2<0,0,0> (Grid.smooth = double Jacobi sweep + halo fill, level 0)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 4096^2, from
                      # profiles/r01_ncu_full_v10_two_vcycle_kernels.csv (269.1 MB + 104.2 MB; algorithmic
                      # 420 MB: the mask-free level reads x and b, writes x; halo re-reads hit L2)
-                     "traffic": 3.733e8 if n == 4096 else None,
+                     "traffic": 3.733e8 if (n == 4096 and rows == 4096) else None,
                      "peak_source": peak_src, "ms_per_launch": smooth_ms,
                      "algorithmic_bytes_per_cell": SMOOTH_BYTES_PER_CELL},
         "step_hbm": {"b_alg_bytes_per_cell": balg, "achieved_gbs": balg*value/world/1e9,
                      "frac_of_peak": balg*value/world/1e9/peak},
         "vcycle_ms": vcycle_ms,
-        "vcycle_frac_of_peak": VCYCLE_BYTES_PER_CELL*n*n/(vcycle_ms*1e-3)/1e9/peak,
+        "vcycle_frac_of_peak": VCYCLE_BYTES_PER_CELL*rows*n/(vcycle_ms*1e-3)/1e9/peak,
         "cpu_baseline": cpu,
         "e2e": e2e,
         "gpu_launches": launches,
@@ -394,6 +406,8 @@ def main():
     ap.add_argument("--tracers", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--replicas", action="store_true", help="N>1: independent replicas instead of slabs")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: --n is the GLOBAL grid (e.g. 16384), split in --gpus y-slabs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -35,7 +35,8 @@ def freedecay(api, datadir, n=64, order=5, tracer=True, timestepping='RK3_SSP', 
               diag_fluxes=False):
     """ny != n gives a rectangular domain with dx = dy; npy > 1 splits it in y-slabs (one
     rank per slab, like the reference run under mpirun with npx=1, npy=nranks); tile=True
-    (needs ny = n*npy) repeats the n x n field in every slab instead of drawing a global one"""
+    (needs ny = n*npy) repeats the n x n field in every slab instead of drawing a global one;
+    tile=T (int) tiles a T x T field over the whole domain"""
     param = api.Param('default.xml')
     param.modelname = 'euler'
     _common(param, 'freedecay_%i' % n, datadir)
@@ -70,19 +71,28 @@ def freedecay(api, datadir, n=64, order=5, tracer=True, timestepping='RK3_SSP', 
         k = ((n//2+np.arange(n)) % n) - n//2
         return 2*np.pi*k/L
 
-    fny = param.nx if tile else param.ny
-    kkx, kky = np.meshgrid(wavenumbers(param.nx, np.pi), wavenumbers(fny, np.pi))
+    # tile = True: the nx x nx field repeated in every slab; tile = T (an int): a T x T field
+    # repeated periodically over the whole domain in both directions (large strong-scaling
+    # grids: nobody has to hold a global 16384^2 complex spectrum on the host)
+    both = not isinstance(tile, bool)
+    fnx = int(tile) if both else param.nx
+    fny = int(tile) if both else (param.nx if tile else param.ny)
+    kkx, kky = np.meshgrid(wavenumbers(fnx, np.pi), wavenumbers(fny, np.pi))
     kk = np.sqrt(kkx**2 + kky**2)
-    k0 = param.nx*0.48
+    k0 = fnx*0.48
     dk = 1
-    phase = np.random.normal(size=(fny, param.nx))*2*np.pi
+    phase = np.random.normal(size=(fny, fnx))*2*np.pi
     hnoise = np.exp(-(kk-k0)**2/(2*dk))*np.exp(1j*phase)
     noise = np.zeros_like(vor)
     nh = grid.nh
     field = 1e3*np.real(np.fft.ifft2(hnoise))     # the global field, identical on every rank
     rows = param.ny//param.npy
-    j0 = 0 if tile else grid.j0
-    noise[nh:-nh, nh:-nh] = field[j0*rows:(j0+1)*rows, :]
+    if both:
+        jj = (grid.j0*rows+np.arange(rows)) % fny
+        noise[nh:-nh, nh:-nh] = field[jj][:, np.arange(param.nx) % fnx]
+    else:
+        j0 = 0 if tile else grid.j0
+        noise[nh:-nh, nh:-nh] = field[j0*rows:(j0+1)*rows, :]
     grid.fill_halo(noise)
     vor[:] = noise
     if tracer:

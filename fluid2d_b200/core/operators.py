@@ -73,6 +73,10 @@ class Operators(Param):
             for g in self.gmg.grid:
                 print('Level %2i: %5ix%5i' % (g.lev, g.n, g.m))
 
+        if hasattr(self, 'sqgoperator'):
+            from fourier import Fourier
+            self.fourier = Fourier(param, grid, r.device)
+
         grid.fill_halo = self.fill_halo
         self.set_boundary_msk()
 
@@ -247,6 +251,21 @@ class Operators(Param):
             self._d_rhsp = self.rt.to_device(self.rhsp, dtype=np.float64)
             self._d_psi_island = self.rt.to_device(self.psi, dtype=np.float64)
         return self.rt.ptr(self._d_rhsp), self.rt.ptr(self._d_psi_island)
+
+    def fourier_invert_vorticity(self, x, flag='full'):
+        """SQG: psi (and the diagnosed vorticity) from the surface pv by a spectral inversion
+        (cuFFT, fourier.py), then (u, v) from psi (operators.py:396-419)"""
+        r, lib = self.rt, self.lib
+        iu, iv, ip, ivor, ipv = self.ix('u'), self.ix('v'), self.ix('psi'), self.ix('vorticity'), self.ix('pv')
+        ny, nx = self.nyl, self.nxl
+        x.rptr(ipv)                       # host edits of pv reach the device first
+        ppsi, pvor = x.wptr(ip), x.wptr(ivor)
+        self.fourier.invert(x.dev[ipv], x.dev[ip], x.dev[ivor])
+        lib.fill_halo(ppsi, self.nh, ny, nx, r.stream)
+        lib.fill_halo(pvor, self.nh, ny, nx, r.stream)
+        self.first_time = False
+        lib.orthogradient(r.ptr(self.d_msk), ppsi, self.dx, self.dy, self.nh, x.wptr(iu), x.wptr(iv),
+                          ny, nx, r.stream)
 
     def invert_vorticity(self, x, flag='full', island=False):
         """psi from x[whosetspsi] by multigrid, then (u, v) from psi (operators.py:421-498).

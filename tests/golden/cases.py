@@ -371,6 +371,41 @@ def qg(api, datadir, n=64, timestepping='LFAM3', diagnosed=False):
     return f2d
 
 
+def sqg(api, datadir, n=32):
+    """experiments/SQG/vortex.py: surface QG, two co-rotating gaussian vortices, spectral
+    inversion (the reference uses numpy.fft, the product cuFFT: agreement to FFT rounding)"""
+    param = api.Param('default.xml')
+    param.modelname = 'sqg'
+    _common(param, 'sqg_%i' % n, datadir)
+    param.nx = n
+    param.ny = n
+    param.geometry = 'perio'
+    param.cfl = 0.8
+    param.adaptable_dt = True
+    param.dt = 1.
+    param.dtmax = 100.
+    param.order = 5
+    param.ageostrophic = False
+    param.var_to_save = ['pv', 'psi', 'u', 'v', 'vorticity']
+    param.beta = 0.
+    param.Rd = 10.
+    param.forcing = False
+    param.noslip = False
+    param.diffusion = False
+    grid = api.Grid(param)
+    f2d = api.Fluid2d(param, grid)
+    model = f2d.model
+    xr, yr = grid.xr, grid.yr
+    pv = model.var.get('pv')
+    sigma = 0.1*param.Lx
+    d = 3*sigma/param.Lx
+    for y0 in (0.5-d/2, 0.5+d/2):
+        r2 = (xr-param.Lx*0.5)**2+(yr-param.Ly*y0)**2
+        pv[:] += -.5*np.exp(-r2/(sigma**2))
+    model.set_psi_from_pv()
+    return f2d
+
+
 CASES = {
     'freedecay_64': lambda api, d: freedecay(api, d, 64),
     'freedecay_32_o3_notracer': lambda api, d: freedecay(api, d, 32, order=3, tracer=False),
@@ -387,11 +422,14 @@ CASES = {
     'dbldiff_32': lambda api, d: dbldiff(api, d, 32),
     'dbldiff_32_tridiag': lambda api, d: dbldiff(api, d, 32, relaxation='tridiagonal'),
     'qg_32_diagnosed': lambda api, d: qg(api, d, 32, timestepping='RK3_SSP', diagnosed=True),
+    'sqg_32': lambda api, d: sqg(api, d, 32),
 }
+# cases whose inversion is an FFT: another FFT library agrees to rounding, not bit for bit
+SPECTRAL = {'sqg_32'}
 # cases added after the last GPU session of round 1: their GPU parity test sits in
 # tests/test_gpu_zz_late.py so that it runs after every test that has already been green on a
 # B200 (the host layer is pinned on the CPU by tests/test_host_emulated.py)
-LATE = {'dbldiff_32', 'dbldiff_32_tridiag', 'qg_32_diagnosed'}
+LATE = {'dbldiff_32', 'dbldiff_32_tridiag', 'qg_32_diagnosed', 'sqg_32'}
 # every other stepper of core/timescheme.py:78-201, with diffusion on so that the
 # `kstage == kforcing` branch of Euler.dynamics is exercised (light fixtures: states only)
 SCHEMES = ['EF', 'LF', 'Heun', 'AB2', 'AB3', 'LFAM3', 'RK4_LS']   # ('RK3' is not in param.py's list)

@@ -24,8 +24,9 @@ from output import Output
 # on the device path
 MODELS = {'euler': ('euler', 'Euler'), 'advection': ('advection', 'Advection'),
           'boussinesq': ('boussinesq', 'Boussinesq'), 'quasigeostrophic': ('quasigeostrophic', 'QG'),
-          'boussinesqTS': ('boussinesqTS', 'BoussinesqTS'), 'sqg': ('sqg', 'SQG')}
-NOT_ON_DEVICE = ('thermalwind',)
+          'boussinesqTS': ('boussinesqTS', 'BoussinesqTS'), 'sqg': ('sqg', 'SQG'),
+          'thermalwind': ('thermalwind', 'Thermalwind')}
+NOT_ON_DEVICE = ()
 PV_MODELS = ('quasigeostrophic', 'sqg')
 
 FROM_PARAM = ('modelname', 'tend', 'dt', 'adaptable_dt', 'cfl', 'dtmax', 'exacthistime', 'rescaledtime',

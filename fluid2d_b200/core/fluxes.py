@@ -36,8 +36,9 @@ class Fluxes(object):
         self.fullflx_list = ['%s_%s_%s' % (r, d, v) for r in ['rev', 'irr']
                              for v in p.tracer_list for d in ['x', 'y']]
         p.copy(self, self.list_param)
-        if self.modelname not in ('euler', 'boussinesq'):
-            raise NotImplementedError('diag_fluxes: model %s (euler and boussinesq only)' % self.modelname)
+        if self.modelname not in ('euler', 'boussinesq', 'thermalwind'):
+            raise NotImplementedError('diag_fluxes: model %s (the reference does euler, boussinesq and '
+                                      'thermalwind, fluxes.py:9-13)' % self.modelname)
         self.list_grid = ['nh', 'dx', 'dy', 'msk']
         grid.copy(self, self.list_grid)
         self.ope = ope
@@ -116,6 +117,8 @@ class Fluxes(object):
         self.rhs_adv(x, t, dxdt)
         if self.modelname == 'boussinesq':
             self.ope.rhs_torque(x, t, dxdt)
+        elif self.modelname == 'thermalwind':
+            self.ope.rhs_thermalwind(x, t, dxdt)
         self.ope.invert_vorticity(dxdt, flag='fast')
 
     def rhs_adv(self, x, t, dxdt):

@@ -216,6 +216,23 @@ class Operators(Param):
                        self.nyl, self.nxl, 0, self.fillmode, r.stream)
         self._xch(dxdt.wptr(iw))
 
+    def rhs_thermalwind(self, x, t, dxdt):
+        """thermal-wind model: g*db/dx - f0*dV/dz on the vorticity, -f0*u on V
+        (operators.py:357-394).  diffx / diffz first extrapolate the first halo line of b
+        and V linearly IN PLACE (operators.py:330-352): the stage state keeps those values."""
+        r, lib = self.rt, self.lib
+        nh, ny, nx, n = self.nh, self.nyl, self.nxl, self.ncell
+        iu, ib, iw, iV = self.ix('u'), self.ix('buoyancy'), self.ix('vorticity'), self.ix('V')
+        msk, y = r.ptr(self.d_msk), r.ptr(self.work)
+        lib.extrapolate_bry(x.wptr(ib), nh, ny, nx, 0, r.stream)
+        lib.extrapolate_bry(x.wptr(iV), nh, ny, nx, 1, r.stream)
+        lib.tw_torque(msk, x.rptr(ib), x.rptr(iV), self.dx, self.dy, self.gravity, self.f0, y, ny, nx, r.stream)
+        lib.fill_halo(y, nh, ny, nx, r.stream)
+        lib.add_scaled(dxdt.wptr(iw), 1., y, n, r.stream)
+        lib.tw_coriolis(msk, x.rptr(iu), self.f0, y, ny, nx, r.stream)
+        lib.fill_halo(y, nh, ny, nx, r.stream)
+        lib.add_scaled(dxdt.wptr(iV), 1., y, n, r.stream)
+
     def rhs_noslip(self, x, source):
         """vorticity source along the walls that cancels the tangential velocity
         (operators.py:245-290); `source` is (DeviceState, field index) or a device tensor"""

@@ -643,3 +643,104 @@ extern "C" int f2d_sub_devscalar_mask(double *y, const double *dev_scalar, doubl
     y[k] = add_rn(y[k], -mul_rn(__ddiv_rn(dev_scalar[0], denom), (double)a[k]));
   });
 }
+
+// ---------------------------------------------------------------------------
+// thermal-wind model (core/thermalwind.py, operators.py:330-394): centred differences with
+// the reference's in-place linear extrapolation of the first halo line, the two right-hand-
+// side terms and the Jacobian of the Ertel PV.  numpy rounding sequence (no FMA).
+// ---------------------------------------------------------------------------
+// operators.py:332-335 (axis 0: diffx / diff1x) and :348-351 (axis 1: diffz):
+//   x[:, -nh] = 2*x[:, -nh-1] - x[:, -nh-2];  x[:, nh-1] = 2*x[:, nh] - x[:, nh+1]
+__global__ void k_extrapolate_bry(double *__restrict__ x, int nh, int ny, int nx, int axis) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (axis == 0) {
+    if (p >= ny) return;
+    double *r = x + (size_t)p * nx;
+    r[nx - nh] = add_rn(mul_rn(2., r[nx - nh - 1]), -r[nx - nh - 2]);
+    r[nh - 1] = add_rn(mul_rn(2., r[nh]), -r[nh + 1]);
+  } else {
+    if (p >= nx) return;
+    x[(size_t)(ny - nh) * nx + p] = add_rn(mul_rn(2., x[(size_t)(ny - nh - 1) * nx + p]), -x[(size_t)(ny - nh - 2) * nx + p]);
+    x[(size_t)(nh - 1) * nx + p] = add_rn(mul_rn(2., x[(size_t)nh * nx + p]), -x[(size_t)(nh + 1) * nx + p]);
+  }
+}
+extern "C" int f2d_extrapolate_bry(double *x, int nh, int ny, int nx, int axis, f2d_stream_t s) {
+  if (!x || nh < 1 || ny < 2 * nh + 2 || nx < 2 * nh + 2 || (axis != 0 && axis != 1))
+    return fail(F2D_ERR_ARG, "extrapolate_bry: bad args");
+  int n = axis == 0 ? ny : nx;
+  k_extrapolate_bry<<<cdiv(n, 128), 128, 0, S(s)>>>(x, nh, ny, nx, axis);
+  F2D_LAUNCHED();
+  return F2D_OK;
+}
+__device__ __forceinline__ double tw_diffx(const double *__restrict__ a, size_t c, double dx) {
+  return __ddiv_rn(mul_rn(0.5, add_rn(a[c + 1], -a[c - 1])), dx);
+}
+__device__ __forceinline__ double tw_diffz(const double *__restrict__ a, size_t c, int nx, double dy) {
+  return __ddiv_rn(mul_rn(0.5, add_rn(a[c + nx], -a[c - nx])), dy);
+}
+// operators.py:374-382: y[1:-1,1:-1] = diffx(b)*gravity - diffz(V)*f0 ; y *= msk
+// (the outer ring of y is left to the halo fill that follows)
+__global__ void k_tw_torque(const int8_t *__restrict__ msk, const double *__restrict__ b, const double *__restrict__ V,
+                            double dx, double dy, double gravity, double f0, double *__restrict__ y, int ny, int nx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (i >= nx - 1 || j >= ny - 1) return;
+  size_t c = (size_t)j * nx + i;
+  double t = mul_rn(tw_diffx(b, c, dx), gravity);
+  t = add_rn(t, -mul_rn(tw_diffz(V, c, nx, dy), f0));
+  y[c] = mul_rn(t, (double)msk[c]);
+}
+extern "C" int f2d_tw_torque(const int8_t *msk, const double *b, const double *V, double dx, double dy,
+                             double gravity, double f0, double *y, int ny, int nx, f2d_stream_t s) {
+  if (!msk || !b || !V || !y || ny < 3 || nx < 3) return fail(F2D_ERR_ARG, "tw_torque: bad args");
+  dim3 blk(32, 8), grd(cdiv(nx - 2, 32), cdiv(ny - 2, 8));
+  k_tw_torque<<<grd, blk, 0, S(s)>>>(msk, b, V, dx, dy, gravity, f0, y, ny, nx);
+  F2D_LAUNCHED();
+  return F2D_OK;
+}
+// operators.py:389-391: y[:, 1:] = -0.5*f0*(u[:, :-1] + u[:, 1:]) ; y *= msk
+__global__ void k_tw_coriolis(const int8_t *__restrict__ msk, const double *__restrict__ u, double f0,
+                              double *__restrict__ y, int ny, int nx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= nx || j >= ny) return;
+  size_t c = (size_t)j * nx + i;
+  double t = mul_rn(mul_rn(-0.5, f0), add_rn(u[c - 1], u[c]));
+  y[c] = mul_rn(t, (double)msk[c]);
+}
+extern "C" int f2d_tw_coriolis(const int8_t *msk, const double *u, double f0, double *y, int ny, int nx,
+                               f2d_stream_t s) {
+  if (!msk || !u || !y || ny < 1 || nx < 2) return fail(F2D_ERR_ARG, "tw_coriolis: bad args");
+  dim3 blk(32, 8), grd(cdiv(nx - 1, 32), cdiv(ny, 8));
+  k_tw_coriolis<<<grd, blk, 0, S(s)>>>(msk, u, f0, y, ny, nx);
+  F2D_LAUNCHED();
+  return F2D_OK;
+}
+// operators.py:354-355 + thermalwind.py:92-95: out = 0 ; out[1:-1,1:-1] =
+// diffx(x)*diffz(y) - diffz(x)*diffx(y) ; out *= msk   (the boundary lines of x and y must
+// have been extrapolated by f2d_extrapolate_bry, as diffx / diffz do in place)
+__global__ void k_jacobian(const int8_t *__restrict__ msk, const double *__restrict__ x, const double *__restrict__ y,
+                           double dx, double dy, double *__restrict__ out, int ny, int nx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= nx || j >= ny) return;
+  size_t c = (size_t)j * nx + i;
+  double t = 0.;
+  if (i >= 1 && i < nx - 1 && j >= 1 && j < ny - 1) {
+    t = add_rn(mul_rn(tw_diffx(x, c, dx), tw_diffz(y, c, nx, dy)), -mul_rn(tw_diffz(x, c, nx, dy), tw_diffx(y, c, dx)));
+  }
+  out[c] = mul_rn(t, (double)msk[c]);
+}
+extern "C" int f2d_jacobian(const int8_t *msk, const double *x, const double *y, double dx, double dy, double *out,
+                            int ny, int nx, f2d_stream_t s) {
+  if (!msk || !x || !y || !out || ny < 3 || nx < 3) return fail(F2D_ERR_ARG, "jacobian: bad args");
+  dim3 blk(32, 8), grd(cdiv(nx, 32), cdiv(ny, 8));
+  k_jacobian<<<grd, blk, 0, S(s)>>>(msk, x, y, dx, dy, out, ny, nx);
+  F2D_LAUNCHED();
+  return F2D_OK;
+}
+// thermalwind.py:136-137: qEneg = qE.copy(); qEneg[qE > 0] = 0
+extern "C" int f2d_negative_part(double *out, const double *x, size_t n, f2d_stream_t s) {
+  if (!out || !x) return fail(F2D_ERR_ARG, "negative_part: null");
+  return elementwise(n, S(s), [=] __device__(size_t k) { out[k] = x[k] > 0. ? 0. : x[k]; });
+}

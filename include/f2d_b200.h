@@ -207,6 +207,26 @@ int f2d_sub_devscalar(double *y, const double *dev_scalar, double denom, size_t 
 int f2d_sub_devscalar_mask(double *y, const double *dev_scalar, double denom,
                            const int8_t *a, size_t n, f2d_stream_t stream);
 
+/* ---- thermal-wind model (core/thermalwind.py; operators.py:330-394).  numpy's rounding
+ * sequence, no FMA.
+ * :332-335 / :348-351 the in-place linear extrapolation diffx / diffz apply to the first halo
+ * line on both sides before differencing: axis 0 -> x[:, -nh] = 2x[:, -nh-1] - x[:, -nh-2],
+ * x[:, nh-1] = 2x[:, nh] - x[:, nh+1]; axis 1 -> the same on rows */
+int f2d_extrapolate_bry(double *x, int nh, int ny, int nx, int axis, f2d_stream_t stream);
+/* :374-382 y[1:-1,1:-1] = diffx(b)*gravity - diffz(V)*f0; y *= msk (b, V already
+ * extrapolated; the halo fill of :383 is the caller's f2d_fill_halo) */
+int f2d_tw_torque(const int8_t *msk, const double *b, const double *V, double dx, double dy,
+                  double gravity, double f0, double *y, int ny, int nx, f2d_stream_t stream);
+/* :389-391 y[:, 1:] = -0.5*f0*(u[:, :-1] + u[:, 1:]); y *= msk */
+int f2d_tw_coriolis(const int8_t *msk, const double *u, double f0, double *y, int ny, int nx,
+                    f2d_stream_t stream);
+/* :354-355 + thermalwind.py:92-95  out = 0; out[1:-1,1:-1] = diffx(x)*diffz(y) -
+ * diffz(x)*diffx(y); out *= msk  (x, y already extrapolated) */
+int f2d_jacobian(const int8_t *msk, const double *x, const double *y, double dx, double dy,
+                 double *out, int ny, int nx, f2d_stream_t stream);
+/* thermalwind.py:136-137  out = x where x <= 0, else 0 */
+int f2d_negative_part(double *out, const double *x, size_t n, f2d_stream_t stream);
+
 /* ---- core/fluxes.py (diag_fluxes: reversible / irreversible advective fluxes)
  * :120-127 uc = 0.5*(u + roll(u,1,axis=1)), vc = 0.5*(v + roll(v,1,axis=0)) + fill_halo */
 int f2d_flx_cellvel(const double *u, const double *v, double *uc, double *vc, int nh, int ny,

@@ -335,6 +335,50 @@ class EmuLib(object):
         Y -= (f64(dev_scalar, 1)[0]/denom)*i8(a, n)
         return 0
 
+    # ---- thermal-wind model: the numpy expressions of operators.py:330-394
+    def extrapolate_bry(self, x, nh, ny, nx, axis, stream):
+        X = f64(x, ny, nx)
+        if axis == 0:
+            X[:, -nh] = 2*X[:, -nh-1]-X[:, -nh-2]
+            X[:, nh-1] = 2*X[:, nh]-X[:, nh+1]
+        else:
+            X[-nh, :] = 2*X[-nh-1, :]-X[-nh-2, :]
+            X[nh-1, :] = 2*X[nh, :]-X[nh+1, :]
+        return 0
+
+    @staticmethod
+    def _diffx(a, dx):
+        return 0.5*(a[1:-1, 2:]-a[1:-1, :-2])/dx
+
+    @staticmethod
+    def _diffz(a, dy):
+        return 0.5*(a[2:, 1:-1]-a[:-2, 1:-1])/dy
+
+    def tw_torque(self, msk, b, V, dx, dy, gravity, f0, y, ny, nx, stream):
+        Y = f64(y, ny, nx)
+        Y[1:-1, 1:-1] = self._diffx(f64(b, ny, nx), dx)*gravity
+        Y[1:-1, 1:-1] -= self._diffz(f64(V, ny, nx), dy)*f0
+        Y *= i8(msk, ny, nx)
+        return 0
+
+    def tw_coriolis(self, msk, u, f0, y, ny, nx, stream):
+        Y, U = f64(y, ny, nx), f64(u, ny, nx)
+        Y[:, 1:] = - 0.5*f0*(U[:, :-1]+U[:, 1:])
+        Y *= i8(msk, ny, nx)
+        return 0
+
+    def jacobian(self, msk, x, y, dx, dy, out, ny, nx, stream):
+        X, Y, O = f64(x, ny, nx), f64(y, ny, nx), f64(out, ny, nx)
+        O[:, :] = 0.
+        O[1:-1, 1:-1] = self._diffx(X, dx)*self._diffz(Y, dy)-self._diffz(X, dy)*self._diffx(Y, dx)
+        O *= i8(msk, ny, nx)
+        return 0
+
+    def negative_part(self, out, x, n, stream):
+        X = f64(x, n)
+        f64(out, n)[:] = np.where(X > 0, 0., X)
+        return 0
+
     # ---- fluxes driver, output
     def flx_cellvel(self, u, v, uc, vc, nh, ny, nx, fill, stream):
         U, V, UC, VC = f64(u, ny, nx), f64(v, ny, nx), f64(uc, ny, nx), f64(vc, ny, nx)

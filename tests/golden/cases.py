@@ -406,6 +406,63 @@ def sqg(api, datadir, n=32):
     return f2d
 
 
+def symmetric_instab(api, datadir, ny=32):
+    """experiments/SymmetricInstability/symmetric_instab.py: the thermal-wind model (vorticity,
+    buoyancy, along-front velocity V, diagnosed Ertel PV), closed basin, order 3, with
+    diag_fluxes (the script's 'symmetric' configuration)"""
+    param = api.Param('default.xml')
+    param.modelname = 'thermalwind'
+    _common(param, 'si_%i' % ny, datadir)
+    ratio = 2
+    param.ny = ny
+    param.nx = param.ny*ratio
+    param.Ly = 1.
+    param.Lx = param.Ly*ratio
+    param.geometry = 'closed'
+    param.cfl = 1.0
+    param.adaptable_dt = True
+    param.dt = .1
+    param.dtmax = 2.
+    param.order = 3
+    param.timestepping = 'RK3_SSP'
+    param.var_to_save = ['vorticity', 'psi', 'V', 'buoyancy', 'qE', 'tracer']
+    param.diag_fluxes = True
+    param.forcing = False
+    param.noslip = False
+    param.diffusion = False
+    param.gravity = 1.
+    param.f0 = 0.1
+    param.additional_tracer = ['tracer']
+    grid = api.Grid(param)
+    param.Kdiff = 5e-1*grid.dx**2
+    f2d = api.Fluid2d(param, grid)
+    model = f2d.model
+    yr = grid.yr
+    vor = model.var.get('vorticity')
+    buoy = model.var.get('buoyancy')
+    V = model.var.get('V')
+    trac = model.var.get('tracer')
+    V0, N2, delta, sigma, alpha = .2, .15, .4, .4, 1.
+    bback = N2*grid.yr0/param.Ly
+    z = grid.yr0/delta
+    x = (grid.xr0)/sigma
+    V[:, :] = V0*(1+np.tanh(z))*(1-alpha*2*x*np.exp(-x**2))
+    buoy[:, :] = (V0*param.f0) / np.cosh(z)**2 * (x+alpha*np.exp(-x**2)) + bback
+    V *= grid.msk
+    buoy *= grid.msk
+    trac[:, :] = np.round(grid.xr*3) % 2
+    vor[:, :] = 0.
+    np.random.seed(1)
+    noise = np.random.normal(size=np.shape(yr))*grid.msk
+    noise -= grid.domain_integration(noise)*grid.msk/grid.area
+    grid.fill_halo(noise)
+    vor[:, :] += 1e-1*noise*grid.msk
+    vor *= grid.msk
+    model.set_psi_from_vorticity()
+    model.compute_pv()
+    return f2d
+
+
 CASES = {
     'freedecay_64': lambda api, d: freedecay(api, d, 64),
     'freedecay_32_o3_notracer': lambda api, d: freedecay(api, d, 32, order=3, tracer=False),
@@ -423,13 +480,14 @@ CASES = {
     'dbldiff_32_tridiag': lambda api, d: dbldiff(api, d, 32, relaxation='tridiagonal'),
     'qg_32_diagnosed': lambda api, d: qg(api, d, 32, timestepping='RK3_SSP', diagnosed=True),
     'sqg_32': lambda api, d: sqg(api, d, 32),
+    'si_32_flx': lambda api, d: symmetric_instab(api, d, 32),
 }
 # cases whose inversion is an FFT: another FFT library agrees to rounding, not bit for bit
 SPECTRAL = {'sqg_32'}
 # cases added after the last GPU session of round 1: their GPU parity test sits in
 # tests/test_gpu_zz_late.py so that it runs after every test that has already been green on a
 # B200 (the host layer is pinned on the CPU by tests/test_host_emulated.py)
-LATE = {'dbldiff_32', 'dbldiff_32_tridiag', 'qg_32_diagnosed', 'sqg_32'}
+LATE = {'dbldiff_32', 'dbldiff_32_tridiag', 'qg_32_diagnosed', 'sqg_32', 'si_32_flx'}
 # every other stepper of core/timescheme.py:78-201, with diffusion on so that the
 # `kstage == kforcing` branch of Euler.dynamics is exercised (light fixtures: states only)
 SCHEMES = ['EF', 'LF', 'Heun', 'AB2', 'AB3', 'LFAM3', 'RK4_LS']   # ('RK3' is not in param.py's list)

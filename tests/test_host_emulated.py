@@ -97,3 +97,83 @@ def test_emulator_covers_the_entry_points_the_host_layer_binds():
     used &= declared
     multi_gpu = {n for n in used if n.startswith("comm_")} | {"fill_halo_x"}
     assert used-multi_gpu <= emulated | {"mg_create_slab"}, sorted(used-multi_gpu-emulated)
+
+
+def _load(path):
+    return dict(np.load(path))
+
+
+def test_loop_writes_history_and_diagnostics_on_emulated_abi(emu):
+    """Fluid2d.loop() with a snapshot at every iteration: history records are the float32
+    interiors of the state, the diag file follows the loop (the CPU twin of
+    tests/test_gpu_loop_output.py)"""
+    api, rt_ = emu
+    with contextlib.redirect_stdout(io.StringIO()):
+        f2d = cases.freedecay(api, tempfile.mkdtemp(), 32, diag_fluxes=True)
+        out = f2d.output
+        out.freq_his = out.freq_diag = 0.
+        out.tnexthis = out.tnextdiag = 0.
+        f2d.exacthistime = False
+        f2d.loop(nsteps=3)
+    assert f2d.kt == 3
+    his = _load(out.hisfile)
+    state = np.array(f2d.model.var.state, copy=True)
+    for name in out.var_to_save:
+        k = f2d.model.var.index(name)
+        assert his[name].shape == (4, 32, 32) and his[name].dtype == np.float32
+        np.testing.assert_array_equal(his[name][-1], state[k][3:-3, 3:-3].astype(np.float32))
+    diag = _load(out.diagfile)
+    assert len(diag["t"]) == 4 and diag["ke"][-1] <= diag["ke"][0]
+    flx = _load(out.flxfile)
+    stack = np.array(f2d.flx.flx, copy=True)
+    for k, name in enumerate(f2d.flx.fullflx_list):
+        np.testing.assert_array_equal(flx[name][-1], stack[k][3:-3, 3:-3].astype(np.float32))
+
+
+def test_restart_round_trip_on_emulated_abi(emu):
+    """two jobs through Restart (restart.py: tend is the LENGTH of a job; the second job starts
+    from the file the first one wrote; output files carry the job index).  What a restart
+    carries over is the model state in double with its halos and the clocks -- bit for bit; the
+    time scheme's tendency buffers (whose psi is the first guess of the truncated inversions)
+    are not in the file, in the reference either, so the continuation agrees with an
+    uninterrupted run to the truncation of those inversions, not to rounding."""
+    import glob
+    import types
+    api, rt_ = emu
+    made = {}
+
+    class F(api.Fluid2d):
+        def __init__(self, param, grid):
+            made['param'], made['grid'] = param, grid
+            api.Fluid2d.__init__(self, param, grid)
+    api2 = types.SimpleNamespace(Param=api.Param, Grid=api.Grid, Fluid2d=F)
+    datadir = tempfile.mkdtemp()
+    from restart import Restart
+    with contextlib.redirect_stdout(io.StringIO()):
+        f1 = cases.freedecay(api2, datadir, 32)
+        f1.exacthistime = False
+        f1.tend = 1.0
+        made['param'].ninterrestart = 2
+        r1 = Restart(made['param'], made['grid'], f1)
+        assert r1.nextrestart == 0 and f1.kt > 0
+        end1 = np.array(f1.model.var.state, copy=True)
+        f2 = cases.freedecay(api2, datadir, 32)
+        f2.exacthistime = False
+        f2.tend = 1.0
+        made['param'].ninterrestart = 2
+        r2 = Restart(made['param'], made['grid'], f2, launch=False)
+    assert r2.lastrestart == 0 and r2.nextrestart == 1
+    np.testing.assert_array_equal(np.array(f2.model.var.state, copy=True), end1)
+    assert (f2.t, f2.dt, f2.kt) == (f1.t, f1.dt, f1.kt)
+    assert (f2.output.tnexthis, f2.output.tnextdiag) == (f1.output.tnexthis, f1.output.tnextdiag)
+    assert os.path.basename(f1.output.diagfile).startswith('freedecay_32_00_diag')
+    assert os.path.basename(f2.output.diagfile).startswith('freedecay_32_01_diag')
+    with contextlib.redirect_stdout(io.StringIO()):
+        r2.launchf2d(f2)
+        ref = cases.freedecay(api, tempfile.mkdtemp(), 32)
+        ref.exacthistime = False
+        ref.loop(nsteps=f2.kt)
+    assert f2.kt > f1.kt and f2.t >= f1.t+1.0
+    assert len(glob.glob(datadir+'/freedecay_32/freedecay_32_*_restart_000.*')) == 2
+    a, b = np.array(f2.model.var.state, copy=True), np.array(ref.model.var.state, copy=True)
+    assert np.linalg.norm(a-b) <= 1e-2*np.linalg.norm(b)

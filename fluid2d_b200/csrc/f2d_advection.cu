@@ -290,5 +290,8 @@ extern "C" int f2d_adv_centered(const int8_t *msk, const double *q, double *dq, 
                                 const double *v, double *xflx, double *yflx, const double *cst5, int nh,
                                 int method, int order, int ny, int nx, int fill_halo, f2d_stream_t s) {
   (void)method;
+  // core/fortran_fluxes.f90's adv_centered (flux outputs) has no 6th-order branch: order = 6
+  // falls through to its `order.ge.2` two-point mean
+  if (xflx != nullptr && order == 6) order = 2;
   return adv_common(false, msk, q, dq, u, v, xflx, yflx, cst5, nh, 0, order, ny, nx, fill_halo, S(s));
 }

@@ -157,6 +157,10 @@ def logical_lines(text):
         line = raw.rstrip()
         if not line.strip():
             continue
+        m = re.match(r"\s*!f2py\s+intent\(out\)\s*::\s*(.*)$", line, re.I)
+        if m:
+            out.append("f2pyout "+m.group(1).strip())
+            continue
         if line.lstrip().startswith("!") or line[0] in "cC*":
             continue
         # inline comment (no string in these files contains '!', except inside write())
@@ -302,8 +306,12 @@ def parse_decl(line, table):
 def translate_subroutine(name, args, body):
     table = {}
     stmts = []
+    outs = []
     for ln in body:
         low = ln.lower()
+        if low.startswith("f2pyout "):
+            outs += [a.strip().lower() for a in ln[8:].split(",")]
+            continue
         if low.startswith("implicit") or parse_decl(ln, table):
             continue
         stmts.append(ln)
@@ -435,12 +443,14 @@ def translate_subroutine(name, args, body):
     # dimension arguments f2py would hide and fill from the array shapes
     infer = {}
     for a in args:
-        if a in arrays:
+        if a in arrays and a not in outs:
             for axis, d in enumerate(table[a][1]):
                 d = d.strip().lower()
                 if d in args and d not in arrays and d not in infer:
                     infer[d] = (a, axis)
-    META[name] = {"args": args, "infer": infer}
+    META[name] = {"args": args, "infer": infer, "outs": outs,
+                  "dims": {a: table[a][1] for a in args if a in arrays},
+                  "kinds": {a: table[a][0] for a in args if a in table}}
     return "\n".join(lines)
 
 
@@ -500,6 +510,49 @@ def call(key, routine, **given):
             values.append(0.)          # intent(out) scalar
     with np.errstate(all="ignore"):
         return ns[routine](*values)
+
+
+def f2py_namespace(key):
+    """{routine: callable} with the calling convention of the f2py module the reference
+    builds from this file (build.py:12-39): dimension arguments hidden, intent(out) arguments
+    returned, intent(inplace) arrays modified in place (an array of another dtype is converted
+    and copied back, as f2py's intent(inplace) does)"""
+    ns = module(key)
+
+    def make(routine):
+        meta = ns["__meta__"][routine]
+        visible = [a for a in meta["args"] if a not in meta["infer"] and a not in meta["outs"]]
+
+        def fn(*pos, **kw):
+            given = dict(zip(visible, pos))
+            given.update({k.lower(): v for k, v in kw.items()})
+            back = []
+            for a, dims in meta["dims"].items():
+                if a in given:
+                    want = DTYPES[meta["kinds"][a]]
+                    arr = given[a]
+                    if not isinstance(arr, np.ndarray) or arr.dtype != want:
+                        conv = np.array(arr, dtype=want)
+                        if isinstance(arr, np.ndarray):
+                            back.append((arr, conv))
+                        given[a] = conv
+            sizes = {d: given[arr].shape[axis] for d, (arr, axis) in meta["infer"].items()}
+            for a in meta["outs"]:
+                if a in meta["dims"]:      # intent(out) array: allocated from its declared shape
+                    shape = tuple(int(eval(expr(d, set()), dict(sizes))) for d in meta["dims"][a])
+                    given[a] = np.zeros(shape, dtype=DTYPES[meta["kinds"][a]])
+            values = [given[a] if a in given else (sizes[a] if a in sizes else 0.) for a in meta["args"]]
+            with np.errstate(all="ignore"):
+                res = ns[routine](*values)
+            for dst, tmp in back:
+                dst[...] = tmp
+            got = [given[a] if a in meta["dims"] else res[a] for a in meta["outs"]]
+            if not got:
+                return None
+            return got[0] if len(got) == 1 else tuple(got)
+        fn.__name__ = routine
+        return fn
+    return {r: make(r) for r in ns["__routines__"]}
 
 
 if __name__ == "__main__":

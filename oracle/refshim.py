@@ -24,8 +24,12 @@ def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "core", "gmg"))
 
 
-def install(reference_root=REFERENCE_ROOT):
+def install(reference_root=REFERENCE_ROOT, kernels="oracle"):
+    """kernels="oracle": the f2py modules are replaced by the C restatement (default);
+    kernels="fortran_source": by the reference's own Fortran source, executed through
+    oracle/fortran_source.py (slow: small grids only)"""
     import numpy
+    use_source = kernels == "fortran_source"
     if not hasattr(numpy, "NaN"):
         numpy.NaN = numpy.nan
     here = os.path.dirname(os.path.abspath(__file__))
@@ -39,9 +43,17 @@ def install(reference_root=REFERENCE_ROOT):
     sys.path.insert(0, repo)
     from oracle import kernels
     mod = types.ModuleType("gmg.fortran_multigrid")
-    for k, v in vars(kernels.fortran_multigrid).items():
-        if not k.startswith("_"):
-            setattr(mod, k, v.__func__ if isinstance(v, staticmethod) else v)
+    if use_source:
+        from oracle import fortran_source
+        for key in ("fortran_advection", "fortran_fluxes", "fortran_operators", "fortran_diag"):
+            m = types.ModuleType(key)
+            m.__dict__.update(fortran_source.f2py_namespace(key))
+            sys.modules[key] = m
+        mod.__dict__.update(fortran_source.f2py_namespace("fortran_multigrid"))
+    else:
+        for k, v in vars(kernels.fortran_multigrid).items():
+            if not k.startswith("_"):
+                setattr(mod, k, v.__func__ if isinstance(v, staticmethod) else v)
     sys.modules["gmg.fortran_multigrid"] = mod
     import gmg  # the reference package (core/gmg/__init__.py)
     gmg.fortran_multigrid = mod

@@ -27,8 +27,8 @@ sys.path.insert(0, REPO)
 from oracle import refshim  # noqa: E402
 
 
-def reference_api():
-    refshim.install()
+def reference_api(kernels="oracle"):
+    refshim.install(kernels=kernels)
     import types
     from param import Param
     from grid import Grid
@@ -36,11 +36,14 @@ def reference_api():
     return types.SimpleNamespace(Param=Param, Grid=Grid, Fluid2d=Fluid2d, name="reference")
 
 
-def generate(names=None):
+def generate(names=None, kernels="oracle", check=False, nsteps=None):
+    """check=True: nothing is written; the run is compared with the committed fixture bit for
+    bit (used with kernels="fortran_source": the reference's Python on the reference's own
+    Fortran source must reproduce what it gave on the C restatement); nsteps limits the run"""
     import numpy as np
     sys.path.insert(0, HERE)
     import cases
-    api = reference_api()
+    api = reference_api(kernels)
     datadir = tempfile.mkdtemp(prefix="f2d_golden_")
     real_stdout = sys.stdout
     for name, builder in cases.CASES.items():
@@ -68,17 +71,26 @@ def generate(names=None):
         if getattr(f2d, "diag_fluxes", False):
             out["flxnames"] = np.array(f2d.flx.fullflx_list)
             out["flx0"] = cases.run_fluxes(f2d)
-        res = cases.run_steps(f2d)
+        res = cases.run_steps(f2d) if nsteps is None else cases.run_steps(f2d, (nsteps,))
         for k, (state, t, dt, diags) in res.items():
             out["state%i" % k] = state
             out["t%i" % k] = np.array(t)
             out["dt%i" % k] = np.array(dt)
             for dn, dv in diags.items():
                 out["diag%i_%s" % (k, dn)] = np.array(dv)
-        if getattr(f2d, "diag_fluxes", False):
+        if getattr(f2d, "diag_fluxes", False) and nsteps is None:
             out["flx10"] = cases.run_fluxes(f2d)
         sys.stdout = real_stdout
         path = os.path.join(HERE, name + ".npz")
+        if check:
+            gold = np.load(path)
+            bad = [k for k, v in out.items() if k in gold.files and not np.array_equal(np.asarray(v), gold[k])]
+            missing = [k for k in out if k not in gold.files]
+            print("%-28s %s kernels: %d records compared with the fixture: %s" % (
+                name, kernels, len(out)-len(missing), "IDENTICAL" if not bad else "DIFFERENT: %s" % bad))
+            if bad:
+                sys.exit(1)
+            continue
         np.savez_compressed(path, **out)
         print("%-28s -> %s (%.0f KB)  t10=%.6g  maxspeed=%.6g" % (
             name, os.path.relpath(path, REPO), os.path.getsize(path)/1024.,
@@ -89,4 +101,17 @@ def generate(names=None):
 if __name__ == "__main__":
     if not refshim.available():
         sys.exit("make_golden.py needs the reference at /root/reference (build container only)")
-    generate(sys.argv[1:])
+    argv = sys.argv[1:]
+    opts = {"kernels": "oracle", "check": False, "nsteps": None}
+    names = []
+    while argv:
+        a = argv.pop(0)
+        if a == "--kernels":
+            opts["kernels"] = argv.pop(0)
+        elif a == "--check":
+            opts["check"] = True
+        elif a == "--steps":
+            opts["nsteps"] = int(argv.pop(0))
+        else:
+            names.append(a)
+    generate(names, **opts)

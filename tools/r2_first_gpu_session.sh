@@ -16,6 +16,13 @@ if [ "${1:-}" = "scaling" ]; then
     fi
     tail -c 600 gpurun_out/s5_strong_$N.json
   done
+  # how many levels stay distributed (weak scaling line, 8 GPUs): every distributed level costs
+  # one neighbour synchronisation per operator application, a gathered one costs redundant work
+  for C in 1048576 4194304 16777216; do
+    F2D_SLAB_MIN_CELLS=$C timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+      --master-port 29611 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/weak8_mincells_$C.json 2> gpurun_out/weak8_mincells_$C.err
+    tail -c 300 gpurun_out/weak8_mincells_$C.json
+  done
   exit 0
 fi
 # 1. the late tests alone (line relaxation, BoussinesqTS, QG diagnosed), verbose, under a timeout

@@ -43,7 +43,6 @@ def test_line_relaxation_against_oracle(L, kind, ny, nx, dx, dy):
     fortran_multigrid.f90:215-317).  The last case has flat cells (dy/dx = 1/8 <= 0.2): the
     5-point operator, and f2d_mg_create selects the line relaxation by itself.
     Bit-exact on the -fmad=false build; 1e-11 of the field's maximum on the product build."""
-    import torch
     import gpu_util as g
     from oracle import model as om
     lib, strict = L

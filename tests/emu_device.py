@@ -129,8 +129,9 @@ class EmuLib(object):
     def _fill(self, a, nh, mode):
         if mode == 1:
             fm.fillhalo(a, nh)
-        elif mode:
-            raise NotImplementedError("emulator: one rank (fill mode %d)" % mode)
+        elif mode == 2:           # y-slab decomposition: x images only, rows come from the exchange
+            a[:, :nh] = a[:, -2*nh:-nh]
+            a[:, -nh:] = a[:, nh:2*nh]
 
     # ---- advection
     def _adv(self, upwind, msk, q, dq, u, v, xflx, yflx, cst5, nh, method, order, ny, nx, fill):
@@ -416,8 +417,15 @@ class EmuLib(object):
         self._h(h).mg.relaxation = 'tridiagonal' if mode else 'default'
         return 0
 
-    def mg_create_slab(self, *a):
-        raise NotImplementedError("emulator: one rank")
+    def mg_create_slab(self, h, comm, cornermask, ny_loc, nx, dx, dy, omega, hydroepsilon, Rd, stream):
+        glob = self._assemble(f64(cornermask, ny_loc, nx))
+        mg = om.MG(glob, nx-6, glob.shape[0]-6, dx, dy, omega=omega, hydroepsilon=hydroepsilon,
+                   Rd=(Rd if Rd > 0 else None))
+        key = len(self.handles)+1
+        self.handles[key] = _Handle(mg)
+        self.handles[key].slab = (ny_loc, nx)
+        h._obj.value = key
+        return 0
 
     def _h(self, h):
         return self.handles[_addr(h)]
@@ -427,7 +435,7 @@ class EmuLib(object):
         return 0
 
     def mg_slab_levels(self, h):
-        return 0
+        return 1 if getattr(self._h(h), "slab", None) else 0
 
     def mg_nlevels(self, h):
         return self._h(h).mg.nlevs
@@ -462,17 +470,33 @@ class EmuLib(object):
         self._h(h).mg.fcycle(lev1)
         return 0
 
+    def _shape(self, h):
+        H = self._h(h)
+        return getattr(H, "slab", None) or H.mg.x[0].shape
+
     def mg_two_vcycle(self, h, psi, rhs, stream):
-        mg = self._h(h).mg
-        shape = mg.x[0].shape
+        H = self._h(h)
+        mg = H.mg
+        shape = self._shape(h)
+        if getattr(H, "slab", None):
+            P, R = self._assemble(f64(psi, *shape)), self._assemble(f64(rhs, *shape))
+            mg.two_vcycle(P, R)
+            f64(psi, *shape)[...] = self._local_rows(P, shape[0])
+            return 0
         mg.two_vcycle(f64(psi, *shape), f64(rhs, *shape))
         return 0
 
     def mg_solve(self, h, psi, rhs, tol, maxite, nite, res, stream):
-        mg = self._h(h).mg
-        shape = mg.x[0].shape
+        H = self._h(h)
+        mg = H.mg
+        shape = self._shape(h)
         try:
-            n, r = mg.solve(f64(psi, *shape), f64(rhs, *shape), maxite=maxite, tol=tol)
+            if getattr(H, "slab", None):
+                P, R = self._assemble(f64(psi, *shape)), self._assemble(f64(rhs, *shape))
+                n, r = mg.solve(P, R, maxite=maxite, tol=tol)
+                f64(psi, *shape)[...] = self._local_rows(P, shape[0])
+            else:
+                n, r = mg.solve(f64(psi, *shape), f64(rhs, *shape), maxite=maxite, tol=tol)
         except RuntimeError:
             return 4
         if nite is not None:
@@ -483,8 +507,7 @@ class EmuLib(object):
 
     def invert_vorticity(self, h, msk, mskp, w, psi, u, v, work, rhsp, psi_island, full, perio, area, dx, dy,
                          nh, nite, res, scratch, stream):
-        mg = self._h(h).mg
-        ny, nx = mg.x[0].shape
+        ny, nx = self._shape(h)
         n = ny*nx
         self.celltocorner(w, work, ny, nx, stream)
         if _addr(rhsp):
@@ -495,7 +518,10 @@ class EmuLib(object):
                 return err
             if perio:
                 P = f64(psi, ny, nx)
-                P -= np.sum(P[nh:-nh, nh:-nh])/area
+                total = np.array([np.sum(P[nh:-nh, nh:-nh])])
+                if self.nranks > 1:
+                    self.comm_allreduce(None, total.ctypes.data, 1, 0, stream)
+                P -= total[0]/area
         else:
             self.mg_two_vcycle(h, psi, work, stream)
             if nite is not None:
@@ -508,8 +534,70 @@ class EmuLib(object):
         self.add_scaled(psi, 1., psi_island, n, stream)
         return self.orthogradient(msk, psi, dx, dy, nh, u, v, ny, nx, stream)
 
-    # ---- one rank: the multi-GPU entry points degenerate
+    # ---- y-slab decomposition (npx = 1, npy = ranks): the communicator entry points over a
+    # gloo process group (one CPU process per rank); the slab multigrid is emulated by
+    # assembling the global problem on every rank, running the oracle's hierarchy on it and
+    # keeping the local rows -- Jacobi smoothing is order independent, so this is what the
+    # distributed cycles compute
+    nranks = 1
+    rank = 0
+
+    def _gather(self, a):
+        import torch.distributed as dist
+        mine = torch.from_numpy(np.ascontiguousarray(a).copy())
+        parts = [torch.zeros_like(mine) for _ in range(self.nranks)]
+        dist.all_gather(parts, mine)
+        return [p.numpy() for p in parts]
+
+    def _assemble(self, loc, nh=3):
+        """local slabs [ny_loc, nx] of every rank -> the global array (south to north): the
+        interiors, with the outer halo rows of the first and last rank"""
+        parts = self._gather(loc)
+        return np.concatenate([parts[0][:nh]]+[p[nh:-nh] for p in parts]+[parts[-1][-nh:]], axis=0)
+
+    def _local_rows(self, glob, ny_loc, nh=3):
+        j0 = self.rank*(ny_loc-2*nh)
+        return glob[j0:j0+ny_loc]
+
     def comm_barrier(self, comm, stream):
+        if self.nranks > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        return 0
+
+    def comm_rank(self, comm):
+        return self.rank
+
+    def comm_size(self, comm):
+        return self.nranks
+
+    def fill_halo_x(self, x, nh, ny, nx, stream):
+        self._fill(f64(x, ny, nx), nh, 2)
+        return 0
+
+    def comm_exchange_y(self, comm, x, nh, ny, nx, stream):
+        X = f64(x, ny, nx)
+        if self.nranks == 1:
+            X[:nh] = X[-2*nh:-nh]
+            X[-nh:] = X[nh:2*nh]
+            return 0
+        parts = self._gather(np.stack([X[nh:2*nh], X[-2*nh:-nh]]))     # my bottom / top interior rows
+        X[:nh] = parts[(self.rank-1) % self.nranks][1]
+        X[-nh:] = parts[(self.rank+1) % self.nranks][0]
+        return 0
+
+    def comm_allreduce(self, comm, vals, n, maxmask, stream):
+        V = f64(vals, n)
+        parts = self._gather(V)
+        for k in range(n):
+            col = [p[k] for p in parts]
+            if (maxmask >> k) & 1:
+                V[k] = max(col)
+            else:
+                acc = col[0]
+                for c in col[1:]:
+                    acc = acc+c
+                V[k] = acc
         return 0
 
 
@@ -527,8 +615,20 @@ class EmuRuntime(object):
         self.rank = 0
 
     def ensure_comm(self, nranks, fieldbytes):
-        if nranks != 1:
-            raise NotImplementedError("emulator: one rank")
+        """y-slabs: one CPU process per rank under torchrun, gloo process group"""
+        if nranks == 1 or self.comm is not None:
+            return
+        import runtime
+        import torch.distributed as dist
+        runtime.ensure_dist()
+        if dist.get_world_size() != nranks:
+            raise RuntimeError("param.npy = %d but %d processes were launched" % (nranks, dist.get_world_size()))
+        self.rank = self.lib.rank = dist.get_rank()
+        self.nranks = self.lib.nranks = nranks
+        self.comm = ctypes.c_void_p(1)      # a non-null token: the host layer only tests it and passes it on
+
+    def exchange_y(self, ptr, ny, nx, nh=3):
+        self.lib.comm_exchange_y(self.comm, ptr, nh, ny, nx, self.stream)
 
     def alloc(self, shape, dtype=torch.float64):
         return torch.zeros(shape, dtype=dtype)

@@ -1,0 +1,61 @@
+"""Worker of tests/test_slab_emulated.py: two CPU processes (gloo), the product's host layer on
+the emulated C ABI with the y-slab communicator (tests/emu_device.py).  Builds freedecay with
+npy = world size, advances it, gathers the global fields and compares them with the same
+global problem run on ONE rank in the same process (the CPU twin of tests/slab_worker.py).
+
+    torchrun --nproc-per-node 2 tests/slab_emu_worker.py out.json nx ny nsteps
+"""
+import contextlib
+import io
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+import emu_device  # noqa: E402
+import cases  # noqa: E402
+
+
+def main():
+    out, nx, ny, nsteps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+    world = int(os.environ["WORLD_SIZE"])
+    api, emu = emu_device.install()
+    with contextlib.redirect_stdout(io.StringIO()):
+        f2d = cases.freedecay(api, tempfile.mkdtemp(), nx, ny=ny, npy=world)
+        res = cases.run_steps(f2d, (nsteps,))[nsteps]
+    import torch.distributed as dist
+    rank = dist.get_rank()
+    state = np.array(res[0])
+    parts = [np.stack(emu.lib._gather(state[k])) for k in range(state.shape[0])]     # [nvar][rank][rows][nx]
+    glob = np.stack([np.concatenate([p[0][:3]]+[q[3:-3] for q in p]+[p[-1][-3:]], axis=0) for p in parts])
+    report = {"rank": rank, "kt": f2d.kt, "t": res[1], "dt": res[2], "diags": res[3],
+              "solve": list(f2d.model.ope.last_solve), "slab_levels": f2d.model.ope.gmg.slab_levels}
+    if rank == 0:
+        # the same global problem on one rank (a fresh single-rank emulator; no process group use)
+        emu_device.uninstall()
+        api1, emu1 = emu_device.install()
+        with contextlib.redirect_stdout(io.StringIO()):
+            one = cases.freedecay(api1, tempfile.mkdtemp(), nx, ny=ny, npy=1)
+            r1 = cases.run_steps(one, (nsteps,))[nsteps]
+        ref = np.array(r1[0])
+        names = list(one.model.var.varname_list)
+        report["fields_equal"] = {nm: bool(np.array_equal(glob[k][3:-3], ref[k][3:-3])) for k, nm in enumerate(names)}
+        report["maxdiff"] = {nm: float(np.abs(glob[k][3:-3]-ref[k][3:-3]).max()) for k, nm in enumerate(names)}
+        report["one"] = {"t": r1[1], "dt": r1[2], "diags": r1[3], "solve": list(one.model.ope.last_solve)}
+    everyone = [None]*world
+    dist.all_gather_object(everyone, report)
+    if rank == 0:
+        json.dump(everyone, open(out, "w"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

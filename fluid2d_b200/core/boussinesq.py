@@ -2,7 +2,6 @@
 Same interface: var, ope, tscheme, diags, step, dynamics, add_noslip,
 set_psi_from_vorticity, diagnostics, forc / extrastep hooks."""
 import numpy as np
-import torch
 
 from modelbase import adopt, declare_state, user_object, EMBEDDED_FORCING_NOTE
 from operators import Operators
@@ -31,7 +30,7 @@ class Boussinesq(object):
         # reference buoyancy: the buoyancy field at construction time (zeros); scripts set it
         # afterwards in place (model.bref[:, :] = buoy), hence a HostField
         self.bref = HostField(self.var.get('buoyancy'))
-        self.source = torch.zeros((grid.nyl, grid.nxl), dtype=torch.float64, device=r.device)
+        self.source = r.alloc((grid.nyl, grid.nxl))    # (symmetric heap on y-slabs: its halo rows are exchanged)
         self.d_yr = r.to_device(self.yr, dtype=np.float64)
         self.ope = Operators(param, grid)
         self.tscheme = Timescheme(param, self.var.dstate)

@@ -6,7 +6,6 @@ of libf2d_b200.so on device-resident fields."""
 import ctypes
 
 import numpy as np
-import torch
 
 from modelbase import adopt, declare_state, user_object, EMBEDDED_FORCING_NOTE
 from operators import Operators
@@ -35,7 +34,7 @@ class BoussinesqTS(object):
         # reference density: the density field at construction time (zeros); a script may
         # set it afterwards in place, like Boussinesq.bref
         self.dref = HostField(self.var.get('density'))
-        self.source = torch.zeros((grid.nyl, grid.nxl), dtype=torch.float64, device=r.device)
+        self.source = r.alloc((grid.nyl, grid.nxl))    # (symmetric heap on y-slabs: its halo rows are exchanged)
         self.d_yr = r.to_device(self.yr, dtype=np.float64)
         self.ope = Operators(param, grid)
         self.tscheme = Timescheme(param, self.var.dstate)

@@ -42,8 +42,6 @@ class Fluxes(object):
         self.list_grid = ['nh', 'dx', 'dy', 'msk']
         grid.copy(self, self.list_grid)
         self.ope = ope
-        if ope.comm is not None:
-            raise NotImplementedError('diag_fluxes on a decomposed domain')
         self.rt = rt()
         ny, nx = self.sizevar
         self.ny, self.nx, self.fieldsize = ny, nx, ny*nx
@@ -92,7 +90,9 @@ class Fluxes(object):
         iu, iv, ip, iw = self.ix('u'), self.ix('v'), self.ix('psi'), self.ix('vorticity')
         self._copy_fields(self.xe, 0, x, 0, nvs-2)
         lib.flx_cellvel(x.rptr(iu), x.rptr(iv), self.xe.wptr(nvs-2), self.xe.wptr(nvs-1),
-                        self.nh, self.ny, self.nx, 1, r.stream)
+                        self.nh, self.ny, self.nx, self.ope.fillmode, r.stream)
+        self.ope._xch(self.xe.wptr(nvs-2))      # (y-slabs: halo rows from the neighbours)
+        self.ope._xch(self.xe.wptr(nvs-1))
         # forward step
         self._copy_fields(self.x, 0, self.xe, 0, nvs)
         self._zero_fluxes(self.x)
@@ -134,6 +134,7 @@ class Fluxes(object):
             ifx = self.nvarstate+itrac*2
             xf, yf = dxdt.wptr(ifx), dxdt.wptr(ifx+1)
             adv(msk, x.rptr(ik), dxdt.wptr(ik), x.rptr(iu), x.rptr(iv), xf, yf, cst,
-                self.nh, self.fs_method, self.order, self.ny, self.nx, 1, r.stream)
-            lib.fill_halo(xf, self.nh, self.ny, self.nx, r.stream)
-            lib.fill_halo(yf, self.nh, self.ny, self.nx, r.stream)
+                self.nh, self.fs_method, self.order, self.ny, self.nx, ope.fillmode, r.stream)
+            ope._xch(dxdt.wptr(ik))
+            ope._fill(xf, self.ny, self.nx)
+            ope._fill(yf, self.ny, self.nx)

@@ -246,8 +246,9 @@ class Operators(Param):
         lib.copy(src, work, n*8, r.stream)
         # zero net source: subtract its mean over the boundary cells
         lib.domain_sum(src, self.nh, ny, nx, r.ptr(r.out), r.ptr(r.scratch), r.stream)
-        if self.mpitools.nbproc > 1:
-            raise NotImplementedError('no-slip source on several ranks')
+        if self.comm is not None:
+            # y-slabs: the integral is over the whole domain (bcarea is the global one)
+            lib.comm_allreduce(self.comm, r.ptr(r.out), 1, 0, r.stream)
         lib.sub_devscalar_mask(src, r.ptr(r.out), float(self.bcarea[0]), r.ptr(self.d_mskbc), n, r.stream)
         if self.enforce_momentum:
             lib.computedotprod(r.ptr(self.d_msk), src, r.ptr(self.d_xr0), self.nh, ny, nx,
@@ -259,7 +260,7 @@ class Operators(Param):
             px, py = cst[0]/self.x2bc, cst[1]/self.y2bc
             lib.sub_lin2_mask(src, float(px), r.ptr(self.d_xr0), float(py), r.ptr(self.d_yr0),
                               r.ptr(self.d_mskbc), n, r.stream)
-        lib.fill_halo(src, self.nh, ny, nx, r.stream)
+        self._fill(src, ny, nx)
         lib.add_scaled(x.wptr(iw), -1., src, n, r.stream)
 
     # ------------------------------------------------------------------

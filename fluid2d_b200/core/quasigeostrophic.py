@@ -2,7 +2,6 @@
 The elliptic operator is the Helmholtz operator (Laplacian - 1/Rd^2), built by the
 device multigrid when param.qgoperator is set (hierarchy.py:80-84)."""
 import numpy as np
-import torch
 
 from modelbase import adopt, declare_state, user_object
 from operators import Operators
@@ -28,7 +27,7 @@ class QG(object):
         r = rt()
         self.rt = r
         self.ncell = grid.nyl*grid.nxl
-        self.source = torch.zeros((grid.nyl, grid.nxl), dtype=torch.float64, device=r.device)
+        self.source = r.alloc((grid.nyl, grid.nxl))    # (symmetric heap on y-slabs: its halo rows are exchanged)
         ix = self.var.index
         self.ipv, self.ipsi, self.ipva, self.ivor = ix('pv'), ix('psi'), ix('pvanom'), ix('vorticity')
         self.pvback = self.beta*(grid.yr-grid.Ly*.5)*grid.msk

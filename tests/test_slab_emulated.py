@@ -17,18 +17,24 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("nx,ny,nsteps,nranks", [(32, 64, 3, 2), (32, 32, 2, 2), (16, 64, 2, 4)])
-def test_slabs_reproduce_single_rank_run(tmp_path, nx, ny, nsteps, nranks):
+@pytest.mark.parametrize("case,nx,ny,nsteps,nranks", [("freedecay", 32, 64, 3, 2), ("freedecay", 32, 32, 2, 2),
+                                                      ("freedecay", 16, 64, 2, 4),
+                                                      # Boussinesq x-channel with NO-SLIP walls, forcing, diffusion
+                                                      ("rb", 64, 32, 3, 2),
+                                                      # diag_fluxes: the reversible / irreversible stacks too
+                                                      ("freedecay_flx", 32, 64, 2, 2)])
+def test_slabs_reproduce_single_rank_run(tmp_path, case, nx, ny, nsteps, nranks):
     out = str(tmp_path/"rep.json")
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="", MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks),
            "--master-addr", "127.0.0.1", "--master-port", "29541",
-           os.path.join(HERE, "slab_emu_worker.py"), out, str(nx), str(ny), str(nsteps)]
+           os.path.join(HERE, "slab_emu_worker.py"), out, str(nx), str(ny), str(nsteps), case]
     p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:]+p.stderr[-4000:]
     reports = json.load(open(out))
     r0 = reports[0]
     assert all(r0["fields_equal"].values()), r0["maxdiff"]
+    assert r0.get("fluxes_equal", True), r0.get("fluxes_maxdiff")
     assert r0["slab_levels"] >= 1
     for rep in reports:
         assert rep["kt"] == nsteps

@@ -2,7 +2,7 @@
 freedecay case with npy = world size, advances it, gathers the global fields on rank 0
 and compares them with a single-GPU run of the same global problem (ref .npz).
 
-    torchrun --nproc-per-node 2 tests/slab_worker.py ref.npz out.json nx ny nsteps
+    torchrun --nproc-per-node 2 tests/slab_worker.py ref.npz out.json nx ny nsteps [case]
 """
 import json
 import os
@@ -37,7 +37,13 @@ def main():
     world = int(os.environ["WORLD_SIZE"])
     so = sys.stdout
     sys.stdout = sys.stderr
-    f2d = cases.freedecay(api, tempfile.mkdtemp(), nx, ny=ny, npy=world)
+    case = sys.argv[6] if len(sys.argv) > 6 else "freedecay"
+    if case == "freedecay":
+        f2d = cases.freedecay(api, tempfile.mkdtemp(), nx, ny=ny, npy=world)
+    else:
+        sys.path.insert(0, os.path.join(REPO, "tests"))
+        from slab_cases import BUILDERS
+        f2d = BUILDERS[case](api, tempfile.mkdtemp(), nx, ny, world)
     model = f2d.model
     rank = dist.get_rank()
     ref = np.load(refpath)

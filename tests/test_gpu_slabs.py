@@ -65,3 +65,34 @@ def test_two_slabs_match_single_gpu(nx, ny, min_cells):
         assert e <= 1e-12, (key, e)
     for k in (1, nsteps):
         assert abs(rep["dt%d" % k]-rep["dt%d_ref" % k]) <= 1e-12*rep["dt%d_ref" % k]
+
+
+def test_two_slabs_match_single_gpu_with_noslip_walls():
+    """Boussinesq x-channel with no-slip walls, forcing and diffusion (tests/slab_cases.py: rb):
+    masked slab multigrid, boundary integral of the no-slip source through the all-reduce.
+    The host side of this is pinned on two CPU ranks by tests/test_slab_emulated.py."""
+    if ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import fluid2d_b200
+    from slab_cases import BUILDERS
+    api = fluid2d_b200.api()
+    nx, ny, nsteps = 128, 64, 3
+    d = tempfile.mkdtemp()
+    f2d = BUILDERS["rb"](api, d, nx, ny, 1)
+    ref = {"state0": np.array(f2d.model.var.state)}
+    res = cases.run_steps(f2d, (1, nsteps))
+    for k in (1, nsteps):
+        ref["state%d" % k] = res[k][0]
+        ref["dt%d" % k] = np.array(res[k][2])
+    refpath = os.path.join(d, "ref.npz")
+    np.savez(refpath, **ref)
+    out = os.path.join(d, "out.json")
+    env = dict(os.environ, F2D_SLAB_MIN_CELLS="1500")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
+           os.path.join(REPO, "tests", "slab_worker.py"), refpath, out, str(nx), str(ny), str(nsteps), "rb"]
+    p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-3000:]
+    rep = json.load(open(out))
+    for key, e in rep["errors"].items():
+        assert e <= 1e-12, (key, e)

@@ -2,9 +2,15 @@
 # First GPU session of round 2: everything that was written at the end of round 1 without GPU
 # access.  Usage (from the repo root):
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/r2_first_gpu_session.sh'
+#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 1300 -- 'bash tools/r2_first_gpu_session.sh slabs'
 #   /usr/local/graft/bin/gpurun --gpus 8 --timeout 1500 -- 'bash tools/r2_first_gpu_session.sh scaling'
 set -u
 mkdir -p gpurun_out
+if [ "${1:-}" = "slabs" ]; then
+  # needs --gpus 2: decomposition invariance, the no-slip Rayleigh-Benard channel included
+  timeout 1200 python -m pytest tests/test_gpu_slabs.py -m gpu -q -x 2>&1 | tail -15 | tee gpurun_out/slab_tests.log
+  exit 0
+fi
 if [ "${1:-}" = "scaling" ]; then
   # SURVEY 8d case S5: strong scaling of the 16384^2 Euler step (1-GPU run = the denominator)
   for N in 1 2 4 8; do

@@ -73,6 +73,10 @@ def test_two_slabs_match_single_gpu_with_noslip_walls():
     The host side of this is pinned on two CPU ranks by tests/test_slab_emulated.py."""
     if ngpus() < 2:
         pytest.skip("needs 2 GPUs")
+    if os.environ.get("F2D_TEST_UNVERIFIED_SLABS") != "1":
+        # the masked slab multigrid has not run on real GPUs yet (written after the round's GPU
+        # budget was spent): opt-in until tools/r2_first_gpu_session.sh slabs has been green once
+        pytest.skip("set F2D_TEST_UNVERIFIED_SLABS=1 (first run: tools/r2_first_gpu_session.sh slabs)")
     import fluid2d_b200
     from slab_cases import BUILDERS
     api = fluid2d_b200.api()

@@ -8,7 +8,7 @@ set -u
 mkdir -p gpurun_out
 if [ "${1:-}" = "slabs" ]; then
   # needs --gpus 2: decomposition invariance, the no-slip Rayleigh-Benard channel included
-  timeout 1200 python -m pytest tests/test_gpu_slabs.py -m gpu -q -x 2>&1 | tail -15 | tee gpurun_out/slab_tests.log
+  F2D_TEST_UNVERIFIED_SLABS=1 timeout 1200 python -m pytest tests/test_gpu_slabs.py -m gpu -q -x 2>&1 | tail -15 | tee gpurun_out/slab_tests.log
   exit 0
 fi
 if [ "${1:-}" = "scaling" ]; then

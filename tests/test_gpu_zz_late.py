@@ -23,7 +23,7 @@ from test_gpu_golden import test_case_matches_reference_run as check_case  # noq
 NEW_KERNELS = {"si_32_flx": "thermal-wind kernels", "dbldiff_32_tridiag": "line relaxation"}
 
 
-@pytest.mark.parametrize("name", sorted(cases.LATE-set(NEW_KERNELS)))
+@pytest.mark.parametrize("name", sorted(cases.LATE-set(NEW_KERNELS), reverse=True))
 def test_late_case_matches_reference_run(name):
     check_case(name)
 

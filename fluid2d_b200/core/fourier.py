@@ -1,42 +1,52 @@
-"""Fourier: spectral inversion of the SQG model, psi = -pv/|k| (reference: core/fourier.py).
+"""Spectral inversion of the SQG model on the device: psi_hat = -pv_hat/|k|, moved half a cell
+to the corners, and the diagnosed vorticity |k| pv_hat (reference interface: core/fourier.py,
+`Fourier(param, grid).invert(pv, psi, vor)`).
 
-The transforms are a library FFT on the device (cuFFT through torch.fft, complex128) where the
-reference calls numpy.fft on the host; the spectral multipliers are built exactly as the
-reference builds them (fourier.py:19-31) and uploaded once.  Nothing here is a hand-written
-kernel; the fields never leave HBM."""
+The transforms are a library FFT (cuFFT through torch.fft, complex128) where the reference
+calls numpy.fft on the host; the fields never leave HBM and nothing here is a hand-written
+kernel.  The two spectral multipliers are tabulated once on the host, with the arithmetic of
+fourier.py:19-31 so that they hold the same doubles, and uploaded."""
 import numpy as np
 import torch
 
 
-def set_x_and_k(n, L):
-    k = ((n//2+np.arange(n)) % n) - n//2
-    return (np.arange(n)+0.5)*L/n, 2*np.pi*k/L
+def cell_centres_and_wavenumbers(n, length):
+    """x_i = (i + 1/2) L/n and the angular wavenumbers 2 pi m/L in FFT order (m = 0..n/2-1, -n/2..-1)"""
+    m = np.rint(np.fft.fftfreq(n)*n)
+    return (np.arange(n)+0.5)*length/n, 2*np.pi*m/length
+
+
+def multipliers(nx, ny, Lx, Ly, dx, dy):
+    """(pv -> psi at corners, pv -> vorticity) on the [ny, nx] spectral grid; the mean mode of
+    psi is set to zero"""
+    kx = cell_centres_and_wavenumbers(nx, Lx)[1]
+    ky = cell_centres_and_wavenumbers(ny, Ly)[1]
+    KX, KY = np.meshgrid(kx, ky)
+    kmod = np.sqrt(KX**2+KY**2)
+    safe = kmod.copy()
+    safe[0, 0] = 1.                                  # no division by zero for the mean
+    to_corner = np.exp(1j*(KX*dx*0.5+KY*dy*0.5))     # half-cell shift: pv at centres, psi at corners
+    to_psi = -(1/safe)*to_corner
+    to_psi[0, 0] = 0.
+    return to_psi, kmod
 
 
 class Fourier(object):
     def __init__(self, param, grid, device):
-        dx, dy = grid.dx, grid.dy
-        self.nx, self.ny = param.nx, param.ny
-        self.Lx, self.Ly = param.Lx, param.Ly
         self.nh = param.nh
-        self.x, self.kx = set_x_and_k(self.nx, self.Lx)
-        self.y, self.ky = set_x_and_k(self.ny, self.Ly)
-        self.xx, self.yy = np.meshgrid(self.x, self.y)
-        self.kxx, self.kyy = np.meshgrid(self.kx, self.ky)
-        self.ktot = np.sqrt(self.kxx**2+self.kyy**2)
-        self.ktot[0, 0] = 1.          # avoid the division by zero of the mean mode
-        # half-cell shift in Fourier space: psi lives on cell corners, pv on cell centres
-        shift = np.exp(1j*(self.kxx*dx*0.5+self.kyy*dy*0.5))
-        self.pv2psi = -(1/self.ktot)*shift
-        self.pv2vor = self.ktot
-        self.pv2psi[0, 0] = 0.
-        self.ktot[0, 0] = 0.
+        self.nx, self.ny = param.nx, param.ny
+        self.x, self.kx = cell_centres_and_wavenumbers(param.nx, param.Lx)
+        self.y, self.ky = cell_centres_and_wavenumbers(param.ny, param.Ly)
+        self.pv2psi, self.pv2vor = multipliers(param.nx, param.ny, param.Lx, param.Ly, grid.dx, grid.dy)
+        self.ktot = self.pv2vor
         self.d_pv2psi = torch.from_numpy(np.ascontiguousarray(self.pv2psi)).to(device)
         self.d_pv2vor = torch.from_numpy(np.ascontiguousarray(self.pv2vor)).to(device)
 
     def invert(self, pv, psi, vor):
-        """pv, psi, vor: device tensors [nyl, nxl]; interiors of psi and vor are overwritten"""
-        nh = self.nh
-        hpv = torch.fft.fft2(pv[nh:-nh, nh:-nh])
-        psi[nh:-nh, nh:-nh] = torch.fft.ifft2(hpv*self.d_pv2psi).real
-        vor[nh:-nh, nh:-nh] = torch.fft.ifft2(hpv*self.d_pv2vor).real
+        """pv, psi, vor: device tensors [nyl, nxl]; the interiors of psi and vor are overwritten
+        (their halos are the caller's fill_halo, operators.py:411-412)"""
+        h = self.nh
+        inner = (slice(h, -h), slice(h, -h))
+        spectrum = torch.fft.fft2(pv[inner])
+        psi[inner] = torch.fft.ifft2(spectrum*self.d_pv2psi).real
+        vor[inner] = torch.fft.ifft2(spectrum*self.d_pv2vor).real

@@ -60,3 +60,13 @@ def check(a, b, strict, tol=1e-13, what=""):
 
 def libs():
     return [("strict", _lib.lib(strict=True), True), ("product", _lib.lib(strict=False), False)]
+
+
+def check_res(res, res_ref):
+    """the residual norm a solve reports against the oracle's: relative 1e-6 while it is a
+    meaningful number (> 1e-9); once the solve has converged to rounding level the norm is
+    rounding noise (an FMA build differs in the 4th digit at 5e-13), so absolute 1e-12"""
+    if abs(res_ref) > 1e-9:
+        assert abs(res - res_ref) <= 1e-6 * abs(res_ref), (res, res_ref)
+    else:
+        assert abs(res - res_ref) <= 1e-12, (res, res_ref)

@@ -194,7 +194,7 @@ def test_cycles_and_solve(L, kind, ny, nx, graphs, force_stored, notail, noctail
         nite, res = ctypes.c_int(), ctypes.c_double()
         lib.mg_solve(h, g.ptr(d), g.ptr(drhs), 1e-11, 4, ctypes.byref(nite), ctypes.byref(res), s)
         assert nite.value == nite_ref
-        np.testing.assert_allclose(res.value, res_ref, rtol=1e-6)
+        g.check_res(res.value, res_ref)
         g.check(g.host(d), pr, strict, tol=1e-11, what="solve")
         # zero right-hand side: returns (0, 0.) without touching psi (hierarchy.py:161-164)
         d = g.dev(psi0)

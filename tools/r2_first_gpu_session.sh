@@ -32,9 +32,9 @@ if [ "${1:-}" = "scaling" ]; then
   exit 0
 fi
 # 1. the late tests alone (line relaxation, BoussinesqTS, QG diagnosed), verbose, under a timeout
-timeout 900 python -m pytest tests/test_gpu_zz_late.py -m gpu -q -x 2>&1 | tail -30 | tee gpurun_out/late_tests.log
+timeout 900 python -m pytest tests/test_gpu_zz_late.py -m gpu -q 2>&1 | tail -60 | tee gpurun_out/late_tests.log
 # 2. the whole GPU suite
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/gpu_tests.log
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -40 | tee gpurun_out/gpu_tests.log
 # 3. how slow is the line relaxation (doublediffusion at its own size, 128 x 256)
 timeout 300 python - <<'PY' 2>&1 | tail -3 | tee gpurun_out/tridiag_time.log
 import sys, time, tempfile, io, contextlib

@@ -8,9 +8,11 @@ step plus the end-of-step full solve, diagnostics -- on the freedecay initial st
 4096^2 per GPU.  A "step" is one iteration of Fluid2d.loop(): set_dt, model.step,
 diagnostics.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--n 4096] [--tracers 1]
-    python bench.py --strong --n 16384 --gpus N --no-cpu     # SURVEY.md 8d case S5 (not the driver's line)
-    python bench.py --impl reference ...     # the CPU arm (oracle port on the host cores)
+    python bench.py [--steps K] [--warmup W] [--tracers 1]      # N=1: 4096^2 (SURVEY.md 8d case S1)
+    torchrun ... bench.py --gpus N ...     # N>1: case S5, 16384^2 GLOBAL split in N y-slabs (strong scaling)
+    python bench.py --strong --n 16384     # case S5 on one GPU (the parallel-efficiency denominator)
+    torchrun ... bench.py --gpus N --weak  # weak scaling: 4096^2 per GPU (round 1's line)
+    python bench.py --impl reference ...   # the CPU arm (oracle port on the host cores)
 
 One JSON line on stdout (rank 0); everything else goes to stderr.
 """
@@ -35,6 +37,95 @@ def b_alg(T, n_F):
 
 SMOOTH_BYTES_PER_CELL = 25.   # one Grid.smooth application: read x, b, mask; write x
 VCYCLE_BYTES_PER_CELL = 139.3
+
+
+def workload_string(n, T, strong, weak_world=1):
+    """config.workload -- the same string in the GPU arm and in the reference arm"""
+    where = "in total (global grid, y-slabs over the GPUs)" if strong else (
+        "per GPU" if weak_world > 1 else "on one GPU")
+    return ("Euler freedecay %dx%d perio %s (experiments/Twodim_turbulence), RK3_SSP, upwind5 + parabolic "
+            "splitting, 2 truncated MG inversions + full solve per step, T=%d advected tracer(s)" % (n, n, where, T))
+
+
+def kernel_bytes_per_cell(name):
+    """algorithmic bytes per cell of one launch of a tagged kernel (per
+    operator; matrix coefficients count 0, masks 1 B where the instantiation reads them), and
+    the number of cells the launch works on -- (None, None) for the latency-bound kernels"""
+    import re
+    m = re.match(r"k_smooth2<mode(\d),input(\d)(,peer)?> (\d+)x(\d+)", name)
+    if m:
+        mode, inp = int(m.group(1)), int(m.group(2))
+        b = {0: 24., 1: 16., 2: 18., 3: 26.}[inp]+(0. if mode == 1 else 1.)
+        return b, int(m.group(4))*int(m.group(5))
+    m = re.match(r"k_resid_restrict<mode(\d)(,peer)?> (\d+)x(\d+)", name)
+    if m:
+        return 18.+(0. if int(m.group(1)) == 1 else 1.), int(m.group(3))*int(m.group(4))
+    m = re.match(r"k_resid_sumsq<mode(\d)> (\d+)x(\d+)", name)
+    if m:
+        return 24.+(0. if int(m.group(1)) == 1 else 1.), int(m.group(2))*int(m.group(3))
+    m = re.match(r"k_restrict(<peer>)? (\d+)x(\d+)", name)
+    if m:
+        return 10., int(m.group(2))*int(m.group(3))
+    m = re.match(r"k_adv<upw\d,order\d,masked(\d)> (\d+)x(\d+)", name)
+    if m:
+        return 32.+float(m.group(1)), int(m.group(2))*int(m.group(3))
+    m = re.match(r"k_map_vec<(\d) in> (\d+) doubles", name)
+    if m:
+        return 8.*(int(m.group(1))+1), int(m.group(2))
+    m = re.match(r"k_elementwise (\d+) doubles", name)
+    if m:
+        return 16., int(m.group(1))
+    m = re.match(r"k_reduce1<nout(\d+)> (\d+)x(\d+)", name)
+    if m:
+        nout = int(m.group(1))
+        return (40. if nout == 8 else 8.), int(m.group(2))*int(m.group(3))
+    return None, None
+
+
+def kernel_table(lib, r, f2d, peak, shape, nsteps=2):
+    """per-kernel accounting of `nsteps` steps run WITHOUT CUDA graphs (f2d_prof_begin /
+    f2d_prof_report: a CUDA event behind every launch): share of the step, average duration,
+    achieved algorithmic GB/s and fraction of the measured HBM peak for each kernel"""
+    import ctypes
+    g = f2d.model.ope.gmg
+    lib.mg_set_graphs(g.h, 0)
+    loop_body(f2d)                              # first ungraphed step: lazy set-up outside the accounting
+    lib.prof_begin(r.stream)
+    for _ in range(nsteps):
+        loop_body(f2d)
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.prof_report(buf, len(buf))
+    lib.mg_set_graphs(g.h, 1)
+    rows = []
+    for ln in buf.value.decode().splitlines():
+        name, cnt, us = ln.split("\t")
+        rows.append([name, int(cnt), float(us)])
+    total = sum(x[2] for x in rows) or 1.
+    ny, nx = shape
+    out = []
+    for name, cnt, us in sorted(rows, key=lambda x: -x[2]):
+        bpc, cells = kernel_bytes_per_cell(name)
+        # f2d_* entry points without a tag work on the whole local grid
+        if bpc is None and name in ("f2d_mask_orthogradient", "f2d_celltocorner"):
+            bpc, cells = (32., ny*nx) if name == "f2d_mask_orthogradient" else (16., ny*nx)
+        avg = us/cnt
+        gbs = bpc*cells/(avg*1e-6)/1e9 if bpc else None
+        out.append({"kernel": name, "launches_per_step": cnt/float(nsteps), "share": us/total, "avg_us": avg,
+                    "alg_bytes_per_cell": bpc, "cells": cells, "achieved_gbs": gbs,
+                    "frac_of_peak": (gbs/peak if gbs else None)})
+    return out, total/nsteps
+
+
+def dram_traffic_table():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
+    capture (tools/ncu_dram_table.py writes the file); {} when absent"""
+    p = os.path.join(REPO, "profiles", "r02_kernel_dram_bytes.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return {}
+    return {}
 
 
 def log(*a):
@@ -157,7 +248,7 @@ def loop_body(f2d):
 # CPU arm: the oracle port (the reference's Fortran cannot be compiled here, so this is
 # kind "port"), all host threads, a bounded number of steps of the SAME workload
 # ---------------------------------------------------------------------------
-def cpu_arm(n, tracers, steps, warmup):
+def cpu_arm(n, tracers, steps, warmup, what=None):
     import types
     # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host
     # thread (the OpenMP runtime reads the variable when the oracle library is loaded, below)
@@ -186,25 +277,44 @@ def cpu_arm(n, tracers, steps, warmup):
         loop_body(f2d)
     dt = time.time()-t0
     return {"value": n*n*steps/dt, "unit": "cell-updates/s", "cores": cores, "kind": "port",
-            "sample": "%d steps (after %d warm-up) of the same %dx%d Euler freedecay workload, oracle C port "
-                      "with OpenMP on all host threads" % (steps, warmup, n, n),
-            "ms_per_step": 1e3*dt/steps}
+            "sample": what or ("%d steps (after %d warm-up) of the same %dx%d Euler freedecay workload, oracle C port "
+                               "with OpenMP on all host threads" % (steps, warmup, n, n)),
+            "ms_per_step": 1e3*dt/steps,
+            # the reference's own end-of-run figure (core/fluid2d.py:329-338): wall time per
+            # iteration per grid point, times the number of cores
+            "rescaled_time_core_s_per_cell_update": cores*dt/(steps*n*n)}
+
+
+def resolve_workload(args, world):
+    """(n, strong): N = 1 -> 4096^2 (S1); N > 1 -> 16384^2 global, strong scaling (S5) unless --weak"""
+    strong = bool(args.strong) or (world > 1 and not args.weak and not args.replicas)
+    n = args.n if args.n else (16384 if strong else 4096)
+    return n, strong
 
 
 def reference_main(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    steps = min(args.steps, 3)
-    warm = min(args.warmup, 1)
-    r = cpu_arm(args.n, args.tracers, steps, warm)
+    n, strong = resolve_workload(args, max(world, args.gpus))
+    # bounded sample: the 16384^2 field is a periodic tiling of one 4096^2 freedecay tile, and
+    # the host arm runs that tile (per-cell work identical; 86 GB of host arrays are not needed)
+    ns = min(n, 4096)
+    steps = max(1, min(args.steps, 40))
+    warm = max(1, min(args.warmup, 5))
+    what = None
+    if ns != n:
+        what = ("%d steps (after %d warm-up) of one %dx%d tile of the %dx%d workload (the field is that tile "
+                "repeated), oracle C port with OpenMP on all host threads" % (steps, warm, ns, ns, n, n))
+    r = cpu_arm(ns, args.tracers, steps, warm, what)
     line = {"impl": "reference", "metric": "cell_updates_per_s", "value": r["value"], "unit": r["unit"],
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"],
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": "Euler freedecay %dx%d perio, RK3_SSP, upwind5 parabolic, T=%d"
-                       % (args.n, args.n, args.tracers)},
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_string(n, args.tracers, strong, 1 if strong else max(world, args.gpus))},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample",
+                                               "rescaled_time_core_s_per_cell_update")},
             "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -212,6 +322,22 @@ def reference_main(args):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+def timed_steps(f2d, steps, torch, barrier, lib=None):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nites = []
+    barrier()
+    if lib is not None:
+        lib.launch_count_reset()
+    wall0 = time.time()
+    e0.record()
+    for _ in range(steps):
+        loop_body(f2d)
+        nites.append(f2d.model.ope.last_solve[0])
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1), nites, wall0, time.time()
+
+
 def gpu_main(args):
     import numpy as np
     import torch
@@ -237,18 +363,19 @@ def gpu_main(args):
     real_stdout = sys.stdout
     sys.stdout = sys.stderr
     sampler = ClockSampler(local) if rank == 0 else None     # child process, started well before the timed region
-    n, T = args.n, args.tracers
+    T = args.tracers
+    n, strong = resolve_workload(args, world)
     t0 = time.time()
     slabs = world > 1 and not args.replicas
-    strong = bool(args.strong)
     if strong and (args.replicas or n % world):
-        raise SystemExit("--strong: n must be a multiple of the number of GPUs (and no --replicas)")
+        raise SystemExit("strong scaling: n must be a multiple of the number of GPUs (and no --replicas)")
     rows = n//world if strong else n          # rows of this rank's slab
     total_cells = n*n if strong else world*n*n
     f2d = build_case(api, n, T, tempfile.mkdtemp(), world if slabs else 1, strong)
     model = f2d.model
     model.diagnostics(model.var, 0.)
     torch.cuda.synchronize()
+    mg_slab_levels = getattr(model.ope.gmg, "slab_levels", 0)
     log("[gpu %d] set-up %.1f s" % (rank, time.time()-t0))
 
     def barrier():
@@ -256,36 +383,34 @@ def gpu_main(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def maxranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
     for _ in range(args.warmup):
         loop_body(f2d)
     if sampler:
         sampler.wait_ready()
-    barrier()
     # ---- timed region: K steps, device timers, inputs (134 MB fields) exceed the 126 MB L2
-    lib.launch_count_reset()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    nites = []
-    wall0 = time.time()
-    e0.record()
-    for _ in range(args.steps):
-        loop_body(f2d)
-        nites.append(model.ope.last_solve[0])
-    e1.record()
-    barrier()
-    wall1 = time.time()
-    ms = e0.elapsed_time(e1)
+    ms, nites, wall0, wall1 = timed_steps(f2d, args.steps, torch, barrier, lib)
     launches = int(lib.launch_count())
     clocks = sampler.window(wall0, wall1) if sampler else None
-    if world > 1:
-        tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms = float(tmax.item())
+    ms = maxranks(ms)
     ms_step = ms/args.steps
     value = total_cells*args.steps/(ms*1e-3)
     n_F = float(np.mean(nites))
 
-    # ---- dominant kernel: the level-0 double Jacobi sweep (Grid.smooth), timed alone
+    # ---- per-kernel accounting of the same step without graphs (every rank: the slabs run in lock step)
     peak, peak_src = measured_peaks()
+    table, us_nograph = kernel_table(lib, r, f2d, peak, (rows, n))
+    dram = dram_traffic_table()
+    for row in table:
+        row["dram_bytes_per_launch"] = dram.get(row["kernel"])
+
+    # ---- the level-0 smoother and the V-cycle timed alone
     if slabs:
         # kernel-level numbers come from a single-GPU hierarchy of the slab's size on this rank
         cm = torch.ones((rows+6, n+6), dtype=torch.float64, device="cuda")
@@ -309,7 +434,7 @@ def gpu_main(args):
     s1.record()
     torch.cuda.synchronize()
     smooth_ms = s0.elapsed_time(s1)/(2*reps)
-    achieved = SMOOTH_BYTES_PER_CELL*rows*n/(smooth_ms*1e-3)/1e9
+    smooth_gbs = SMOOTH_BYTES_PER_CELL*rows*n/(smooth_ms*1e-3)/1e9
     # ---- V-cycle (metric part 2): one Vcycle(0) through its CUDA graph
     lib.mg_vcycle(mgh, 0, r.stream)
     torch.cuda.synchronize()
@@ -319,10 +444,10 @@ def gpu_main(args):
     s1.record()
     torch.cuda.synchronize()
     vcycle_ms = s0.elapsed_time(s1)/10
+    del x0, b0
 
     # ---- end to end: host buffers in, host buffers out, every step
     ds = model.var.dstate
-    nvar = ds.nvar
     _ = model.var.state            # materialise the pinned mirror
     for _ in range(2):
         ds._host_written(None)
@@ -331,6 +456,7 @@ def gpu_main(args):
     barrier()
     h2d0, d2h0 = ds.h2d_bytes, ds.d2h_bytes
     ke = min(args.steps, 5)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(ke):
         ds._host_written(None)     # the caller's (pinned) host state is the step's input ...
@@ -338,14 +464,34 @@ def gpu_main(args):
         _ = model.var.state        # ... and the new state is read back (D2H of every field)
     e1.record()
     barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    if world > 1:
-        tmax = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tmax.item())
+    e2e_ms = maxranks(e0.elapsed_time(e1))
     e2e = {"value": total_cells*ke/(e2e_ms*1e-3), "unit": "cell-updates/s",
            "h2d_bytes_per_step": (ds.h2d_bytes-h2d0)//ke, "d2h_bytes_per_step": (ds.d2h_bytes-d2h0)//ke,
            "ms_per_step": e2e_ms/ke, "steps": ke}
+
+    # ---- N = 1 only: SURVEY.md 8d case S5 on ONE GPU (16384^2, 86 GB), the denominator of the
+    # parallel efficiency of the N > 1 lines (which run 16384^2 split in N slabs)
+    s5 = None
+    if world == 1 and not strong and not args.no_s5 and n == 4096:
+        try:
+            del f2d, model, ds
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            t0 = time.time()
+            g = build_case(api, 16384, T, tempfile.mkdtemp(), 1, True)
+            g.model.diagnostics(g.model.var, 0.)
+            for _ in range(3):
+                loop_body(g)
+            ms5, nit5, _, _ = timed_steps(g, 5, torch, barrier)
+            s5 = {"workload": workload_string(16384, T, True), "n_gpus": 1, "steps": 5, "warmup": 3,
+                  "ms_per_step": ms5/5, "value": 16384.*16384.*5/(ms5*1e-3), "unit": "cell-updates/s",
+                  "n_F_mean": float(np.mean(nit5)), "setup_s": time.time()-t0}
+            del g
+            gc.collect()
+            torch.cuda.empty_cache()
+        except Exception as ex:   # a report next to the line, never a reason to lose the line
+            s5 = {"failed": repr(ex)}
 
     sys.stderr.flush()
     os.dup2(saved_fd1, 1)
@@ -359,33 +505,52 @@ def gpu_main(args):
     cpu = None
     if world == 1 and not args.no_cpu and not strong:
         try:
-            cpu = cpu_arm(n, T, 2, 1)
+            cpu = cpu_arm(n, T, 3, 1)
+            small = cpu_arm(1024, T, 20, 3)
+            cpu["also_1024"] = {k: small[k] for k in ("value", "ms_per_step", "rescaled_time_core_s_per_cell_update")}
         except Exception as ex:   # the baseline is a report, never a reason to lose the GPU line
             cpu = {"value": None, "unit": "cell-updates/s", "cores": 0, "kind": "port", "sample": "failed: %r" % ex}
     balg = b_alg(T, n_F)
+    # dominant kernel = the largest share of the step in the accounting above, among the
+    # bandwidth-bound kernels (the latency-bound tail is listed in the table without a roofline)
+    dom = next((row for row in table if row["achieved_gbs"]), None)
+    step_dram = None
+    if dram and all(row["dram_bytes_per_launch"] is not None for row in table if row["share"] > 0.01):
+        step_dram = sum((row["dram_bytes_per_launch"] or 0.)*row["launches_per_step"] for row in table)
     line = {
         "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Euler freedecay %dx%d perio %s (experiments/Twodim_turbulence), RK3_SSP, "
-                               "upwind5 + parabolic splitting, 2 truncated MG inversions + full solve per step, "
-                               "T=%d advected tracer(s)" % (n, n, "in total" if strong else "per GPU", T),
+        "config": {"workload": workload_string(n, T, strong, world),
                    "grid": [n, n], "tracers": T, "n_F_mean": n_F,
                    "parallelism": "single GPU" if world == 1 else (
-                       "%d y-slabs of %dx%d (global %dx%d), peer halo exchange over NVLink, coarse levels gathered"
-                       % (world, n, rows, n, rows*world) if slabs else "%d independent replicas" % world),
-                   "mg_slab_levels": getattr(model.ope.gmg, "slab_levels", 0),
+                       "%d y-slabs of %dx%d (global %dx%d), halo rows by peer stores over NVLink fused into the "
+                       "producing kernels, coarse levels gathered" % (world, n, rows, n, rows*world)
+                       if slabs else "%d independent replicas" % world),
+                   "mg_slab_levels": mg_slab_levels,
                    "cache": "working set %.1f GB >> 126 MB L2 (no flush needed)" % (40*(n+6)*(rows+6)*8/1e9)},
-        "roofline": {"bound": "hbm", "kernel": "k_smooth2<0,0,0> (Grid.smooth = double Jacobi sweep + halo fill, level 0)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 4096^2, from
-                     # profiles/r01_ncu_full_v10_two_vcycle_kernels.csv (269.1 MB + 104.2 MB; algorithmic
-                     # 420 MB: the mask-free level reads x and b, writes x; halo re-reads hit L2)
-                     "traffic": 3.733e8 if (n == 4096 and rows == 4096) else None,
-                     "peak_source": peak_src, "ms_per_launch": smooth_ms,
-                     "algorithmic_bytes_per_cell": SMOOTH_BYTES_PER_CELL},
+        "roofline": {"bound": "hbm",
+                     "kernel": dom["kernel"] if dom else None,
+                     "share_of_step": dom["share"] if dom else None,
+                     "achieved": dom["achieved_gbs"] if dom else None, "peak": peak, "unit": "GB/s",
+                     "frac": dom["frac_of_peak"] if dom else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture
+                     # committed under profiles/ (r02_kernel_dram_bytes.json); null without a capture
+                     "traffic": dom["dram_bytes_per_launch"] if dom else None,
+                     "peak_source": peak_src, "ms_per_launch": dom["avg_us"]*1e-3 if dom else None,
+                     "algorithmic_bytes_per_cell": dom["alg_bytes_per_cell"] if dom else None,
+                     "how": "CUDA events behind every launch of 2 steps run without CUDA graphs "
+                            "(f2d_prof_begin/report); achieved = algorithmic bytes per launch / average duration",
+                     "level0_smoother_alone": {"kernel": "k_smooth2<mode1,input0> (Grid.smooth, level 0)",
+                                               "ms_per_launch": smooth_ms, "achieved": smooth_gbs,
+                                               "frac": smooth_gbs/peak, "algorithmic_bytes_per_cell": SMOOTH_BYTES_PER_CELL}},
+        "kernels": [row for row in table if row["share"] >= 0.004],
+        "step_us_without_graphs": us_nograph,
         "step_hbm": {"b_alg_bytes_per_cell": balg, "achieved_gbs": balg*value/world/1e9,
-                     "frac_of_peak": balg*value/world/1e9/peak},
+                     "frac_of_peak": balg*value/world/1e9/peak,
+                     "note": "contract bytes (SURVEY.md 8d): fused kernels and the field-skipping RK maps move "
+                             "less than this; step_dram_bytes is what ncu saw",
+                     "step_dram_bytes": step_dram},
         "vcycle_ms": vcycle_ms,
         "vcycle_frac_of_peak": VCYCLE_BYTES_PER_CELL*rows*n/(vcycle_ms*1e-3)/1e9/peak,
         "cpu_baseline": cpu,
@@ -393,6 +558,8 @@ def gpu_main(args):
         "gpu_launches": launches,
         "clocks": clocks,
     }
+    if s5 is not None:
+        line["s5_one_gpu"] = s5
     print(json.dumps(line), flush=True)
 
 
@@ -402,12 +569,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=4096)
+    ap.add_argument("--n", type=int, default=0, help="grid size (default: 4096 on one GPU, 16384 global on several)")
     ap.add_argument("--tracers", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-s5", action="store_true", help="N=1: skip the 16384^2 single-GPU run")
     ap.add_argument("--replicas", action="store_true", help="N>1: independent replicas instead of slabs")
     ap.add_argument("--strong", action="store_true",
-                    help="strong scaling: --n is the GLOBAL grid (e.g. 16384), split in --gpus y-slabs")
+                    help="strong scaling: --n is the GLOBAL grid (default 16384), split in --gpus y-slabs "
+                         "(the default when N > 1)")
+    ap.add_argument("--weak", action="store_true", help="N>1: weak scaling, --n (4096) squared cells per GPU")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -226,6 +226,7 @@ int launch_adv_m(const int8_t *msk, const double *q, double *dq, const double *u
   }
   dim3 grid(cdiv(nx - 2 * NH, TX), cdiv(ny - 2 * NH, TY));
   const size_t sm = MASKED ? sizeof(AdvSmem) : offsetof(AdvSmem, m);
+  prof_tag("k_adv<upw%d,order%d,masked%d> %dx%d", (int)UPW, ORDER, (int)MASKED, nx - 2 * NH, ny - 2 * NH);
   k_adv<UPW, ORDER, MASKED><<<grid, NT, sm, s>>>(msk, q, dq, u, v, xflx, yflx, k, ny, nx, fill);
   F2D_LAUNCHED();
   return F2D_OK;

@@ -14,6 +14,15 @@ namespace f2d {
 extern char g_err[512];
 extern long long g_launches;
 
+// per-kernel accounting (f2d_prof_begin / f2d_prof_report): while it is on, every launch site
+// records a CUDA event behind its kernel on the profiled stream; the time between two
+// consecutive events is charged to the later kernel under the name given by prof_tag() (or
+// the launching function's name).  Meant for runs without CUDA graphs (graph replays launch
+// nothing from the host).
+extern bool g_prof;
+void prof_mark(const char *fallback);
+void prof_tag(const char *fmt, ...);
+
 inline int fail(int code, const char *msg) {
   snprintf(g_err, sizeof g_err, "%s", msg);
   return code;
@@ -33,6 +42,7 @@ inline int cuda_fail(cudaError_t e, const char *where) {
 #define F2D_LAUNCHED()                                          \
   do {                                                          \
     ++f2d::g_launches;                                          \
+    if (f2d::g_prof) f2d::prof_mark(__func__);                  \
     cudaError_t e__ = cudaPeekAtLastError();                    \
     if (e__ != cudaSuccess) return f2d::cuda_fail(e__, __func__); \
   } while (0)

@@ -72,6 +72,7 @@ int reduce(int nh, int ny, int nx, double *out, double *scratch, cudaStream_t s,
   if (!out || !scratch) return fail(F2D_ERR_ARG, "reduce: null out/scratch");
   if (ny <= 2 * nh || nx <= 2 * nh) return fail(F2D_ERR_ARG, "reduce: bad shape");
   int nblk = ny - 2 * nh < RB ? ny - 2 * nh : RB;
+  prof_tag("k_reduce1<nout%d> %dx%d", NOUT, nx - 2 * nh, ny - 2 * nh);
   k_reduce1<NOUT, MAXMASK><<<nblk, RT, 0, s>>>(ny, nx, nh, scratch, f);
   F2D_LAUNCHED();
   k_reduce2<NOUT, MAXMASK><<<1, RT, 0, s>>>(nblk, scratch, out, finish);

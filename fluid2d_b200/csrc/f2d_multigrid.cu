@@ -53,7 +53,8 @@ struct f2d_mg {
   bool tail_const = false;    // every tail level is in the constant-stencil class
   size_t tail_smem = 0;
   int tail_nt = tail::NT;     // threads of the one-CTA tail kernel (F2D_TAIL_NT)
-  bool ctail = false;         // the tail runs on a thread-block cluster (f2d_mg_ctail.cuh), from 128^2 down
+  bool ctail = false;         // the tail runs on a thread-block cluster (f2d_mg_ctail.cuh), from 256^2 / 128^2 down
+  int ctail_nc = 1;           // CTAs of that cluster (1 when no level of the tail is distributed)
   ctail::Params ctp;          // its level table (pointers / program filled per launch)
   long long *trace = nullptr; // f2d_mg_set_trace
   int trace_cap = 0;
@@ -493,6 +494,7 @@ int launch_smooth2(f2d_mg *mg, Level &l, Level *cl, const double *xin, const dou
   int use_tma = get_tmap(mg, b, l.ny, l.nx, fused::YH, fused::YW, &tmb);
   if (use_tma && (INPUT == 0 || INPUT == 3)) use_tma = get_tmap(mg, xin, l.ny, l.nx, fused::XH, fused::XP, &tmx);
   if (use_tma && INPUT >= 2) use_tma = get_tmap(mg, xc, nyc, nxc, fused::CH, fused::CP, &tmc);
+  prof_tag("k_smooth2<mode%d,input%d%s> %dx%d", l.mode, INPUT, peer ? ",peer" : "", l.nx - 2 * NH, l.ny - 2 * NH);
 #define F2D_SM2(M, St)                                                                                              \
   do {                                                                                                              \
     if (peer) fused::k_smooth2<M, St, INPUT, true><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc, acc, P, use_tma, tmx, tmb, tmc); \
@@ -590,6 +592,7 @@ int op_resid_sumsq_L(f2d_mg *mg, Level &l, const double *x, const double *b, dou
                      cudaStream_t s) {
   fused::LevelK k = level_k(mg, l);
   int nb = l.ny - 2 * NH < RSB ? l.ny - 2 * NH : RSB;
+  prof_tag("k_resid_sumsq<mode%d> %dx%d", l.mode, l.nx - 2 * NH, l.ny - 2 * NH);
   switch (l.mode) {
     case 1: k_resid_sumsq<false, false><<<nb, RST, 0, s>>>(k, x, b, r, mg->scratch); break;
     case 2: k_resid_sumsq<true, false><<<nb, RST, 0, s>>>(k, x, b, r, mg->scratch); break;
@@ -609,6 +612,7 @@ int op_restrict_L(f2d_mg *mg, Level &f, Level &c, const double *xf, double *xc, 
   f2d::Peer P = comm_peer(peer ? mg->comm : nullptr);
   if (peer && !comm_owns(mg->comm, xc))
     return fail(F2D_ERR_ARG, "restrict: the output of a slab level must live in the symmetric heap");
+  prof_tag("k_restrict%s %dx%d", peer ? "<peer>" : "", f.nx - 2 * NH, f.ny - 2 * NH);
   if (peer) k_restrict<true><<<grid2d(c.ny, c.nx, blk), blk, 0, s>>>(c.msk, xf, xc, c.ny, c.nx, f.nx, c.ywrap, P);
   else k_restrict<false><<<grid2d(c.ny, c.nx, blk), blk, 0, s>>>(c.msk, xf, xc, c.ny, c.nx, f.nx, c.ywrap, P);
   F2D_LAUNCHED();
@@ -636,6 +640,7 @@ int op_resid_restrict_L(f2d_mg *mg, Level &l, Level &c, const double *x, const d
   memset(&tmx, 0, sizeof tmx); memset(&tmb, 0, sizeof tmb);
   int use_tma = get_tmap(mg, x, l.ny, l.nx, fused::RXH, fused::RXP, &tmx);
   if (use_tma) use_tma = get_tmap(mg, b, l.ny, l.nx, fused::RH, fused::RBP, &tmb);
+  prof_tag("k_resid_restrict<mode%d%s> %dx%d", l.mode, peer ? ",peer" : "", l.nx - 2 * NH, l.ny - 2 * NH);
 #define F2D_RR(M, St)                                                                                         \
   do {                                                                                                        \
     if (peer) fused::k_resid_restrict<M, St, true><<<grid, fused::NT, sm, s>>>(k, x, b, bc, c.msk, c.ny, c.nx, P, use_tma, tmx, tmb); \
@@ -687,6 +692,10 @@ int coarsest_enqueue(f2d_mg *mg, double *X, const double *B, cudaStream_t s) {
 // 2 = F-cycle of the levels tail0..last; rhs b_in, result x_out (both of level tail0)
 int tail_launch(f2d_mg *mg, int program, const double *b_in, const double *x_in, double *x_out, cudaStream_t s,
                 double *acc = nullptr) {
+  {
+    Level &t0l = mg->L[mg->tail0];
+    prof_tag("%s<program%d> %dx%d", mg->ctail ? "k_mg_ctail" : "k_mg_tail", program, t0l.nx - 2 * NH, t0l.ny - 2 * NH);
+  }
   if (mg->ctail) {
     ctail::Params P = mg->ctp;
     P.b_in = b_in;
@@ -696,13 +705,13 @@ int tail_launch(f2d_mg *mg, int program, const double *b_in, const double *x_in,
     P.trace = mg->trace;
     P.trace_cap = mg->trace_cap;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ctail::NC);
+    cfg.gridDim = dim3(mg->ctail_nc);
     cfg.blockDim = dim3(ctail::NT);
     cfg.dynamicSmemBytes = mg->tail_smem;
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = ctail::NC;
+    at[0].val.clusterDim.x = mg->ctail_nc;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
@@ -1200,50 +1209,95 @@ int finish_setup(f2d_mg *mg, double Rd, cudaStream_t s) {
                                (int)mg->tail_smem));
     }
   }
-  // cluster tail: the deepest levels whose interior is at most 128 wide, on 8 SMs
+  // cluster tail (default): the deepest levels whose interior is at most F2D_CTAIL_MAXN (128)
+  // wide on a cluster of F2D_CTAIL_NC (16, else 8) CTAs; F2D_MG_NO_CTAIL=1 keeps the one-CTA tail
   {
-    // Opt-in (F2D_MG_CTAIL=1): measured on B200 it is not yet faster than the one-CTA tail plus
-    // the per-level kernels of the 128^2 level (55 us against 49 us per V-cycle of a 128^2
-    // hierarchy) -- its per-point passes go through the row-address table.
-    const char *notail = getenv("F2D_MG_NO_TAIL"), *noct = getenv("F2D_MG_NO_CTAIL"), *ct = getenv("F2D_MG_CTAIL");
-    int t0 = (int)mg->L.size();
-    while (t0 > 0) {
-      Level &l = mg->L[t0 - 1];
-      if (l.ny - 2 * NH > ctail::MAXN || l.nx - 2 * NH > ctail::MAXN) break;
-      if ((int)mg->L.size() - (t0 - 1) > ctail::MAXL) break;
-      t0--;
-    }
-    const bool off = (notail && notail[0] == '1') || (noct && noct[0] == '1') || !(ct && ct[0] == '1');
-    if (!off && t0 < (int)mg->L.size() && mg->L[t0].n() > (size_t)ctail::REPL_CELLS) {
-      ctail::Params &P = mg->ctp;
+    const char *notail = getenv("F2D_MG_NO_TAIL"), *noct = getenv("F2D_MG_NO_CTAIL");
+    const bool off = (notail && notail[0] == '1') || (noct && noct[0] == '1');
+    int maxn = 128, nc_want = ctail::MAXNC;   // measured on B200 (tools/trace_ctail.py): 16 CTAs from 128^2 down is the fastest
+    if (const char *e = getenv("F2D_CTAIL_MAXN")) maxn = atoi(e);
+    if (const char *e = getenv("F2D_CTAIL_NC")) nc_want = atoi(e);
+    if (nc_want != 16 && nc_want != 8 && nc_want != 4 && nc_want != 2 && nc_want != 1) nc_want = ctail::MAXNC;
+    long long mincells = 2048;   // smaller levels are replicated: a cluster barrier costs more than their sweeps
+    if (const char *e = getenv("F2D_CTAIL_MINCELLS")) mincells = atoll(e);
+    const size_t budget = 220 * 1024;
+    // level table for the levels [t0, last] on nc CTAs; returns the bytes of shared memory
+    auto plan = [&](int t0, int nc, ctail::Params &P) -> size_t {
       P = ctail::Params{};
       P.nlev = (int)mg->L.size() - t0;
-      int o = 0, rp = 0;
-      bool all_const = true;
+      int o = 0, tmax = 0;
       for (int k = 0; k < P.nlev; k++) {
         Level &l = mg->L[t0 + k];
-        P.lv[k] = level_k(mg, t0 + k);
-        P.dist[k] = l.n() > (size_t)ctail::REPL_CELLS ? 1 : 0;
-        P.rows[k] = (l.ny + ctail::NC - 1) / ctail::NC;
-        P.off[k] = o;
-        P.rp[k] = rp;
-        o += P.dist[k] ? P.rows[k] * l.nx : l.ny * l.nx;
-        if (P.dist[k]) rp += l.ny;
-        if (l.mode != 1) all_const = false;
+        const int m = l.ny - 2 * NH, n = l.nx - 2 * NH;
+        ctail::Lev &v = P.lv[k];
+        v.k = level_k(mg, t0 + k);
+        v.dist = (nc > 1 && m % nc == 0 && m / nc >= ctail::MINROWS && (long long)m * n >= mincells) ? 1 : 0;
+        v.R = v.dist ? m / nc : m;
+        v.off = o;
+        v.lgn = 0;
+        while ((1 << v.lgn) < n) v.lgn++;
+        int cells = (v.R + 2 * NH) * l.nx;
+        cells += cells & 1;
+        o += cells;
+        tmax = std::max(tmax, cells);
       }
-      P.total = o + (o & 1);
-      P.rptotal = rp;
+      P.total = o;
+      P.tsize = tmax;
       P.ndeepest = mg->ndeepest;
-      size_t smem = 3 * (size_t)P.total * sizeof(double) + 3 * (size_t)rp * sizeof(double *);
-      if (smem <= 220 * 1024) {
+      return (2 * (size_t)o + tmax) * sizeof(double);
+    };
+    if (!off && mg->L.size() >= 1) {
+      for (int nc = nc_want; nc >= 1 && !mg->ctail; nc = (nc == 16 ? 8 : (nc > 1 ? 1 : 0))) {
+        if (nc > 8) {
+          cudaError_t e1 = cudaFuncSetAttribute(ctail::k_mg_ctail<false, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+          cudaError_t e2 = cudaFuncSetAttribute(ctail::k_mg_ctail<true, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+          if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaGetLastError(); continue; }
+        }
+        int t0 = (int)mg->L.size();
+        ctail::Params P;
+        size_t smem = 0;
+        while (t0 > 0) {
+          Level &l = mg->L[t0 - 1];
+          if (l.ny - 2 * NH > maxn || l.nx - 2 * NH > maxn) break;
+          if ((int)mg->L.size() - (t0 - 1) > ctail::MAXL) break;
+          ctail::Params Q;
+          size_t need = plan(t0 - 1, nc, Q);
+          if (need > budget) break;
+          t0--;
+        }
+        if (t0 >= (int)mg->L.size()) continue;
+        smem = plan(t0, nc, P);
+        const int nc_launch = P.lv[0].dist ? nc : 1;
+        if (nc > 1 && nc_launch == 1) continue;   // nothing to distribute with this cluster size: try a smaller one
+        cudaError_t e1 = cudaFuncSetAttribute(ctail::k_mg_ctail<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e2 = cudaFuncSetAttribute(ctail::k_mg_ctail<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaGetLastError(); continue; }
+        if (nc_launch > 1) {
+          // can the device co-schedule such a cluster at all?
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3(nc_launch);
+          cfg.blockDim = dim3(ctail::NT);
+          cfg.dynamicSmemBytes = smem;
+          cudaLaunchAttribute at[1];
+          at[0].id = cudaLaunchAttributeClusterDimension;
+          at[0].val.clusterDim.x = nc_launch;
+          at[0].val.clusterDim.y = 1;
+          at[0].val.clusterDim.z = 1;
+          cfg.attrs = at;
+          cfg.numAttrs = 1;
+          int nclusters = 0;
+          cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, ctail::k_mg_ctail<false, false>, &cfg);
+          if (e != cudaSuccess || nclusters < 1) { cudaGetLastError(); continue; }
+        }
+        bool all_const = true;
+        for (size_t lev = t0; lev < mg->L.size(); lev++)
+          if (mg->L[lev].mode != 1) all_const = false;
         mg->ctail = true;
+        mg->ctail_nc = nc_launch;
+        mg->ctp = P;
         mg->tail0 = t0;
         mg->tail_smem = smem;
         mg->tail_const = all_const;
-        MGC(cudaFuncSetAttribute(ctail::k_mg_ctail<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
-        MGC(cudaFuncSetAttribute(ctail::k_mg_ctail<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
       }
     }
   }

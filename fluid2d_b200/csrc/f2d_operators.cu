@@ -1,11 +1,41 @@
 // Stencil operators of core/fortran_operators.f90, the periodic halo fill of
 // gmg/fortran_multigrid.f90:365-412, and the whole-state combinations of
 // core/timescheme.py -- memory-bound elementwise / 5-point kernels.
+#include <stdarg.h>
+#include <map>
+#include <string>
+#include <vector>
+
 #include "f2d_common.cuh"
 
 namespace f2d {
 char g_err[512] = "";
 long long g_launches = 0;
+bool g_prof = false;
+namespace {
+cudaStream_t g_prof_stream = nullptr;
+std::vector<std::pair<std::string, cudaEvent_t>> g_prof_marks;
+char g_prof_tag[160] = "";
+}  // namespace
+void prof_tag(const char *fmt, ...) {
+  if (!g_prof) return;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_prof_tag, sizeof g_prof_tag, fmt, ap);
+  va_end(ap);
+}
+void prof_mark(const char *fallback) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(g_prof_stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+    g_prof_tag[0] = 0;
+    return;
+  }
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, g_prof_stream);
+  g_prof_marks.emplace_back(g_prof_tag[0] ? g_prof_tag : fallback, e);
+  g_prof_tag[0] = 0;
+}
 }  // namespace f2d
 
 using namespace f2d;
@@ -14,6 +44,44 @@ extern "C" int f2d_abi_version(void) { return F2D_ABI_VERSION; }
 extern "C" const char *f2d_last_error(void) { return f2d::g_err; }
 extern "C" long long f2d_launch_count(void) { return f2d::g_launches; }
 extern "C" void f2d_launch_count_reset(void) { f2d::g_launches = 0; }
+
+extern "C" int f2d_prof_begin(f2d_stream_t s) {
+  for (auto &m : f2d::g_prof_marks) cudaEventDestroy(m.second);
+  f2d::g_prof_marks.clear();
+  f2d::g_prof_stream = S(s);
+  f2d::g_prof = true;
+  f2d::prof_mark("(begin)");
+  return F2D_OK;
+}
+extern "C" int f2d_prof_report(char *buf, size_t cap) {
+  if (!buf || cap < 2) return fail(F2D_ERR_ARG, "prof_report: no buffer");
+  f2d::g_prof = false;
+  F2D_CUDA(cudaStreamSynchronize(f2d::g_prof_stream));
+  std::map<std::string, std::pair<long long, double>> agg;   // name -> (launches, microseconds)
+  std::vector<std::string> order;
+  for (size_t k = 1; k < f2d::g_prof_marks.size(); k++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, f2d::g_prof_marks[k - 1].second, f2d::g_prof_marks[k].second);
+    auto it = agg.find(f2d::g_prof_marks[k].first);
+    if (it == agg.end()) {
+      order.push_back(f2d::g_prof_marks[k].first);
+      it = agg.emplace(f2d::g_prof_marks[k].first, std::make_pair(0LL, 0.)).first;
+    }
+    it->second.first++;
+    it->second.second += 1e3 * ms;
+  }
+  for (auto &m : f2d::g_prof_marks) cudaEventDestroy(m.second);
+  f2d::g_prof_marks.clear();
+  size_t used = 0;
+  buf[0] = 0;
+  for (auto &name : order) {
+    auto &v = agg[name];
+    int n = snprintf(buf + used, cap - used, "%s\t%lld\t%.3f\n", name.c_str(), v.first, v.second);
+    if (n < 0 || (size_t)n >= cap - used) { buf[used] = 0; break; }
+    used += (size_t)n;
+  }
+  return F2D_OK;
+}
 
 extern "C" int f2d_copy(void *dst, const void *src, size_t nbytes, f2d_stream_t s) {
   if (!dst || !src) return fail(F2D_ERR_ARG, "copy: null");
@@ -421,6 +489,7 @@ static int elementwise(size_t n, cudaStream_t s, F f) {
   int threads = 256;
   long long blocks = (long long)((n + threads - 1) / threads);
   if (blocks > 148LL * 16) blocks = 148LL * 16;
+  prof_tag("k_elementwise %zu doubles", n);
   k_elementwise<<<(int)blocks, threads, 0, s>>>(n, f);
   F2D_LAUNCHED();
   return F2D_OK;
@@ -481,6 +550,7 @@ static int map_fields(size_t n, cudaStream_t s, double *out, const double *const
   if (nvec) {
     long long blocks = (long long)((nvec + 511) / 512);
     if (blocks > 148LL * 8) blocks = 148LL * 8;
+    prof_tag("k_map_vec<%d in> %zu doubles", NIN, n);
     k_map_vec<NIN><<<(int)blocks, 256, 0, s>>>(nvec, reinterpret_cast<double2 *>(out), in, f);
     F2D_LAUNCHED();
   }

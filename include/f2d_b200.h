@@ -48,6 +48,13 @@ const char *f2d_last_error(void);
 /* number of kernels this library launched since load / since the last reset */
 long long f2d_launch_count(void);
 void f2d_launch_count_reset(void);
+/* Per-kernel accounting for bench.py's roofline table (no reference counterpart; the
+ * reference times whole phases with core/timers.py).  Between f2d_prof_begin(stream) and
+ * f2d_prof_report every kernel launched on `stream` is followed by a CUDA event; the report is
+ * one line "name<TAB>launches<TAB>microseconds" per kernel (instantiation and grid size in
+ * the name).  Run with CUDA graphs disabled (f2d_mg_set_graphs(h, 0)). */
+int f2d_prof_begin(f2d_stream_t stream);
+int f2d_prof_report(char *buf, size_t cap);
 
 /* plain device-to-device copy / fill of nbytes (numpy slice assignments of the
  * reference's Python, e.g. hierarchy.py:212-217, euler.py:115) */

@@ -44,3 +44,23 @@ def test_algorithmic_bytes_formula():
     assert abs(bench.b_alg(2, 2)-bench.b_alg(1, 2)-144.) < 1e-9
     peak, src = bench.measured_peaks()
     assert peak > 1000.
+
+
+def test_arms_name_the_same_workload_and_kernel_bytes():
+    sys.path.insert(0, REPO)
+    import bench
+    import argparse
+    # N = 1: 4096^2 (S1); N > 1: 16384^2 strong scaling (S5) unless --weak
+    a = argparse.Namespace(strong=False, weak=False, replicas=False, n=0)
+    assert bench.resolve_workload(a, 1) == (4096, False)
+    assert bench.resolve_workload(a, 8) == (16384, True)
+    a.weak = True
+    assert bench.resolve_workload(a, 8) == (4096, False)
+    assert "16384x16384" in bench.workload_string(16384, 1, True)
+    # algorithmic bytes per cell of the tagged kernels
+    assert bench.kernel_bytes_per_cell("k_smooth2<mode1,input3> 4096x4096") == (26., 4096*4096)
+    assert bench.kernel_bytes_per_cell("k_smooth2<mode2,input0,peer> 4096x512") == (25., 4096*512)
+    assert bench.kernel_bytes_per_cell("k_resid_restrict<mode1> 2048x2048") == (18., 2048*2048)
+    assert bench.kernel_bytes_per_cell("k_adv<upw1,order5,masked0> 4096x4096") == (32., 4096*4096)
+    assert bench.kernel_bytes_per_cell("k_map_vec<3 in> 1000 doubles") == (32., 1000)
+    assert bench.kernel_bytes_per_cell("k_mg_ctail<program0> 128x128") == (None, None)

@@ -49,13 +49,20 @@ def L(request):
     return _lib.lib(strict=request.param == "strict"), request.param == "strict"
 
 
-def make(lib, kind, ny, nx, Rd=0., force_stored=False, notail=False, noctail=False):
+def make(lib, kind, ny, nx, Rd=0., force_stored=False, notail=False, noctail=False, ctail_nc=None, ctail_mincells=None):
     import os
     import gpu_util as g
     os.environ["F2D_MG_FORCE_STORED"] = "1" if force_stored else "0"
     os.environ["F2D_MG_NO_TAIL"] = "1" if notail else "0"
     os.environ["F2D_MG_NO_CTAIL"] = "1" if noctail else "0"
-    os.environ["F2D_MG_CTAIL"] = "0" if noctail else "1"   # the cluster tail is opt-in
+    # cluster tail: CTAs per cluster (default 16) and the size below which a level is replicated
+    # (0: distribute every level with >= 4 rows per CTA, so that small test grids exercise the
+    # distributed-shared-memory paths too)
+    for key, val in (("F2D_CTAIL_NC", ctail_nc), ("F2D_CTAIL_MINCELLS", ctail_mincells)):
+        if val is None:
+            os.environ.pop(key, None)
+        else:
+            os.environ[key] = str(val)
     rng = np.random.default_rng(ny + nx)
     msk = cell_mask(kind, ny, nx, rng)
     cm = corner_mask(msk)
@@ -158,16 +165,22 @@ def test_matrix_classes(L):
 
 
 @pytest.mark.parametrize("kind,ny,nx", CASES)
-@pytest.mark.parametrize("graphs,force_stored,notail,noctail",
-                         [(0, False, False, False), (1, False, False, False), (1, True, False, False),
-                          (1, False, True, False), (1, False, False, True), (1, True, False, True)])
-def test_cycles_and_solve(L, kind, ny, nx, graphs, force_stored, notail, noctail):
+@pytest.mark.parametrize("graphs,force_stored,notail,noctail,ctail_nc,ctail_mincells",
+                         [(0, False, False, False, None, None), (1, False, False, False, None, None),
+                          (1, True, False, False, None, None), (1, False, True, False, None, None),
+                          (1, False, False, True, None, None), (1, True, False, True, None, None),
+                          (1, False, False, False, 16, 0), (1, True, False, False, 16, 0),
+                          (1, False, False, False, 8, 0), (1, True, False, False, 8, 0),
+                          (1, False, False, False, 4, 0), (1, False, False, False, 2, 0)])
+def test_cycles_and_solve(L, kind, ny, nx, graphs, force_stored, notail, noctail, ctail_nc, ctail_mincells):
     """graphs on/off; matrix class forced to 'stored'; coarse levels by the cluster tail
-    kernel (<= 128^2, 8 CTAs over distributed shared memory), by the one-CTA tail kernel
+    kernel (<= 256^2, 16 / 8 / 4 / 2 CTAs with ghost rows exchanged through distributed shared
+    memory; small levels distributed too when ctail_mincells = 0), by the one-CTA tail kernel
     (<= 64^2), or by the per-level kernels"""
     import gpu_util as g
     lib, strict = L
-    ref, h, rng = make(lib, kind, ny, nx, force_stored=force_stored, notail=notail, noctail=noctail)
+    ref, h, rng = make(lib, kind, ny, nx, force_stored=force_stored, notail=notail, noctail=noctail,
+                       ctail_nc=ctail_nc, ctail_mincells=ctail_mincells)
     s = g.stream()
     lib.mg_set_graphs(h, graphs)
     tol_cycle = 1e-12

@@ -113,9 +113,12 @@ constexpr int CW = XW / 2 + 2, CH = XH / 2 + 2;  // coarse tile for the fused in
 // one column earlier and are two columns wider; the tile proper sits at column offset 1.
 constexpr int XP = XW + 2, CP = CW + 2;
 
+// b is read by the very thread that applies the operator at a point, and by nobody else: it
+// goes from global memory straight into the registers of the column strip (one coalesced load
+// per strip row, shared by both sweeps) instead of through a shared-memory tile -- 18 KB less
+// shared memory per CTA and two shared loads less per point.
 struct Smooth2Smem {
   alignas(128) double xs[XH][XP];   // TMA destinations: 128-byte aligned, dense boxes
-  alignas(128) double bs[YH][YW];
   // the coarse tile is dead once the interpolation pass has folded it into xs (a block
   // barrier later sweep 1 starts writing y1): the two share their storage
   union {
@@ -182,9 +185,10 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // the 3x3 window is carried in registers, so each point costs three shared loads.  GUARD:
 // per-point range test [lo, n-1-lo] (rim tiles); the fast path has none.  out(k, val)
 // consumes row k (called for in-range points only).
-template <bool MASKED, bool STORED, bool ZERO, bool GUARD, int NR, int SLD, int BLD, int MLD, class OUT>
+// bget(k): the right-hand side of row k (registers).
+template <bool MASKED, bool STORED, bool ZERO, bool GUARD, int NR, int SLD, int MLD, class BGET, class OUT>
 __device__ __forceinline__ void jacobi_strip(const LevelK &L, const Coefs<MASKED, STORED> &kc, const double *sp,
-                                             const double *bp, const int8_t *mp, int nr, int j, int i, int lo,
+                                             BGET bget, const int8_t *mp, int nr, int j, int i, int lo,
                                              OUT out) {
   const int ny = L.ny, nx = L.nx;
   const size_t g = (size_t)j * nx + i;
@@ -204,7 +208,7 @@ __device__ __forceinline__ void jacobi_strip(const LevelK &L, const Coefs<MASKED
         if (!MASKED || mp[k * MLD] != 0) {
           Coefs<MASKED, STORED> kk;
           if (MASKED || STORED) kk.load(L, g + (size_t)k * nx, MASKED ? mp + k * MLD : nullptr, MLD); else kk = kc;
-          val = jacobi_val<MASKED, STORED>(L, kk, a0, a1, a2, m0, m1, m2, h0, h1, h2, bp[k * BLD]);
+          val = jacobi_val<MASKED, STORED>(L, kk, a0, a1, a2, m0, m1, m2, h0, h1, h2, bget(k));
         }
         out(k, val);
       }
@@ -224,12 +228,11 @@ template <bool MASKED, bool STORED, int INPUT, bool PEER>
 __global__ void __launch_bounds__(NT)
 k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b, double *__restrict__ xout,
           const double *__restrict__ xc, const int8_t *__restrict__ mskc, int nxc, int nyc, double *acc,
-          f2d::Peer P, int use_tma, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmb,
-          const __grid_constant__ CUtensorMap tmc) {
+          f2d::Peer P, int use_tma, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smooth2Smem &S = *reinterpret_cast<Smooth2Smem *>(smem_raw);
   const int ny = L.ny, nx = L.nx;
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int t = threadIdx.x;
   const int by = PEER ? f2d::peer_tile_row(blockIdx.y, gridDim.y) : blockIdx.y;
   const bool bsouth = PEER && by == 0, bnorth = PEER && by == (int)gridDim.y - 1;
   if (PEER && (bsouth || bnorth)) f2d::peer_wait(P, bsouth, bnorth);
@@ -240,6 +243,26 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
   const int cj0 = ((j0 - 2) >> 1) + 1, ci0 = ((i0 - 2) >> 1) + 1;
   // inner tile: every point of the sweep-1 ring and of the output tile is a valid target
   const bool inner = (j0 + TY <= ny - 3) && (i0 + TX <= nx - 3);
+  // ---- column strips.  Thread (tx, tg) owns column i0 + tx: in sweep 1 the rows
+  // j0-1+r1 .. (9, 8, 8, 9 rows: the 34 rows of the tile + ring 1), in sweep 2 the 8 tile rows
+  // among them -- so the b of its points is loaded once, into registers, for both sweeps.
+  // The two ring columns i0-1 and i0+TX of sweep 1 are done point-wise by the first 68 threads.
+  const int tx = t & (TX - 1), tg = t >> 6;  // TX == 64
+  const int r1 = tg * 8 + (tg > 0 ? 1 : 0);  // first sweep-1 row (y1 tile coordinates): 0, 9, 17, 25
+  const int n1 = (tg == 0 || tg == 3) ? 9 : 8;
+  double bv[9], bx = 0.;
+  auto load_b = [&]() {
+    const int i = i0 + tx;
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      const int j = j0 - 1 + r1 + k;
+      bv[k] = (k < n1 && (inner || (j < ny && i < nx))) ? b[(size_t)j * nx + i] : 0.;
+    }
+    if (t < YH * 2) {
+      const int j = j0 - 1 + (t >> 1), ii = (t & 1) ? i0 + TX : i0 - 1;
+      if (j < ny && ii < nx) bx = b[(size_t)j * nx + ii];
+    }
+  };
   // ---- stage the tiles: TMA boxes (one instruction per tile, zero fill outside the
   // array) or, on levels smaller than a box, per-element asynchronous copies
   if (use_tma) {
@@ -248,16 +271,16 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
     if (t == 0) {
       // (PEER) the neighbour's halo rows were observed through the generic proxy
       if (PEER) asm volatile("fence.proxy.async;" ::: "memory");
-      constexpr unsigned bytes = (HAVE_X ? XH * XP * 8 : 0) + YH * YW * 8 + (INTERP ? CH * CP * 8 : 0);
-      f2d::mbar_expect_tx(&S.bar, bytes);
+      constexpr unsigned bytes = (HAVE_X ? XH * XP * 8 : 0) + (INTERP ? CH * CP * 8 : 0);
+      if (bytes) f2d::mbar_expect_tx(&S.bar, bytes);
       if (HAVE_X) f2d::tma_load_2d(&S.xs[0][0], &tmx, &S.bar, i0 - 3, j0 - 2);
-      f2d::tma_load_2d(&S.bs[0][0], &tmb, &S.bar, i0 - 1, j0 - 1);
       if (INTERP) f2d::tma_load_2d(&S.cs[0][0], &tmc, &S.bar, ci0 - 1, cj0);
     }
     const int vr = ny - (j0 - 2), vc = nx - (i0 - 2);
     if (INTERP && MASKED) load_tile_i8<CH, CW, CW>(&S.cm[0][0], mskc + (size_t)cj0 * nxc + ci0, nxc, nyc - cj0, nxc - ci0);
     if (MASKED) load_tile_i8<XH, XW, XW>(&S.ms[0][0], L.msk + (size_t)(j0 - 2) * nx + (i0 - 2), nx, vr, vc);
-    f2d::mbar_wait(&S.bar, 0);
+    load_b();
+    if (HAVE_X || INTERP) f2d::mbar_wait(&S.bar, 0);
   } else {
     const int vr = ny - (j0 - 2), vc = nx - (i0 - 2);
     if (HAVE_X) {
@@ -265,14 +288,12 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
       if (inner) load_tile<XH, XW, XP, true>(&S.xs[0][1], src, nx, 0, 0);
       else load_tile<XH, XW, XP, false>(&S.xs[0][1], src, nx, vr, vc);
     }
-    const double *bsrc = b + (size_t)(j0 - 1) * nx + (i0 - 1);
-    if (inner) load_tile<YH, YW, YW, true>(&S.bs[0][0], bsrc, nx, 0, 0);
-    else load_tile<YH, YW, YW, false>(&S.bs[0][0], bsrc, nx, vr - 1, vc - 1);
     if (INTERP) {
       load_tile<CH, CW, CP, false>(&S.cs[0][1], xc + (size_t)cj0 * nxc + ci0, nxc, nyc - cj0, nxc - ci0);
       if (MASKED) load_tile_i8<CH, CW, CW>(&S.cm[0][0], mskc + (size_t)cj0 * nxc + ci0, nxc, nyc - cj0, nxc - ci0);
     }
     if (MASKED) load_tile_i8<XH, XW, XW>(&S.ms[0][0], L.msk + (size_t)(j0 - 2) * nx + (i0 - 2), nx, vr, vc);
+    load_b();
     cp_async_wait_all();
   }
   __syncthreads();
@@ -316,29 +337,26 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
     __syncthreads();
   }
   // ---- sweep 1 on the tile + ring 1, restricted to [2, n-3] (all that sweep 2 reads).
-  // Thread (tx, tg) takes column tx of the y1 tile and a run of rows (9,9,8,8); the two
-  // extra columns of the ring are done point-wise afterwards.
-  const int tx = t & (TX - 1), tg = t >> 6;  // TX == 64
   Coefs<MASKED, STORED> kc;
   if (!MASKED && !STORED) kc.load(L, 0, nullptr, 0);
   {
-    const int r0 = tg * 8 + (tg < 2 ? tg : 2), nr = tg < 2 ? 9 : 8;
-    const int j = j0 - 1 + r0, i = i0 - 1 + tx;
-    const double *sp = &S.xs[r0 + 1][tx + 2];
-    const double *bp = &S.bs[r0][tx];
-    const int8_t *mp = &S.ms[r0 + 1][tx + 1];
-    double *yp = &S.y1[r0][tx];
+    const int j = j0 - 1 + r1, i = i0 + tx;
+    const double *sp = &S.xs[r1 + 1][tx + 3];
+    const int8_t *mp = &S.ms[r1 + 1][tx + 2];
+    double *yp = &S.y1[r1][tx + 1];
     auto out = [&](int k, double val) { yp[k * YW] = val; };
+    auto bget = [&](int k) { return bv[k]; };
     if (inner)
-      jacobi_strip<MASKED, STORED, ZERO, false, 9, XP, YW, XW>(L, kc, sp, bp, mp, nr, j, i, 2, out);
+      jacobi_strip<MASKED, STORED, ZERO, false, 9, XP, XW>(L, kc, sp, bget, mp, n1, j, i, 2, out);
     else
-      jacobi_strip<MASKED, STORED, ZERO, true, 9, XP, YW, XW>(L, kc, sp, bp, mp, nr, j, i, 2, out);
-    if (t < YH * 2) {   // ring columns TX, TX+1 of the y1 tile
-      const int r = t >> 1, q = TX + (t & 1);
+      jacobi_strip<MASKED, STORED, ZERO, true, 9, XP, XW>(L, kc, sp, bget, mp, n1, j, i, 2, out);
+    if (t < YH * 2) {   // ring columns 0 and YW-1 of the y1 tile
+      const int r = t >> 1, q = (t & 1) ? YW - 1 : 0;
       double *y = &S.y1[r][q];
       auto out1 = [&](int, double val) { *y = val; };
-      jacobi_strip<MASKED, STORED, ZERO, true, 1, XP, YW, XW>(L, kc, &S.xs[r + 1][q + 2], &S.bs[r][q],
-                                                              &S.ms[r + 1][q + 1], 1, j0 - 1 + r, i0 - 1 + q, 2, out1);
+      auto bget1 = [&](int) { return bx; };
+      jacobi_strip<MASKED, STORED, ZERO, true, 1, XP, XW>(L, kc, &S.xs[r + 1][q + 2], bget1, &S.ms[r + 1][q + 1], 1,
+                                                          j0 - 1 + r, i0 - 1 + q, 2, out1);
     }
   }
   __syncthreads();
@@ -379,12 +397,14 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
       }
     };
     const double *sp = &S.y1[r0 + 1][tx + 1];
-    const double *bp = &S.bs[r0 + 1][tx + 1];
     const int8_t *mp = &S.ms[r0 + 2][tx + 2];
+    // tile row k of this strip is row k + 1 of the first group's sweep-1 strip (which starts on
+    // the ring), row k of the others'
+    auto bget = [&](int k) { return tg == 0 ? bv[k + 1] : bv[k]; };
     if (inner)
-      jacobi_strip<MASKED, STORED, false, false, 8, YW, YW, XW>(L, kc, sp, bp, mp, 8, j, i, NH, out);
+      jacobi_strip<MASKED, STORED, false, false, 8, YW, XW>(L, kc, sp, bget, mp, 8, j, i, NH, out);
     else
-      jacobi_strip<MASKED, STORED, false, true, 8, YW, YW, XW>(L, kc, sp, bp, mp, 8, j, i, NH, out);
+      jacobi_strip<MASKED, STORED, false, true, 8, YW, XW>(L, kc, sp, bget, mp, 8, j, i, NH, out);
   }
   if (PEER && (bsouth || bnorth)) f2d::peer_done(P, gridDim.x * (gridDim.y == 1 ? 1u : 2u));
 }

@@ -489,16 +489,16 @@ int launch_smooth2(f2d_mg *mg, Level &l, Level *cl, const double *xin, const dou
   f2d::Peer P = comm_peer(peer ? mg->comm : nullptr);
   if (peer && !comm_owns(mg->comm, acc ? acc : xout))
     return fail(F2D_ERR_ARG, "smooth: the output of a slab level must live in the symmetric heap");
-  CUtensorMap tmx, tmb, tmc;
-  memset(&tmx, 0, sizeof tmx); memset(&tmb, 0, sizeof tmb); memset(&tmc, 0, sizeof tmc);
-  int use_tma = get_tmap(mg, b, l.ny, l.nx, fused::YH, fused::YW, &tmb);
+  CUtensorMap tmx, tmc;
+  memset(&tmx, 0, sizeof tmx); memset(&tmc, 0, sizeof tmc);
+  int use_tma = mg->tma ? 1 : 0;   // (INPUT == 1 stages nothing but the masks: either path does)
   if (use_tma && (INPUT == 0 || INPUT == 3)) use_tma = get_tmap(mg, xin, l.ny, l.nx, fused::XH, fused::XP, &tmx);
   if (use_tma && INPUT >= 2) use_tma = get_tmap(mg, xc, nyc, nxc, fused::CH, fused::CP, &tmc);
   prof_tag("k_smooth2<mode%d,input%d%s> %dx%d", l.mode, INPUT, peer ? ",peer" : "", l.nx - 2 * NH, l.ny - 2 * NH);
 #define F2D_SM2(M, St)                                                                                              \
   do {                                                                                                              \
-    if (peer) fused::k_smooth2<M, St, INPUT, true><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc, acc, P, use_tma, tmx, tmb, tmc); \
-    else fused::k_smooth2<M, St, INPUT, false><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc, acc, P, use_tma, tmx, tmb, tmc);     \
+    if (peer) fused::k_smooth2<M, St, INPUT, true><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc, acc, P, use_tma, tmx, tmc); \
+    else fused::k_smooth2<M, St, INPUT, false><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc, acc, P, use_tma, tmx, tmc);     \
   } while (0)
   switch (l.mode) {
     case 1: F2D_SM2(false, false); break;

@@ -14,26 +14,38 @@ long long g_launches = 0;
 bool g_prof = false;
 namespace {
 cudaStream_t g_prof_stream = nullptr;
-std::vector<std::pair<std::string, cudaEvent_t>> g_prof_marks;
+struct ProfMark { std::string name; cudaEvent_t start, end; };   // start == nullptr: the previous mark's end
+std::vector<ProfMark> g_prof_marks;
 char g_prof_tag[160] = "";
+cudaEvent_t g_prof_start = nullptr;
+bool prof_capturing() {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  return cudaStreamIsCapturing(g_prof_stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone;
+}
 }  // namespace
+// names the next launch and records its start: an event recorded in front of a kernel carries
+// the time the stream reached it, so a host that issues launches slower than the device runs
+// them does not inflate the kernel's figure
 void prof_tag(const char *fmt, ...) {
-  if (!g_prof) return;
+  if (!g_prof || prof_capturing()) return;
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_prof_tag, sizeof g_prof_tag, fmt, ap);
   va_end(ap);
+  if (g_prof_start) cudaEventDestroy(g_prof_start);
+  g_prof_start = nullptr;
+  if (cudaEventCreate(&g_prof_start) == cudaSuccess) cudaEventRecord(g_prof_start, g_prof_stream);
 }
 void prof_mark(const char *fallback) {
-  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(g_prof_stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+  if (prof_capturing()) {
     g_prof_tag[0] = 0;
     return;
   }
   cudaEvent_t e;
   if (cudaEventCreate(&e) != cudaSuccess) return;
   cudaEventRecord(e, g_prof_stream);
-  g_prof_marks.emplace_back(g_prof_tag[0] ? g_prof_tag : fallback, e);
+  g_prof_marks.push_back(ProfMark{g_prof_tag[0] ? g_prof_tag : fallback, g_prof_tag[0] ? g_prof_start : nullptr, e});
+  if (g_prof_tag[0]) g_prof_start = nullptr;
   g_prof_tag[0] = 0;
 }
 }  // namespace f2d
@@ -46,7 +58,10 @@ extern "C" long long f2d_launch_count(void) { return f2d::g_launches; }
 extern "C" void f2d_launch_count_reset(void) { f2d::g_launches = 0; }
 
 extern "C" int f2d_prof_begin(f2d_stream_t s) {
-  for (auto &m : f2d::g_prof_marks) cudaEventDestroy(m.second);
+  for (auto &m : f2d::g_prof_marks) {
+    cudaEventDestroy(m.end);
+    if (m.start) cudaEventDestroy(m.start);
+  }
   f2d::g_prof_marks.clear();
   f2d::g_prof_stream = S(s);
   f2d::g_prof = true;
@@ -61,16 +76,20 @@ extern "C" int f2d_prof_report(char *buf, size_t cap) {
   std::vector<std::string> order;
   for (size_t k = 1; k < f2d::g_prof_marks.size(); k++) {
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, f2d::g_prof_marks[k - 1].second, f2d::g_prof_marks[k].second);
-    auto it = agg.find(f2d::g_prof_marks[k].first);
+    const auto &mk = f2d::g_prof_marks[k];
+    cudaEventElapsedTime(&ms, mk.start ? mk.start : f2d::g_prof_marks[k - 1].end, mk.end);
+    auto it = agg.find(mk.name);
     if (it == agg.end()) {
-      order.push_back(f2d::g_prof_marks[k].first);
-      it = agg.emplace(f2d::g_prof_marks[k].first, std::make_pair(0LL, 0.)).first;
+      order.push_back(mk.name);
+      it = agg.emplace(mk.name, std::make_pair(0LL, 0.)).first;
     }
     it->second.first++;
     it->second.second += 1e3 * ms;
   }
-  for (auto &m : f2d::g_prof_marks) cudaEventDestroy(m.second);
+  for (auto &m : f2d::g_prof_marks) {
+    cudaEventDestroy(m.end);
+    if (m.start) cudaEventDestroy(m.start);
+  }
   f2d::g_prof_marks.clear();
   size_t used = 0;
   buf[0] = 0;

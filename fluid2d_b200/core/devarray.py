@@ -122,6 +122,8 @@ class TrackedArray(np.ndarray):
         return res
 
     def fill(self, value):
+        if self._own is not None:
+            self._own[0]._wait_upload()
         np.ndarray.fill(self, value)
         self._after_write()
 
@@ -206,6 +208,14 @@ class DeviceState(object):
         self.shape = (nvar, ny, nx)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self._upload_evt = None    # CUDA event behind the last asynchronous upload from the mirror
+
+    def _wait_upload(self):
+        """an upload from the pinned mirror is asynchronous: the host must not write the mirror
+        again while the DMA may still be reading it"""
+        if self._upload_evt is not None:
+            self._upload_evt.synchronize()
+            self._upload_evt = None
 
     # -- host side -----------------------------------------------------------
     def _ensure_host(self):
@@ -222,6 +232,7 @@ class DeviceState(object):
 
     def _refresh_host(self, k=None):
         self._ensure_host()
+        self._wait_upload()        # every host write passes through here first (TrackedArray._before_read)
         todo = [f for f in self._fields(k) if not self.host_fresh[f]]
         if not todo:
             return
@@ -254,6 +265,13 @@ class DeviceState(object):
 
     def __setitem__(self, k, value):
         if isinstance(k, (int, np.integer)):
+            own = getattr(value, '_own', None)
+            if isinstance(value, TrackedArray) and own is not None and own[0] is self and own[1] == int(k) \
+                    and value.shape == (self.ny, self.nx) and value.flags['C_CONTIGUOUS'] \
+                    and self._host is not None and value.ctypes.data == self._host[int(k)].ctypes.data:
+                # `state[k] += a` ends with `state[k] = <the view it just updated in place>`: the
+                # in-place operation (host or device) has already recorded who holds the fresh copy
+                return
             v = self.host_view(int(k))
             if not (isinstance(value, np.ndarray) and np.shares_memory(value, v)):
                 np.ndarray.__setitem__(v, slice(None), np.asarray(value))
@@ -264,11 +282,16 @@ class DeviceState(object):
 
     # -- device side ---------------------------------------------------------
     def to_device(self, k=None):
+        moved = False
         for f in self._fields(k):
             if not self.dev_fresh[f]:
                 self.dev[f].copy_(self._host_t[f], non_blocking=True)
                 self.dev_fresh[f] = True
                 self.h2d_bytes += self.fieldbytes
+                moved = True
+        if moved and self.device.type == 'cuda':
+            self._upload_evt = torch.cuda.Event()
+            self._upload_evt.record()
 
     def rptr(self, k):
         """device address of field k for reading"""

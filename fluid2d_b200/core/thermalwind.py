@@ -23,6 +23,11 @@ class Thermalwind(object):
         adopt(self, grid, FROM_GRID)
         if self.noslip:
             raise NotImplementedError('thermalwind: the reference defines no add_noslip for this model')
+        if param.npx*param.npy != 1:
+            # rhs_thermalwind / compute_pv fill halos by a local periodic wrap and extrapolate the y
+            # boundary rows on every rank (the reference's diffz does so on the first / last rank
+            # only, operators.py:330-394): not decomposed over slabs
+            raise NotImplementedError('thermalwind: this model runs on one GPU (npx = npy = 1)')
         declare_state(param, grid, ['vorticity', 'psi', 'u', 'v', 'buoyancy', 'V', 'qE'],
                       ['vorticity', 'buoyancy', 'V'], 'vorticity',
                       more_tracers=getattr(self, 'additional_tracer', ()))

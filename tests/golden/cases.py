@@ -51,7 +51,7 @@ def freedecay(api, datadir, n=64, order=5, tracer=True, timestepping='RK3_SSP', 
     param.dtmax = 10.
     param.order = order
     param.timestepping = timestepping
-    param.var_to_save = ['vorticity', 'psi', 'tracer']
+    param.var_to_save = ['vorticity', 'psi', 'tracer'] if tracer else ['vorticity', 'psi']
     param.forcing = False
     param.noslip = False
     param.diffusion = False

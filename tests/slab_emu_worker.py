@@ -32,11 +32,42 @@ def glue(emu, stack):
     return np.stack([np.concatenate([p[0][:3]]+[q[3:-3] for q in p]+[p[-1][-3:]], axis=0) for p in parts])
 
 
+def history_per_rank(api, out, nx, ny, nsteps, world):
+    """Fluid2d.loop() on slabs: EVERY rank writes its own history file, record by record, while
+    the loop runs (output.py:24-31,77-95); only the diagnostics file belongs to rank 0"""
+    import torch.distributed as dist
+    import output
+    with contextlib.redirect_stdout(io.StringIO()):
+        f2d = BUILDERS["freedecay"](api, tempfile.mkdtemp(), nx, ny, world)
+        o = f2d.output
+        o.freq_his = o.freq_diag = 0.
+        o.tnexthis = o.tnextdiag = 0.
+        f2d.exacthistime = False
+        f2d.loop(nsteps=nsteps, joinhis=False)        # not even the end-of-run dump: the records are on disk already
+    rank = dist.get_rank()
+    his = output.load_records(o.hisfile)
+    state = np.array(f2d.model.var.state, copy=True)
+    k = f2d.model.var.index("vorticity")
+    report = {"rank": rank, "hisfile": os.path.basename(o.hisfile), "exists": os.path.exists(o.hisfile),
+              "nrec": int(len(his["t"])), "shape": list(his["vorticity"].shape),
+              "last_is_my_slab": bool(np.array_equal(his["vorticity"][-1], state[k][3:-3, 3:-3].astype(np.float32))),
+              "diag_exists": os.path.exists(o.diagfile)}
+    everyone = [None]*world
+    dist.all_gather_object(everyone, report)
+    if rank == 0:
+        json.dump(everyone, open(out, "w"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     out, nx, ny, nsteps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
-    build = BUILDERS[sys.argv[5] if len(sys.argv) > 5 else "freedecay"]
+    case = sys.argv[5] if len(sys.argv) > 5 else "freedecay"
     world = int(os.environ["WORLD_SIZE"])
     api, emu = emu_device.install()
+    if case == "freedecay_his":
+        return history_per_rank(api, out, nx, ny, nsteps, world)
+    build = BUILDERS[case]
     with contextlib.redirect_stdout(io.StringIO()):
         f2d = build(api, tempfile.mkdtemp(), nx, ny, world)
         res = cases.run_steps(f2d, (nsteps,))[nsteps]

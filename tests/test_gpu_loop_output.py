@@ -13,11 +13,8 @@ import cases  # noqa: E402
 
 
 def _load(path):
-    if path.endswith(".npz"):
-        return dict(np.load(path))
-    from netCDF4 import Dataset
-    with Dataset(path) as nc:
-        return {k: np.array(v[:]) for k, v in nc.variables.items()}
+    import output
+    return output.load_records(path)
 
 
 @pytest.mark.parametrize("diag_fluxes", [False, True])

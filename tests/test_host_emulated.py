@@ -100,7 +100,8 @@ def test_emulator_covers_the_entry_points_the_host_layer_binds():
 
 
 def _load(path):
-    return dict(np.load(path))
+    import output
+    return output.load_records(path)
 
 
 def test_loop_writes_history_and_diagnostics_on_emulated_abi(emu):

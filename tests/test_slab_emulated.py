@@ -42,3 +42,24 @@ def test_slabs_reproduce_single_rank_run(tmp_path, case, nx, ny, nsteps, nranks)
         assert rep["solve"][0] == r0["one"]["solve"][0]
         for k, v in r0["one"]["diags"].items():      # sums folded in rank order (a cancelling sum is rounding noise)
             assert abs(rep["diags"][k]-v) <= 1e-12*abs(v)+1e-13, (k, rep["diags"][k], v)
+
+
+def test_every_rank_streams_its_own_history_file(tmp_path):
+    """two slabs through Fluid2d.loop(): each rank's <expname>_his_<rank> file exists after the
+    loop (no end-of-run dump needed), holds one record per iteration + the initial one, of that
+    rank's slab"""
+    out = str(tmp_path/"rep.json")
+    nx, ny, nsteps, nranks = 32, 64, 3, 2
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks),
+           "--master-addr", "127.0.0.1", "--master-port", "29543",
+           os.path.join(HERE, "slab_emu_worker.py"), out, str(nx), str(ny), str(nsteps), "freedecay_his"]
+    p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:]+p.stderr[-4000:]
+    reports = json.load(open(out))
+    assert len(reports) == nranks
+    for rep in reports:
+        assert rep["exists"] and "_his_%03i." % rep["rank"] in rep["hisfile"]
+        assert rep["nrec"] == nsteps+1 and rep["shape"] == [nsteps+1, ny//nranks, nx]
+        assert rep["last_is_my_slab"]
+        assert rep["diag_exists"] == (rep["rank"] == 0)

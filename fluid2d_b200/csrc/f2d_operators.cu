@@ -380,10 +380,13 @@ extern "C" int f2d_mask_orthogradient(const int8_t *msk, const int8_t *mskp, dou
 }
 
 // add_diffusion: fortran_operators.f90:125-156, rows/cols 2..m-1 where msk==1
+// jlo..jhi: rows written.  On a y-slab (fill mode 2) only the interior rows: the y halo rows of
+// the tendency belong to the neighbours' exchange, which may already be storing into them while
+// this kernel runs (a read-modify-write there would corrupt what the neighbour pushed).
 __global__ void k_add_diffusion(const int8_t *__restrict__ msk, const double *__restrict__ t,
-                                double coef, double *__restrict__ d, int ny, int nx) {
+                                double coef, double *__restrict__ d, int ny, int nx, int jlo, int jhi) {
   IJ();
-  if (j < 1 || j > ny - 2 || i < 1 || i > nx - 2) return;
+  if (j < jlo || j > jhi || i < 1 || i > nx - 2) return;
   if (msk[c] != 1) return;
   double tc = t[c];
   double acc = msk[c - 1] * (t[c - 1] - tc);
@@ -396,7 +399,8 @@ extern "C" int f2d_add_diffusion(const int8_t *msk, const double *trac, double d
                                  double *dtrac, int ny, int nx, int fill, f2d_stream_t s) {
   if (!msk || !trac || !dtrac || ny < 3 || nx < 3) return fail(F2D_ERR_ARG, "add_diffusion: bad args");
   dim3 b(32, 8);
-  k_add_diffusion<<<grid2d(ny, nx, b), b, 0, S(s)>>>(msk, trac, Kdiff / (dx * dx), dtrac, ny, nx);
+  const int jlo = fill == 2 ? nh : 1, jhi = fill == 2 ? ny - 1 - nh : ny - 2;
+  k_add_diffusion<<<grid2d(ny, nx, b), b, 0, S(s)>>>(msk, trac, Kdiff / (dx * dx), dtrac, ny, nx, jlo, jhi);
   F2D_LAUNCHED();
   if (fill == 2) return f2d_fill_halo_x(dtrac, nh, ny, nx, s);
   if (fill) return f2d_fill_halo(dtrac, nh, ny, nx, s);
@@ -406,9 +410,11 @@ extern "C" int f2d_add_diffusion(const int8_t *msk, const double *trac, double d
 // add_torque: fortran_operators.f90:330-381.  ml/mr = max(1, pair sums); the update is
 // applied where ml+mr == 4, i.e. msk(i-1)=msk(i)=msk(i+1)=1.  premask: y *= msk first
 // on the WHOLE array (operators.py:311).
+// slab != 0 (fill mode 2): the y halo rows are left to the neighbours' exchange (see k_add_diffusion)
 __global__ void k_add_torque(const int8_t *__restrict__ msk, const double *__restrict__ b, double coef,
-                             double *__restrict__ d, int ny, int nx, int nh, int premask) {
+                             double *__restrict__ d, int ny, int nx, int nh, int premask, int slab) {
   IJ();
+  if (slab && (j < nh || j >= ny - nh)) return;
   double y = d[c];
   int m0 = msk[c];
   bool touched = false;
@@ -426,7 +432,7 @@ extern "C" int f2d_add_torque(const int8_t *msk, const double *buoy, double dx, 
                               double *domega, int ny, int nx, int premask, int fill, f2d_stream_t s) {
   if (!msk || !buoy || !domega || ny <= 2 * nh || nx <= 2 * nh) return fail(F2D_ERR_ARG, "add_torque: bad args");
   dim3 b(32, 8);
-  k_add_torque<<<grid2d(ny, nx, b), b, 0, S(s)>>>(msk, buoy, 0.5 * gravity / dx, domega, ny, nx, nh, premask);
+  k_add_torque<<<grid2d(ny, nx, b), b, 0, S(s)>>>(msk, buoy, 0.5 * gravity / dx, domega, ny, nx, nh, premask, fill == 2);
   F2D_LAUNCHED();
   if (fill == 2) return f2d_fill_halo_x(domega, nh, ny, nx, s);
   if (fill) return f2d_fill_halo(domega, nh, ny, nx, s);

@@ -51,6 +51,12 @@ def main():
     report = {"slab_levels": model.ope.gmg.slab_levels, "nlevs": model.ope.gmg.nlevs, "errors": {}}
 
     def compare(tag, gstate):
+        if "oracle_"+tag in ref.files:      # the CPU oracle's run of the same global problem
+            g = ref["oracle_"+tag]
+            for k, nm in enumerate(names):
+                n = np.linalg.norm(g[k][3:-3])
+                e = np.linalg.norm(gstate[k][3:-3]-g[k][3:-3])/(n if n > 0 else 1.)
+                report.setdefault("oracle_errors", {})["%s:%s" % (tag, nm)] = float(e)
         g = ref[tag]
         for k, nm in enumerate(names):
             n = np.linalg.norm(g[k][3:-3])

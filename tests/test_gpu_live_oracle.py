@@ -43,8 +43,8 @@ def rel(a, b):
 @pytest.mark.parametrize("name", sorted(BUILD))
 def test_product_matches_live_oracle(name):
     import fluid2d_b200
-    from runtime import rt
     f2d = BUILD[name](fluid2d_b200.api(), tempfile.mkdtemp())
+    from runtime import rt
     ref = BUILD[name](oracle_api(), tempfile.mkdtemp())
     model = f2d.model
     names = list(model.var.varname_list)

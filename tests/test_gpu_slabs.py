@@ -28,6 +28,27 @@ def free_port():
     return p
 
 
+def oracle_states(build, nsteps):
+    """the same global problem on the CPU oracle (oracle/model.py): states after 0, 1 and nsteps steps"""
+    import types
+    from oracle import model as om
+    api = types.SimpleNamespace(Param=om.Param, Grid=om.Grid, Fluid2d=om.Fluid2d)
+    f = build(api, tempfile.mkdtemp())
+    out = {"oracle_state0": np.array(f.model.var.state)}
+    res = cases.run_steps(f, (1, nsteps))
+    for k in (1, nsteps):
+        out["oracle_state%d" % k] = res[k][0]
+    return out
+
+
+def check_against_oracle(rep, nsteps):
+    """contract of BASELINE.json against the reference's algorithm: 1e-12 after one step, 1e-9 after ten"""
+    assert rep.get("oracle_errors"), "the worker did not compare with the oracle"
+    for key, e in rep["oracle_errors"].items():
+        tol = 1e-9 if key.startswith("state%d:" % nsteps) and nsteps > 1 else 1e-12
+        assert e <= tol, ("oracle", key, e)
+
+
 def ngpus():
     import torch
     return torch.cuda.device_count()
@@ -48,6 +69,7 @@ def test_two_slabs_match_single_gpu(nx, ny, min_cells):
     for k in (1, nsteps):
         ref["state%d" % k] = res[k][0]
         ref["dt%d" % k] = np.array(res[k][2])
+    ref.update(oracle_states(lambda api_, d_: cases.freedecay(api_, d_, nx, ny=ny), nsteps))
     refpath = os.path.join(d, "ref.npz")
     np.savez(refpath, **ref)
     out = os.path.join(d, "out.json")
@@ -63,6 +85,7 @@ def test_two_slabs_match_single_gpu(nx, ny, min_cells):
         assert rep["slab_levels"] >= 1
     for key, e in rep["errors"].items():
         assert e <= 1e-12, (key, e)
+    check_against_oracle(rep, nsteps)
     for k in (1, nsteps):
         assert abs(rep["dt%d" % k]-rep["dt%d_ref" % k]) <= 1e-12*rep["dt%d_ref" % k]
 
@@ -73,10 +96,6 @@ def test_two_slabs_match_single_gpu_with_noslip_walls():
     The host side of this is pinned on two CPU ranks by tests/test_slab_emulated.py."""
     if ngpus() < 2:
         pytest.skip("needs 2 GPUs")
-    if os.environ.get("F2D_TEST_UNVERIFIED_SLABS") != "1":
-        # the masked slab multigrid has not run on real GPUs yet (written after the round's GPU
-        # budget was spent): opt-in until tools/r2_first_gpu_session.sh slabs has been green once
-        pytest.skip("set F2D_TEST_UNVERIFIED_SLABS=1 (first run: tools/r2_first_gpu_session.sh slabs)")
     import fluid2d_b200
     from slab_cases import BUILDERS
     api = fluid2d_b200.api()
@@ -88,6 +107,7 @@ def test_two_slabs_match_single_gpu_with_noslip_walls():
     for k in (1, nsteps):
         ref["state%d" % k] = res[k][0]
         ref["dt%d" % k] = np.array(res[k][2])
+    ref.update(oracle_states(lambda api_, d_: BUILDERS["rb"](api_, d_, nx, ny, 1), nsteps))
     refpath = os.path.join(d, "ref.npz")
     np.savez(refpath, **ref)
     out = os.path.join(d, "out.json")
@@ -100,3 +120,4 @@ def test_two_slabs_match_single_gpu_with_noslip_walls():
     rep = json.load(open(out))
     for key, e in rep["errors"].items():
         assert e <= 1e-12, (key, e)
+    check_against_oracle(rep, nsteps)

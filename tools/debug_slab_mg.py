@@ -38,10 +38,26 @@ P0 = 0.01*rng.standard_normal((ny, nx))
 def with_halo(a):
     return np.pad(a, 3, mode='wrap')
 Gh, Ph = with_halo(G), with_halo(P0)
-cm = np.ones((ny+6, nx+6)); cm[-1, :] = 0; cm[:, -1] = 0
+geom = sys.argv[4] if len(sys.argv) > 4 else "perio"
+msk = np.ones((ny+6, nx+6))
+if geom in ("xchannel", "closed"):
+    msk[:3, :] = 0; msk[-3:, :] = 0
+if geom == "closed":
+    msk[:, :3] = 0; msk[:, -3:] = 0
+if geom == "obstacle":
+    yy, xx = np.mgrid[0:ny+6, 0:nx+6]
+    msk[:3, :] = 0; msk[-3:, :] = 0
+    msk[(yy-ny*0.5)**2+(xx-nx*0.3)**2 < (0.15*min(nx, ny))**2] = 0
+cm = np.zeros((ny+6, nx+6))
+cm[:-1, :-1] = ((msk[:-1, :-1]+msk[:-1, 1:]+msk[1:, :-1]+msk[1:, 1:]) == 4)*1.
 def slab(a):
     return np.ascontiguousarray(a[rank*ml:rank*ml+ml+6, :])
-cml = np.ones((ml+6, nx+6)); cml[-1, :] = 0; cml[:, -1] = 0
+# what the host layer hands to f2d_mg_create_slab: the corner mask of the LOCAL cell mask
+# (operators.py:59-67 per rank: its last row and column are 0 on every rank)
+mskl = slab(msk)
+cml = np.zeros((ml+6, nx+6))
+cml[:-1, :-1] = ((mskl[:-1, :-1]+mskl[:-1, 1:]+mskl[1:, :-1]+mskl[1:, 1:]) == 4)*1.
+Gh *= cm; Ph *= cm
 h = ctypes.c_void_p()
 L.mg_create_slab(ctypes.byref(h), comm, ptr(torch.from_numpy(cml).cuda()), ml+6, nx+6, 1./nx, 1./nx, 8./9., 1., 0., s)
 print(rank, "levels", L.mg_nlevels(h), "slab levels", L.mg_slab_levels(h), "modes", [L.mg_level_matrix_mode(h, l) for l in range(L.mg_nlevels(h))], flush=True)

@@ -39,6 +39,43 @@ SMOOTH_BYTES_PER_CELL = 25.   # one Grid.smooth application: read x, b, mask; wr
 VCYCLE_BYTES_PER_CELL = 139.3
 
 
+# the other BASELINE.json configurations (SURVEY.md 8d cases S3, S4): bench.py --config rb | vk
+CONFIGS = {
+    "rb": {"nx": 2048, "ny": 1024, "tracers": 2,
+           "workload": "RayleighBenard 2048x1024 (experiments/RayleighBenard): Boussinesq, xchannel, RK3_SSP, upwind5 "
+                       "(aparab 0.02) on vorticity and buoyancy, torque, diffusion, no-slip walls, cool-roof forcing; "
+                       "4 truncated MG inversions per step"},
+    "vk": {"nx": 4096, "ny": 1024, "tracers": 1,
+           "workload": "VonKarman 4096x1024 (experiments/VonKarman/karman_street.py): Euler, xchannel, RK3_SSP, upwind3, "
+                       "disc obstacle + 2 islands, no-slip, diffusion, sponge layer; 4 truncated MG inversions + full "
+                       "solve per step"},
+}
+
+
+def b_alg_config(config, T, n_F):
+    """algorithmic bytes per cell per step of the masked configurations, by the rule of SURVEY.md
+    8d / appendix B (every operand field of a logical operator read once, every result written
+    once, masks 1 B, matrix coefficients 0; truncated inversion = celltocorner 16 + 2 V-cycles
+    2 x 139.3 + orthogradient 34 = 328.6).  Derivation: DESIGN.md section 5."""
+    inv = 328.6
+    if config == "rb":
+        # adv 3(16T+17), torque 3x25, diffusion Tx25 and forcing hook 40 at the last stage, 3 stage
+        # inversions + the no-slip one, no-slip source 114, RK on all 6 fields 96x6, banom 24, diagnostics 52
+        return 3*(16*T+17)+75+25*T+40+4*inv+114+96*6+24+52
+    if config == "vk":
+        # adv 3x33, diffusion 25, 3 stage inversions + no-slip one + island terms 65 each (5 inversions),
+        # full solve 101 + 272.5 n_F, no-slip 114+16, sponge 24, RK 24x3 + 32x3 + 40x2, diagnostics 41
+        return 3*33+25+4*inv+5*65+101+272.5*n_F+130+24+248+41
+    return b_alg(T, n_F)
+
+
+def build_config(api, config, datadir):
+    import cases
+    if config == "rb":
+        return cases.rb(api, datadir, CONFIGS["rb"]["nx"])
+    return cases.karman(api, datadir, CONFIGS["vk"]["ny"], ratio=CONFIGS["vk"]["nx"]//CONFIGS["vk"]["ny"])
+
+
 def workload_string(n, T, strong, weak_world=1):
     """config.workload -- the same string in the GPU arm and in the reference arm"""
     where = "in total (global grid, y-slabs over the GPUs)" if strong else (
@@ -114,6 +151,56 @@ def kernel_table(lib, r, f2d, peak, shape, nsteps=2):
                     "alg_bytes_per_cell": bpc, "cells": cells, "achieved_gbs": gbs,
                     "frac_of_peak": (gbs/peak if gbs else None)})
     return out, total/nsteps
+
+
+def isolated_times(lib, r, mgh, table, torch, reps=10):
+    """re-time the multigrid kernels of the table in isolation: `reps` back-to-back launches of
+    the same operator on the hierarchy's own level arrays (f2d_mg_bench_op), CUDA events around
+    the batch.  The in-step accounting charges a kernel with the wait for a host that issues
+    launches slower than the device runs them (the step runs without graphs there); this does
+    not.  Adds 'isolated_us' to the rows it can re-time and recomputes their roofline figures."""
+    import ctypes
+    import re
+    shapes = {}
+    ny, nx = ctypes.c_int(), ctypes.c_int()
+    for lev in range(lib.mg_nlevels(mgh)):
+        lib.mg_level_shape(mgh, lev, ctypes.byref(ny), ctypes.byref(nx))
+        shapes[(nx.value-6, ny.value-6)] = lev
+    tail0 = lib.mg_tail_level(mgh)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(kind, lev):
+        if lib.mg_bench_op(mgh, kind, lev, 2, r.stream) != 0:
+            return None
+        torch.cuda.synchronize()
+        e0.record()
+        lib.mg_bench_op(mgh, kind, lev, reps, r.stream)
+        e1.record()
+        torch.cuda.synchronize()
+        return 1e3*e0.elapsed_time(e1)/reps
+
+    for row in table:
+        name = row["kernel"]
+        us = None
+        m = re.match(r"k_smooth2<mode\d,input(\d)(,peer)?> (\d+)x(\d+)", name)
+        if m and (int(m.group(3)), int(m.group(4))) in shapes:
+            us = timed(int(m.group(1)), shapes[(int(m.group(3)), int(m.group(4)))])
+        m = re.match(r"k_resid_restrict<mode\d(,peer)?> (\d+)x(\d+)", name)
+        if m and (int(m.group(2)), int(m.group(3))) in shapes:
+            us = timed(4, shapes[(int(m.group(2)), int(m.group(3)))])
+        m = re.match(r"k_restrict(<peer>)? (\d+)x(\d+)", name)
+        if m and (int(m.group(2)), int(m.group(3))) in shapes:
+            us = timed(5, shapes[(int(m.group(2)), int(m.group(3)))])
+        if name.startswith("k_resid_sumsq"):
+            us = timed(6, 0)
+        m = re.match(r"k_mg_c?tail<program(\d)>", name)
+        if m and tail0 >= 0:
+            us = timed(7 if m.group(1) in "01" else 8, tail0)
+        if us:
+            row["isolated_us"] = us
+            if row["alg_bytes_per_cell"]:
+                row["achieved_gbs"] = row["alg_bytes_per_cell"]*row["cells"]/(us*1e-6)/1e9
+    return table
 
 
 def dram_traffic_table():
@@ -248,7 +335,7 @@ def loop_body(f2d):
 # CPU arm: the oracle port (the reference's Fortran cannot be compiled here, so this is
 # kind "port"), all host threads, a bounded number of steps of the SAME workload
 # ---------------------------------------------------------------------------
-def cpu_arm(n, tracers, steps, warmup, what=None):
+def cpu_arm(n, tracers, steps, warmup, what=None, config="turb"):
     import types
     # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host
     # thread (the OpenMP runtime reads the variable when the oracle library is loaded, below)
@@ -267,7 +354,14 @@ def cpu_arm(n, tracers, steps, warmup, what=None):
             om.Fluid2d.__init__(self, p, g, fast_axpy=True)
     api = types.SimpleNamespace(Param=om.Param, Grid=om.Grid, Fluid2d=F)
     t0 = time.time()
-    f2d = build_case(api, n, tracers, tempfile.mkdtemp())
+    if config == "turb":
+        f2d = build_case(api, n, tracers, tempfile.mkdtemp())
+        cells = n*n
+    else:
+        f2d = build_config(api, config, tempfile.mkdtemp())
+        cells = CONFIGS[config]["nx"]*CONFIGS[config]["ny"]
+        what = what or ("%d steps (after %d warm-up) of the same workload, oracle C port with OpenMP on all host "
+                        "threads" % (steps, warmup))
     f2d.model.diagnostics(f2d.model.var, 0.)
     log("[cpu] set-up %.1f s on %d threads" % (time.time()-t0, cores))
     for _ in range(warmup):
@@ -276,13 +370,13 @@ def cpu_arm(n, tracers, steps, warmup, what=None):
     for _ in range(steps):
         loop_body(f2d)
     dt = time.time()-t0
-    return {"value": n*n*steps/dt, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+    return {"value": cells*steps/dt, "unit": "cell-updates/s", "cores": cores, "kind": "port",
             "sample": what or ("%d steps (after %d warm-up) of the same %dx%d Euler freedecay workload, oracle C port "
                                "with OpenMP on all host threads" % (steps, warmup, n, n)),
             "ms_per_step": 1e3*dt/steps,
             # the reference's own end-of-run figure (core/fluid2d.py:329-338): wall time per
             # iteration per grid point, times the number of cores
-            "rescaled_time_core_s_per_cell_update": cores*dt/(steps*n*n)}
+            "rescaled_time_core_s_per_cell_update": cores*dt/(steps*cells)}
 
 
 def resolve_workload(args, world):
@@ -296,6 +390,19 @@ def reference_main(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
+        return
+    if args.config != "turb":
+        steps = max(1, min(args.steps, 40))
+        warm = max(1, min(args.warmup, 5))
+        r = cpu_arm(0, CONFIGS[args.config]["tracers"], steps, warm, None, args.config)
+        line = {"impl": "reference", "metric": "cell_updates_per_s", "value": r["value"], "unit": r["unit"],
+                "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": CONFIGS[args.config]["workload"]},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample",
+                                                   "rescaled_time_core_s_per_cell_update")},
+                "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
         return
     n, strong = resolve_workload(args, max(world, args.gpus))
     # bounded sample: the 16384^2 field is a periodic tiling of one 4096^2 freedecay tile, and
@@ -364,14 +471,23 @@ def gpu_main(args):
     sys.stdout = sys.stderr
     sampler = ClockSampler(local) if rank == 0 else None     # child process, started well before the timed region
     T = args.tracers
+    config = args.config
     n, strong = resolve_workload(args, world)
     t0 = time.time()
     slabs = world > 1 and not args.replicas
     if strong and (args.replicas or n % world):
         raise SystemExit("strong scaling: n must be a multiple of the number of GPUs (and no --replicas)")
-    rows = n//world if strong else n          # rows of this rank's slab
-    total_cells = n*n if strong else world*n*n
-    f2d = build_case(api, n, T, tempfile.mkdtemp(), world if slabs else 1, strong)
+    if config != "turb":
+        if world > 1:
+            raise SystemExit("--config rb / vk are single-GPU lines")
+        T = CONFIGS[config]["tracers"]
+        n, rows = CONFIGS[config]["nx"], CONFIGS[config]["ny"]
+        total_cells = n*rows
+        f2d = build_config(api, config, tempfile.mkdtemp())
+    else:
+        rows = n//world if strong else n          # rows of this rank's slab
+        total_cells = n*n if strong else world*n*n
+        f2d = build_case(api, n, T, tempfile.mkdtemp(), world if slabs else 1, strong)
     model = f2d.model
     model.diagnostics(model.var, 0.)
     torch.cuda.synchronize()
@@ -408,7 +524,7 @@ def gpu_main(args):
     table, us_nograph = kernel_table(lib, r, f2d, peak, (rows, n))
     dram = dram_traffic_table()
     for row in table:
-        row["dram_bytes_per_launch"] = dram.get(row["kernel"])
+        row["dram_bytes_per_launch"] = dram.get(row["kernel"].replace(",peer", ""))
 
     # ---- the level-0 smoother and the V-cycle timed alone
     if slabs:
@@ -421,6 +537,15 @@ def gpu_main(args):
         lib.mg_create(ctypes.byref(mgh), r.ptr(cm), rows+6, n+6, 1./n, 1./n, 8./9., 1., 0., r.stream)
     else:
         mgh = model.ope.gmg.h
+    # the multigrid kernels of the table re-timed alone; shares from launches x best available time
+    isolated_times(lib, r, mgh, table, torch)
+    for row in table:
+        row["us_per_step"] = row["launches_per_step"]*row.get("isolated_us", row["avg_us"])
+    tot = sum(row["us_per_step"] for row in table) or 1.
+    for row in table:
+        row["share"] = row["us_per_step"]/tot
+        row["frac_of_peak"] = row["achieved_gbs"]/peak if row["achieved_gbs"] else None
+    table.sort(key=lambda row: -row["share"])
     x0 = torch.zeros((rows+6, n+6), dtype=torch.float64, device="cuda")
     b0 = torch.randn((rows+6, n+6), dtype=torch.float64, device="cuda")
     reps = 10
@@ -472,7 +597,7 @@ def gpu_main(args):
     # ---- N = 1 only: SURVEY.md 8d case S5 on ONE GPU (16384^2, 86 GB), the denominator of the
     # parallel efficiency of the N > 1 lines (which run 16384^2 split in N slabs)
     s5 = None
-    if world == 1 and not strong and not args.no_s5 and n == 4096:
+    if world == 1 and not strong and not args.no_s5 and n == 4096 and config == "turb":
         try:
             del f2d, model, ds
             import gc
@@ -505,12 +630,15 @@ def gpu_main(args):
     cpu = None
     if world == 1 and not args.no_cpu and not strong:
         try:
-            cpu = cpu_arm(n, T, 3, 1)
-            small = cpu_arm(1024, T, 20, 3)
-            cpu["also_1024"] = {k: small[k] for k in ("value", "ms_per_step", "rescaled_time_core_s_per_cell_update")}
+            if config != "turb":
+                cpu = cpu_arm(0, T, 5, 1, None, config)
+            else:
+                cpu = cpu_arm(n, T, 3, 1)
+                small = cpu_arm(1024, T, 20, 3)
+                cpu["also_1024"] = {k: small[k] for k in ("value", "ms_per_step", "rescaled_time_core_s_per_cell_update")}
         except Exception as ex:   # the baseline is a report, never a reason to lose the GPU line
             cpu = {"value": None, "unit": "cell-updates/s", "cores": 0, "kind": "port", "sample": "failed: %r" % ex}
-    balg = b_alg(T, n_F)
+    balg = b_alg_config(config, T, n_F)
     # dominant kernel = the largest share of the step in the accounting above, among the
     # bandwidth-bound kernels (the latency-bound tail is listed in the table without a roofline)
     dom = next((row for row in table if row["achieved_gbs"]), None)
@@ -521,8 +649,8 @@ def gpu_main(args):
         "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_string(n, T, strong, world),
-                   "grid": [n, n], "tracers": T, "n_F_mean": n_F,
+        "config": {"workload": CONFIGS[config]["workload"] if config != "turb" else workload_string(n, T, strong, world),
+                   "grid": [n, rows*world if strong or world == 1 else rows], "tracers": T, "n_F_mean": n_F,
                    "parallelism": "single GPU" if world == 1 else (
                        "%d y-slabs of %dx%d (global %dx%d), halo rows by peer stores over NVLink fused into the "
                        "producing kernels, coarse levels gathered" % (world, n, rows, n, rows*world)
@@ -537,10 +665,13 @@ def gpu_main(args):
                      # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture
                      # committed under profiles/ (r02_kernel_dram_bytes.json); null without a capture
                      "traffic": dom["dram_bytes_per_launch"] if dom else None,
-                     "peak_source": peak_src, "ms_per_launch": dom["avg_us"]*1e-3 if dom else None,
+                     "peak_source": peak_src,
+                     "ms_per_launch": dom.get("isolated_us", dom["avg_us"])*1e-3 if dom else None,
                      "algorithmic_bytes_per_cell": dom["alg_bytes_per_cell"] if dom else None,
-                     "how": "CUDA events behind every launch of 2 steps run without CUDA graphs "
-                            "(f2d_prof_begin/report); achieved = algorithmic bytes per launch / average duration",
+                     "how": "launch counts from CUDA events around every launch of 2 steps run without CUDA "
+                            "graphs (f2d_prof_begin/report); the multigrid kernels then timed alone, 10 launches "
+                            "back to back between two CUDA events (f2d_mg_bench_op); dominant = largest "
+                            "launches x time; achieved = algorithmic bytes per launch / that time",
                      "level0_smoother_alone": {"kernel": "k_smooth2<mode1,input0> (Grid.smooth, level 0)",
                                                "ms_per_launch": smooth_ms, "achieved": smooth_gbs,
                                                "frac": smooth_gbs/peak, "algorithmic_bytes_per_cell": SMOOTH_BYTES_PER_CELL}},
@@ -571,6 +702,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=0, help="grid size (default: 4096 on one GPU, 16384 global on several)")
     ap.add_argument("--tracers", type=int, default=1)
+    ap.add_argument("--config", default="turb", choices=["turb", "rb", "vk"],
+                    help="turb: Twodim_turbulence (the headline); rb / vk: RayleighBenard 2048x1024, VonKarman 4096x1024")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-s5", action="store_true", help="N=1: skip the 16384^2 single-GPU run")
     ap.add_argument("--replicas", action="store_true", help="N>1: independent replicas instead of slabs")

@@ -94,10 +94,9 @@ class Boussinesq(object):
         lib.computesumandnorm(msk, s.rptr(ix('buoyancy')), nh, ny, nx, slot(4), sc, r.stream)
         # potential energy: - g * sum(b * y)   (buoyancy is minus density)
         lib.computedotprod(msk, s.rptr(ix('buoyancy')), r.ptr(self.d_yr), nh, ny, nx, slot(6), sc, r.stream)
-        ke, maxu, z, z2, b, b2, by = r.read_out(7)
+        ke, maxu, z, z2, b, b2, by = self.mpitools.reduce_device(r, 7, 0x2)   # slot 1 (max speed) is a maximum
         pe = - self.gravity * by
-        glo = self.mpitools.local_to_global([(maxu, 'max'), (ke, 'sum'), (z, 'sum'), (z2, 'sum'),
-                                             (pe, 'sum'), (b, 'sum'), (b2, 'sum')])
+        glo = [maxu, ke, z, z2, pe, b, b2]
         # domain means (maxspeed is a maximum, not a mean)
         maxu, ke, z, z2, pe, b, b2 = [glo[0]]+[v/self.area for v in glo[1:]]
         self.diags.update(maxspeed=maxu, ke=ke, pe=pe, energy=(glo[1]+glo[4])/self.area, vorticity=z, enstrophy=0.5*z2,

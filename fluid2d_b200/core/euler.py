@@ -138,8 +138,7 @@ class Euler(object):
                        s.rptr(ix('psi')), s.rptr(ix('source')), r.ptr(self.d_xr), r.ptr(self.d_yr),
                        self.nh, s.ny, s.nx, r.ptr(r.out), r.ptr(r.scratch), r.stream)
         names = ('maxspeed', 'ke', 'vorticity', 'enstrophy', 'px', 'py', 'angmom', 'source')
-        local = r.read_out(8)
-        glo = self.mpitools.local_to_global([(local[0], 'max')]+[(v, 'sum') for v in local[1:]])
+        glo = self.mpitools.reduce_device(r, 8, 0x1)      # slot 0 (max speed) is a maximum
         # domain means, except the maximum speed; enstrophy = half the mean square vorticity
         for k, name in enumerate(names):
             self.diags[name] = glo[k] if k == 0 else glo[k]/self.area

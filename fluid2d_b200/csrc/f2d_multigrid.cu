@@ -17,6 +17,7 @@
 #include "f2d_mg_fused.cuh"
 #include "f2d_mg_tail.cuh"
 #include "f2d_mg_ctail.cuh"
+#include "f2d_mg_ptail.cuh"
 
 using namespace f2d;
 
@@ -42,6 +43,8 @@ struct f2d_mg {
   int npre = 1, npost = 1, ndeepest = 16, nvcyc = 1;  // hierarchy.py:29-32
   int relax = 0;              // 0 damped Jacobi (smoothtwicewithA), 1 line relaxation (smoothtridiag)
   double *scratch = nullptr;  // reductions
+  double *partials = nullptr; // per-block sums of k_resid_sumsq
+  size_t npartials = 0;
   double *dscal = nullptr;    // device scalars [4]
   double *hscal = nullptr;    // pinned host mirror [4]
   cudaStream_t cap = nullptr; // capture stream for CUDA graphs
@@ -56,6 +59,8 @@ struct f2d_mg {
   bool ctail = false;         // the tail runs on a thread-block cluster (f2d_mg_ctail.cuh), from 256^2 / 128^2 down
   int ctail_nc = 1;           // CTAs of that cluster (1 when no level of the tail is distributed)
   ctail::Params ctp;          // its level table (pointers / program filled per launch)
+  bool ptail = false;         // all-fluid doubly periodic square tail: the interior-only kernel (f2d_mg_ptail.cuh)
+  int ptail_top = 0;          // log2 of its finest level
   long long *trace = nullptr; // f2d_mg_set_trace
   int trace_cap = 0;
   struct G { cudaGraphExec_t exec; long long kernels; };
@@ -384,11 +389,11 @@ __global__ void k_add_inplace(double *__restrict__ y, const double *__restrict__
 
 // solve(): residual of the finest level + its squared norm in one pass
 // (hierarchy.py:159-162,172-174: g.residual(x, b, self.b[0]); g.norm(self.b[0])).
-// Block b sweeps rows b, b+RSB, ...; r = b - A x on the interior with its halo images;
+// r = b - A x on the interior with its halo images;
 // the per-block sums of r^2 go to `partial` and are folded by k_fold_partials
 // (deterministic two-stage sum; r is 0 on solid corners, so the unmasked sum of r^2
 // equals computenorm's masked one).
-constexpr int RSB = 148 * 4, RST = 256;
+constexpr int RST = 256;
 
 __device__ __forceinline__ double block_sum(double v) {
   __shared__ double sh[RST / 32];
@@ -400,6 +405,10 @@ __device__ __forceinline__ double block_sum(double v) {
   return v;
 }
 
+// Block (bx, by): columns NH + 256*bx .. of rows NH + RSR*by ..; a thread marches its column
+// north with the 3x3 window of x in registers (3 loads per point, neighbouring lanes share the
+// cache lines), stores r with its halo images and accumulates r^2 in row order.
+constexpr int RSR = 16;
 template <bool MASKED, bool STORED>
 __global__ void __launch_bounds__(RST)
 k_resid_sumsq(fused::LevelK L, const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ r,
@@ -407,28 +416,37 @@ k_resid_sumsq(fused::LevelK L, const double *__restrict__ x, const double *__res
   const int ny = L.ny, nx = L.nx;
   fused::Coefs<MASKED, STORED> kc;
   if (!MASKED && !STORED) kc.load(L, 0, nullptr, 0);
+  const int i = NH + blockIdx.x * RST + threadIdx.x;
+  const int j0 = NH + blockIdx.y * RSR;
   double acc = 0.;
-  for (int j = NH + blockIdx.x; j <= ny - 1 - NH; j += gridDim.x) {
-    const bool rimrow = j < 2 * NH || j >= ny - 2 * NH;
-    for (int i = NH + threadIdx.x; i <= nx - 1 - NH; i += RST) {
-      size_t g = (size_t)j * nx + i;
+  if (i <= nx - 1 - NH) {
+    const bool rimcol = i < 2 * NH || i >= nx - 2 * NH;
+    const double *p = x + (size_t)j0 * nx + i;
+    double a0 = p[-nx - 1], a1 = p[-nx], a2 = p[-nx + 1];
+    double m0 = p[-1], m1 = p[0], m2 = p[1];
+#pragma unroll 4
+    for (int k = 0; k < RSR; k++) {
+      const int j = j0 + k;
+      if (j > ny - 1 - NH) break;
+      const size_t g = (size_t)j * nx + i;
+      const double h0 = x[g + nx - 1], h1 = x[g + nx], h2 = x[g + nx + 1];
       double val = 0.;
       if (!MASKED || L.msk[g] != 0) {
-        fused::Coefs<MASKED, STORED> k;
-        if (MASKED || STORED) k.load(L, g, MASKED ? L.msk + g : nullptr, nx); else k = kc;
-        double cdiag = STORED ? L.A[4 * (size_t)ny * nx + g] : L.c[4];
-        const double *p = x + g;
-        val = fused::resid_val<MASKED, STORED>(L, k, cdiag, p[-nx - 1], p[-nx], p[-nx + 1], p[-1], p[0], p[1],
-                                               p[nx - 1], p[nx], p[nx + 1], b[g]);
+        fused::Coefs<MASKED, STORED> kk;
+        if (MASKED || STORED) kk.load(L, g, MASKED ? L.msk + g : nullptr, nx); else kk = kc;
+        const double cdiag = STORED ? L.A[4 * (size_t)ny * nx + g] : L.c[4];
+        val = fused::resid_val<MASKED, STORED>(L, kk, cdiag, a0, a1, a2, m0, m1, m2, h0, h1, h2, b[g]);
       }
       r[g] = val;
-      if (rimrow || i < 2 * NH || i >= nx - 2 * NH)
+      if (rimcol || j < 2 * NH || j >= ny - 2 * NH)
         for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { r[(size_t)jj * nx + ii] = val; }, L.ywrap != 0);
       acc += val * val;
+      a0 = m0; a1 = m1; a2 = m2;
+      m0 = h0; m1 = h1; m2 = h2;
     }
   }
   acc = block_sum(acc);
-  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+  if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = acc;
 }
 __global__ void __launch_bounds__(RST) k_fold_partials(const double *__restrict__ partial, int n, double *out) {
   double acc = 0.;
@@ -591,15 +609,17 @@ int op_residual(f2d_mg *mg, int lev, const double *x, const double *b, double *r
 int op_resid_sumsq_L(f2d_mg *mg, Level &l, const double *x, const double *b, double *r, double *out,
                      cudaStream_t s) {
   fused::LevelK k = level_k(mg, l);
-  int nb = l.ny - 2 * NH < RSB ? l.ny - 2 * NH : RSB;
+  dim3 grid(cdiv(l.nx - 2 * NH, RST), cdiv(l.ny - 2 * NH, RSR));
+  const int nb = (int)(grid.x * grid.y);
+  if ((size_t)nb > mg->npartials) return fail(F2D_ERR_ARG, "resid_sumsq: partial-sum buffer too small");
   prof_tag("k_resid_sumsq<mode%d> %dx%d", l.mode, l.nx - 2 * NH, l.ny - 2 * NH);
   switch (l.mode) {
-    case 1: k_resid_sumsq<false, false><<<nb, RST, 0, s>>>(k, x, b, r, mg->scratch); break;
-    case 2: k_resid_sumsq<true, false><<<nb, RST, 0, s>>>(k, x, b, r, mg->scratch); break;
-    default: k_resid_sumsq<true, true><<<nb, RST, 0, s>>>(k, x, b, r, mg->scratch); break;
+    case 1: k_resid_sumsq<false, false><<<grid, RST, 0, s>>>(k, x, b, r, mg->partials); break;
+    case 2: k_resid_sumsq<true, false><<<grid, RST, 0, s>>>(k, x, b, r, mg->partials); break;
+    default: k_resid_sumsq<true, true><<<grid, RST, 0, s>>>(k, x, b, r, mg->partials); break;
   }
   F2D_LAUNCHED();
-  k_fold_partials<<<1, RST, 0, s>>>(mg->scratch, nb, out);
+  k_fold_partials<<<1, RST, 0, s>>>(mg->partials, nb, out);
   F2D_LAUNCHED();
   return F2D_OK;
 }
@@ -688,13 +708,74 @@ int coarsest_enqueue(f2d_mg *mg, double *X, const double *B, cudaStream_t s) {
   return F2D_OK;
 }
 
+// instantiations of the periodic tail: (cluster size, log2 of the finest level)
+template <int TOP, int NC>
+int ptail_launch_t(const ptail::Params &P, int program, cudaStream_t s, bool probe, size_t *smem_out) {
+  constexpr size_t smem = ptail::smem_bytes<TOP, NC>();
+  if (smem_out) *smem_out = smem;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(NC);
+  cfg.blockDim = dim3(ptail::NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = NC;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (probe) {   // set-up: attributes, and can the device co-schedule such a cluster?
+    if (NC > 8 && cudaFuncSetAttribute(ptail::k_mg_ptail<TOP, NC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+      cudaGetLastError();
+      return F2D_ERR_CUDA;
+    }
+    if (cudaFuncSetAttribute(ptail::k_mg_ptail<TOP, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return F2D_ERR_CUDA;
+    }
+    if (NC > 1) {
+      int nclusters = 0;
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, ptail::k_mg_ptail<TOP, NC>, &cfg);
+      if (e != cudaSuccess || nclusters < 1) { cudaGetLastError(); return F2D_ERR_CUDA; }
+    }
+    return F2D_OK;
+  }
+  F2D_CUDA(cudaLaunchKernelEx(&cfg, ptail::k_mg_ptail<TOP, NC>, P, program));
+  return F2D_OK;
+}
+int ptail_launch(int top, int nc, const ptail::Params &P, int program, cudaStream_t s, bool probe, size_t *smem_out) {
+#define F2D_PT(T, N) if (top == T && nc == N) return ptail_launch_t<T, N>(P, program, s, probe, smem_out)
+  F2D_PT(8, 16); F2D_PT(7, 16); F2D_PT(6, 16);
+  F2D_PT(7, 8); F2D_PT(6, 8);
+  F2D_PT(6, 1); F2D_PT(5, 1); F2D_PT(4, 1); F2D_PT(3, 1); F2D_PT(2, 1);
+#undef F2D_PT
+  return F2D_ERR_ARG;
+}
+
 // one launch of the shared-memory tail: program 0/1 = V-cycle (x = 0 / x = x_in first),
 // 2 = F-cycle of the levels tail0..last; rhs b_in, result x_out (both of level tail0)
 int tail_launch(f2d_mg *mg, int program, const double *b_in, const double *x_in, double *x_out, cudaStream_t s,
                 double *acc = nullptr) {
   {
     Level &t0l = mg->L[mg->tail0];
-    prof_tag("%s<program%d> %dx%d", mg->ctail ? "k_mg_ctail" : "k_mg_tail", program, t0l.nx - 2 * NH, t0l.ny - 2 * NH);
+    prof_tag("%s<program%d> %dx%d", mg->ptail ? "k_mg_ptail" : (mg->ctail ? "k_mg_ctail" : "k_mg_tail"), program,
+             t0l.nx - 2 * NH, t0l.ny - 2 * NH);
+  }
+  if (mg->ptail) {
+    ptail::Params P;
+    const int last = (int)mg->L.size() - 1;
+    for (int lg = ptail::LGMIN; lg <= mg->ptail_top; lg++) P.k[lg - ptail::LGMIN] = level_k(mg, last - (lg - ptail::LGMIN));
+    P.ndeepest = mg->ndeepest;
+    P.b_in = b_in;
+    P.x_in = x_in;
+    P.x_out = x_out;
+    P.acc = acc;
+    P.trace = mg->trace;
+    P.trace_cap = mg->trace_cap;
+    TRY(ptail_launch(mg->ptail_top, mg->ctail_nc, P, program, s, false, nullptr));
+    F2D_LAUNCHED();
+    return F2D_OK;
   }
   if (mg->ctail) {
     ctail::Params P = mg->ctp;
@@ -1153,6 +1234,14 @@ int finish_setup(f2d_mg *mg, double Rd, cudaStream_t s) {
   }
   MGC(set_smem_all());
   {
+    // per-block partial sums of k_resid_sumsq (finest level of the handle: L[0], or S[0] on slabs)
+    size_t nb = 0;
+    for (auto *lp : {mg->L.empty() ? nullptr : &mg->L[0], mg->S.empty() ? nullptr : &mg->S[0]})
+      if (lp) nb = std::max(nb, (size_t)cdiv(lp->nx - 2 * NH, RST) * (size_t)cdiv(lp->ny - 2 * NH, RSR));
+    MGC(cudaMalloc(&mg->partials, nb * sizeof(double)));
+    mg->npartials = nb;
+  }
+  {
     int *dflag = nullptr;
     unsigned long long *didx = nullptr;
     MGC(cudaMalloc(&dflag, 2 * sizeof(int)));
@@ -1301,6 +1390,45 @@ int finish_setup(f2d_mg *mg, double Rd, cudaStream_t s) {
       }
     }
   }
+  // all-fluid doubly periodic SQUARE tail (every tail level in the constant-stencil class, sizes
+  // 2^k ... 8, 4): the interior-only template kernel (f2d_mg_ptail.cuh), from F2D_PTAIL_MAXN (128)
+  // down; F2D_MG_NO_PTAIL=1 keeps the general cluster tail
+  {
+    const char *notail = getenv("F2D_MG_NO_TAIL"), *noct = getenv("F2D_MG_NO_CTAIL"), *nopt = getenv("F2D_MG_NO_PTAIL");
+    const bool off = (notail && notail[0] == '1') || (noct && noct[0] == '1') || (nopt && nopt[0] == '1');
+    int maxn = 128, nc_want = 16;
+    if (const char *e = getenv("F2D_PTAIL_MAXN")) maxn = atoi(e);
+    if (const char *e = getenv("F2D_CTAIL_NC")) nc_want = atoi(e);
+    const int last = (int)mg->L.size() - 1;
+    if (!off && last >= 0 && mg->L[last].ny - 2 * NH == 4 && mg->L[last].nx - 2 * NH == 4) {
+      // how far up do the square constant-stencil levels go?
+      int t0 = last + 1, top = ptail::LGMIN - 1;
+      while (t0 > 0) {
+        Level &l = mg->L[t0 - 1];
+        const int n = l.nx - 2 * NH, want = 4 << (last - (t0 - 1));
+        if (l.mode != 1 || l.ywrap != 1 || n != want || l.ny - 2 * NH != want || want > maxn || want > 256) break;
+        t0--;
+        top++;
+      }
+      for (int nc = nc_want; nc >= 1 && !mg->ptail && top >= ptail::LGMIN; nc = (nc >= 16 ? 8 : (nc > 1 ? 1 : 0))) {
+        int tp = top;
+        if (nc == 1 && tp > 6) tp = 6;                 // one CTA holds up to 64^2
+        if (nc == 8 && tp > 7) tp = 7;
+        if (nc > 1 && tp < 6) continue;                // nothing to distribute below 64^2
+        ptail::Params P;
+        size_t smem = 0;
+        if (ptail_launch(tp, nc, P, 0, s, true, &smem) != F2D_OK) continue;
+        const int t0p = last - (tp - ptail::LGMIN);
+        if (mg->tail0 >= 0 && mg->tail0 < t0p) continue;   // a general tail above it is not supported
+        mg->ptail = true;
+        mg->ptail_top = tp;
+        mg->ctail_nc = nc;
+        mg->tail0 = t0p;
+        mg->tail_smem = smem;
+        mg->tail_const = true;
+      }
+    }
+  }
   MGC(cudaStreamSynchronize(s));
   MGC(cudaGetLastError());
   return F2D_OK;
@@ -1423,6 +1551,7 @@ extern "C" int f2d_mg_destroy(f2d_mg_t *mg) {
   for (auto &l : mg->L) free_level(l);
   for (auto &l : mg->S) free_level(l);
   cudaFree(mg->scratch);
+  cudaFree(mg->partials);
   cudaFree(mg->dscal);
   if (mg->hscal) cudaFreeHost(mg->hscal);
   if (mg->cap) cudaStreamDestroy(mg->cap);
@@ -1479,6 +1608,7 @@ extern "C" int f2d_mg_set_relaxation(f2d_mg_t *mg, int mode) {
     // path: every level goes through the per-operator kernels on the stored coefficients
     mg->tail0 = -1;
     mg->ctail = false;
+    mg->ptail = false;
     for (auto &l : mg->L) l.mode = 0;
   } else {
     return fail(F2D_ERR_ARG, "mg_set_relaxation: a hierarchy switched to the line relaxation cannot be switched back");
@@ -1582,6 +1712,55 @@ extern "C" int f2d_mg_solve(f2d_mg_t *mg, double *psi, const double *rhs, double
   if (res_out) *res_out = res;
   return F2D_OK;
 }
+
+// bench.py: one operator of the cycles, `reps` launches back to back on the level's own arrays
+// (the kernels the graphs replay, timed in isolation with CUDA events around the batch)
+extern "C" int f2d_mg_bench_op(f2d_mg_t *mg, int kind, int lev, int reps, f2d_stream_t stream) {
+  CHECK_LEV(mg, lev, "mg_bench_op");
+  if (reps < 1) return fail(F2D_ERR_ARG, "mg_bench_op: reps");
+  if (mg->relax != 0) return fail(F2D_ERR_ARG, "mg_bench_op: Jacobi hierarchies only");
+  cudaStream_t s = S(stream);
+  Level &l = mg->L[lev];
+  const bool has_coarse = lev + 1 < (int)mg->L.size();
+  for (int k = 0; k < reps; k++) {
+    switch (kind) {
+      case 0: TRY(smooth2(mg, lev, 0, l.x, l.b, l.t, nullptr, s)); break;
+      case 1: TRY(smooth2(mg, lev, 1, l.x, l.b, l.t, nullptr, s)); break;
+      case 2:
+        if (!has_coarse) return fail(F2D_ERR_ARG, "mg_bench_op: no coarser level");
+        TRY(smooth2(mg, lev, 2, l.x, l.b, l.x, mg->L[lev + 1].x, s));
+        break;
+      case 3:
+        if (!has_coarse) return fail(F2D_ERR_ARG, "mg_bench_op: no coarser level");
+        TRY(smooth2(mg, lev, 3, l.t, l.b, l.x, mg->L[lev + 1].x, s));
+        break;
+      case 4:
+        if (!has_coarse) return fail(F2D_ERR_ARG, "mg_bench_op: no coarser level");
+        TRY(op_resid_restrict(mg, lev, l.t, l.b, mg->L[lev + 1].b, s));
+        break;
+      case 5:
+        if (!has_coarse) return fail(F2D_ERR_ARG, "mg_bench_op: no coarser level");
+        TRY(op_restrict(mg, lev, l.b, mg->L[lev + 1].b, s));
+        break;
+      case 6:
+        if (lev != 0) return fail(F2D_ERR_ARG, "mg_bench_op: the residual norm kernel belongs to level 0");
+        TRY(op_resid_sumsq(mg, l.x, l.b, l.r, mg->dscal + 3, s));
+        break;
+      case 7:
+        if (lev != mg->tail0) return fail(F2D_ERR_ARG, "mg_bench_op: not the first level of the tail");
+        TRY(tail_launch(mg, 0, l.b, nullptr, l.x, s));
+        break;
+      case 8:
+        if (lev != mg->tail0) return fail(F2D_ERR_ARG, "mg_bench_op: not the first level of the tail");
+        TRY(tail_launch(mg, 2, l.b, nullptr, l.x, s));
+        break;
+      default: return fail(F2D_ERR_ARG, "mg_bench_op: kind 0..8");
+    }
+  }
+  return F2D_OK;
+}
+/* first level handled by the shared-memory tail kernel (-1: none) */
+extern "C" int f2d_mg_tail_level(const f2d_mg_t *mg) { return mg ? mg->tail0 : -1; }
 
 // operators.py:421-498
 extern "C" int f2d_mg_set_trace(f2d_mg_t *mg, long long *buf, int cap) {

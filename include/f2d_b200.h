@@ -53,6 +53,12 @@ void f2d_launch_count_reset(void);
  * f2d_prof_report every kernel launched on `stream` is followed by a CUDA event; the report is
  * one line "name<TAB>launches<TAB>microseconds" per kernel (instantiation and grid size in
  * the name).  Run with CUDA graphs disabled (f2d_mg_set_graphs(h, 0)). */
+int f2d_mg_bench_op(f2d_mg_t *mg, int kind, int level, int reps, f2d_stream_t stream);
+/* ^ measurement aid (bench.py): `reps` back-to-back launches of ONE operator of the cycles on the
+ * level's own arrays.  kind: 0 Grid.smooth, 1 Grid.smooth from x = 0, 2 x = I(xc) + smooth,
+ * 3 x += I(xc) + smooth, 4 residual + restriction, 5 restriction, 6 residual + norm (level 0),
+ * 7 / 8 the coarse-tail kernel's V-cycle / F-cycle (first tail level, f2d_mg_tail_level). */
+int f2d_mg_tail_level(const f2d_mg_t *mg);
 int f2d_prof_begin(f2d_stream_t stream);
 int f2d_prof_report(char *buf, size_t cap);
 

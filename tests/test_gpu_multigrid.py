@@ -49,7 +49,8 @@ def L(request):
     return _lib.lib(strict=request.param == "strict"), request.param == "strict"
 
 
-def make(lib, kind, ny, nx, Rd=0., force_stored=False, notail=False, noctail=False, ctail_nc=None, ctail_mincells=None):
+def make(lib, kind, ny, nx, Rd=0., force_stored=False, notail=False, noctail=False, ctail_nc=None, ctail_mincells=None,
+         noptail=False, ptail_maxn=None):
     import os
     import gpu_util as g
     os.environ["F2D_MG_FORCE_STORED"] = "1" if force_stored else "0"
@@ -58,7 +59,8 @@ def make(lib, kind, ny, nx, Rd=0., force_stored=False, notail=False, noctail=Fal
     # cluster tail: CTAs per cluster (default 16) and the size below which a level is replicated
     # (0: distribute every level with >= 4 rows per CTA, so that small test grids exercise the
     # distributed-shared-memory paths too)
-    for key, val in (("F2D_CTAIL_NC", ctail_nc), ("F2D_CTAIL_MINCELLS", ctail_mincells)):
+    os.environ["F2D_MG_NO_PTAIL"] = "1" if noptail else "0"     # all-fluid periodic hierarchies: interior-only tail
+    for key, val in (("F2D_CTAIL_NC", ctail_nc), ("F2D_CTAIL_MINCELLS", ctail_mincells), ("F2D_PTAIL_MAXN", ptail_maxn)):
         if val is None:
             os.environ.pop(key, None)
         else:
@@ -165,14 +167,19 @@ def test_matrix_classes(L):
 
 
 @pytest.mark.parametrize("kind,ny,nx", CASES)
-@pytest.mark.parametrize("graphs,force_stored,notail,noctail,ctail_nc,ctail_mincells",
-                         [(0, False, False, False, None, None), (1, False, False, False, None, None),
-                          (1, True, False, False, None, None), (1, False, True, False, None, None),
-                          (1, False, False, True, None, None), (1, True, False, True, None, None),
-                          (1, False, False, False, 16, 0), (1, True, False, False, 16, 0),
-                          (1, False, False, False, 8, 0), (1, True, False, False, 8, 0),
-                          (1, False, False, False, 4, 0), (1, False, False, False, 2, 0)])
-def test_cycles_and_solve(L, kind, ny, nx, graphs, force_stored, notail, noctail, ctail_nc, ctail_mincells):
+@pytest.mark.parametrize("graphs,force_stored,notail,noctail,ctail_nc,ctail_mincells,noptail,ptail_maxn",
+                         [(0, False, False, False, None, None, False, None), (1, False, False, False, None, None, False, None),
+                          (1, True, False, False, None, None, False, None), (1, False, True, False, None, None, False, None),
+                          (1, False, False, True, None, None, False, None), (1, True, False, True, None, None, False, None),
+                          (1, False, False, False, 16, 0, False, None), (1, True, False, False, 16, 0, False, None),
+                          (1, False, False, False, 8, 0, False, None), (1, True, False, False, 8, 0, False, None),
+                          (1, False, False, False, 4, 0, False, None), (1, False, False, False, 2, 0, False, None),
+                          # the general cluster tail on the periodic cases too; the periodic tail from 256^2
+                          (1, False, False, False, None, None, True, None), (1, False, False, False, 16, 0, True, None),
+                          (1, False, False, False, None, None, False, 256), (0, False, False, False, 8, 0, False, 256),
+                          (1, False, False, False, 1, None, False, None)])
+def test_cycles_and_solve(L, kind, ny, nx, graphs, force_stored, notail, noctail, ctail_nc, ctail_mincells, noptail,
+                          ptail_maxn):
     """graphs on/off; matrix class forced to 'stored'; coarse levels by the cluster tail
     kernel (<= 256^2, 16 / 8 / 4 / 2 CTAs with ghost rows exchanged through distributed shared
     memory; small levels distributed too when ctail_mincells = 0), by the one-CTA tail kernel
@@ -180,7 +187,7 @@ def test_cycles_and_solve(L, kind, ny, nx, graphs, force_stored, notail, noctail
     import gpu_util as g
     lib, strict = L
     ref, h, rng = make(lib, kind, ny, nx, force_stored=force_stored, notail=notail, noctail=noctail,
-                       ctail_nc=ctail_nc, ctail_mincells=ctail_mincells)
+                       ctail_nc=ctail_nc, ctail_mincells=ctail_mincells, noptail=noptail, ptail_maxn=ptail_maxn)
     s = g.stream()
     lib.mg_set_graphs(h, graphs)
     tol_cycle = 1e-12

@@ -32,16 +32,18 @@ def timeit(f, reps=20):
     return 1e3*e0.elapsed_time(e1)/reps
 
 
-CONFIGS = [("cluster 16, <=256", {"F2D_CTAIL_NC": "16", "F2D_CTAIL_MAXN": "256"}),
-           ("cluster 16, <=128", {"F2D_CTAIL_NC": "16", "F2D_CTAIL_MAXN": "128"}),
-           ("cluster 16, <=128, all dist", {"F2D_CTAIL_NC": "16", "F2D_CTAIL_MAXN": "128", "F2D_CTAIL_MINCELLS": "0"}),
-           ("cluster 16, <=256, dist>=16k", {"F2D_CTAIL_NC": "16", "F2D_CTAIL_MAXN": "256", "F2D_CTAIL_MINCELLS": "16384"}),
-           ("cluster 8, <=128", {"F2D_CTAIL_NC": "8", "F2D_CTAIL_MAXN": "128"}),
-           ("cluster 8, <=256", {"F2D_CTAIL_NC": "8", "F2D_CTAIL_MAXN": "256"}),
-           ("cluster 1 (one CTA, <=64)", {"F2D_CTAIL_NC": "1", "F2D_CTAIL_MAXN": "64"}),
+CONFIGS = [("periodic tail 16, <=128", {"F2D_CTAIL_NC": "16", "F2D_PTAIL_MAXN": "128"}),
+           ("periodic tail 16, <=256", {"F2D_CTAIL_NC": "16", "F2D_PTAIL_MAXN": "256"}),
+           ("periodic tail 16, <=128, all dist", {"F2D_CTAIL_NC": "16", "F2D_PTAIL_MAXN": "128", "F2D_CTAIL_MINCELLS": "0"}),
+           ("periodic tail 16, <=128, dist>=8k", {"F2D_CTAIL_NC": "16", "F2D_PTAIL_MAXN": "128", "F2D_CTAIL_MINCELLS": "8192"}),
+           ("periodic tail 8, <=128", {"F2D_CTAIL_NC": "8", "F2D_PTAIL_MAXN": "128"}),
+           ("periodic tail 1 (one CTA, <=64)", {"F2D_CTAIL_NC": "1", "F2D_PTAIL_MAXN": "64"}),
+           ("cluster 16, <=256", {"F2D_CTAIL_NC": "16", "F2D_CTAIL_MAXN": "256", "F2D_MG_NO_PTAIL": "1"}),
+           ("cluster 16, <=128", {"F2D_CTAIL_NC": "16", "F2D_CTAIL_MAXN": "128", "F2D_MG_NO_PTAIL": "1"}),
            ("one-CTA tail (round 1)", {"F2D_MG_NO_CTAIL": "1"}),
            ("per-level kernels", {"F2D_MG_NO_TAIL": "1"})]
-KEYS = ("F2D_CTAIL_NC", "F2D_CTAIL_MAXN", "F2D_CTAIL_MINCELLS", "F2D_MG_NO_CTAIL", "F2D_MG_NO_TAIL")
+KEYS = ("F2D_CTAIL_NC", "F2D_CTAIL_MAXN", "F2D_CTAIL_MINCELLS", "F2D_MG_NO_CTAIL", "F2D_MG_NO_TAIL", "F2D_MG_NO_PTAIL",
+        "F2D_PTAIL_MAXN")
 
 
 def setenv(env):
@@ -68,7 +70,7 @@ for name, env in CONFIGS:
     us = timeit(lambda: L.mg_two_vcycle(h, ptr(x), ptr(b), s))/2
     usf = timeit(lambda: L.mg_fcycle(h, 0, s))
     print("%-30s %d^2: V-cycle %.1f us, F-cycle %.1f us" % (name, n, us, usf))
-    if name.startswith("cluster") and os.environ.get("F2D_TRACE", "1") == "1":
+    if (name.startswith("cluster") or name.startswith("periodic")) and os.environ.get("F2D_TRACE", "1") == "1":
         cap = 4096
         tr = torch.zeros(cap, dtype=torch.int64, device="cuda")
         L.mg_set_trace(h, ptr(tr), cap)

@@ -170,7 +170,9 @@ def isolated_times(lib, r, mgh, table, torch, reps=10):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def timed(kind, lev):
-        if lib.mg_bench_op(mgh, kind, lev, 2, r.stream) != 0:
+        try:
+            lib.mg_bench_op(mgh, kind, lev, 2, r.stream)
+        except Exception:
             return None
         torch.cuda.synchronize()
         e0.record()
@@ -193,7 +195,7 @@ def isolated_times(lib, r, mgh, table, torch, reps=10):
             us = timed(5, shapes[(int(m.group(2)), int(m.group(3)))])
         if name.startswith("k_resid_sumsq"):
             us = timed(6, 0)
-        m = re.match(r"k_mg_c?tail<program(\d)>", name)
+        m = re.match(r"k_mg_[cp]?tail<program(\d)>", name)
         if m and tail0 >= 0:
             us = timed(7 if m.group(1) in "01" else 8, tail0)
         if us:

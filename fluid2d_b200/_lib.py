@@ -86,7 +86,7 @@ class Library(object):
             f.argtypes = argtypes
             self.raw[fn] = f
             if ret is ctypes.c_int and fn not in ("f2d_abi_version", "f2d_mg_nlevels",
-                                                  "f2d_mg_level_matrix_mode", "f2d_mg_slab_levels",
+                                                  "f2d_mg_level_matrix_mode", "f2d_mg_slab_levels", "f2d_mg_tail_level",
                                                   "f2d_comm_rank", "f2d_comm_size"):
                 setattr(self, fn[4:], self._checked(fn, f))
             else:

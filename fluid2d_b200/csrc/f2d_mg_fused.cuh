@@ -61,6 +61,14 @@ struct Coefs {
       c3 = L.c3;
     }
   }
+  // constant stencil x mask products from a 3x3 mask window held in registers (rows lo / mid / hi)
+  __device__ __forceinline__ void from_window(const LevelK &L, int l0, int l1, int l2, int m0, int m2, int h0, int h1,
+                                              int h2) {
+    sw = l0 ? L.c[0] : 0.; s = l1 ? L.c[1] : 0.; se = l2 ? L.c[2] : 0.;
+    w = m0 ? L.c[3] : 0.;  e = m2 ? L.c[3] : 0.;
+    nw = h0 ? L.c[2] : 0.; n = h1 ? L.c[1] : 0.; ne = h2 ? L.c[0] : 0.;
+    c3 = L.c3;
+  }
 };
 
 // damped-Jacobi value from a 3x3 window (rows lo/mid/hi, columns l/c/r)
@@ -169,12 +177,31 @@ __device__ __forceinline__ void load_tile(double *dst, const double *src, int nx
     row += rstep;
   }
 }
+// (fully unrolled, every load issued before the first store: one L2 round trip for the tile
+// instead of one per pass -- the loop form cost the masked kernels 5 dependent round trips)
 template <int ROWS, int COLS, int LD>
 __device__ __forceinline__ void load_tile_i8(int8_t *dst, const int8_t *src, int nx, int vrows, int vcols) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int r = warp; r < ROWS; r += NT / 32)
-    for (int c = lane; c < COLS; c += 32)
-      dst[r * LD + c] = (r < vrows && c < vcols) ? src[(size_t)r * nx + c] : (int8_t)0;
+  constexpr int NW = NT / 32, NK = (ROWS + NW - 1) / NW, NC = (COLS + 31) / 32;
+  int8_t v[NK][NC];
+#pragma unroll
+  for (int k = 0; k < NK; k++) {
+    const int r = warp + k * NW;
+#pragma unroll
+    for (int q = 0; q < NC; q++) {
+      const int c = lane + q * 32;
+      v[k][q] = (r < ROWS && c < COLS && r < vrows && c < vcols) ? src[(size_t)r * nx + c] : (int8_t)0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NK; k++) {
+    const int r = warp + k * NW;
+#pragma unroll
+    for (int q = 0; q < NC; q++) {
+      const int c = lane + q * 32;
+      if (r < ROWS && c < COLS) dst[r * LD + c] = v[k][q];
+    }
+  }
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
@@ -197,23 +224,36 @@ __device__ __forceinline__ void jacobi_strip(const LevelK &L, const Coefs<MASKED
     a0 = sp[-SLD - 1]; a1 = sp[-SLD]; a2 = sp[-SLD + 1];
     m0 = sp[-1]; m1 = sp[0]; m2 = sp[1];
   }
+  // mask-product levels: the 3x3 mask window marches in registers too (3 byte loads per point
+  // instead of 9)
+  constexpr bool MWIN = MASKED && !STORED;
+  int wa0 = 0, wa1 = 0, wa2 = 0, wm0 = 0, wm1 = 0, wm2 = 0;
+  if (MWIN) {
+    wa0 = mp[-MLD - 1]; wa1 = mp[-MLD]; wa2 = mp[-MLD + 1];
+    wm0 = mp[-1]; wm1 = mp[0]; wm2 = mp[1];
+  }
 #pragma unroll
   for (int k = 0; k < NR; k++) {
     if (k < nr) {
       double h0 = 0., h1 = 0., h2 = 0.;
       if (!ZERO) { h0 = sp[(k + 1) * SLD - 1]; h1 = sp[(k + 1) * SLD]; h2 = sp[(k + 1) * SLD + 1]; }
+      int wh0 = 0, wh1 = 0, wh2 = 0;
+      if (MWIN) { wh0 = mp[(k + 1) * MLD - 1]; wh1 = mp[(k + 1) * MLD]; wh2 = mp[(k + 1) * MLD + 1]; }
       const bool ok = !GUARD || (j + k >= lo && j + k <= ny - 1 - lo && i >= lo && i <= nx - 1 - lo);
       if (ok) {
         double val = 0.;
-        if (!MASKED || mp[k * MLD] != 0) {
+        if (!MASKED || (MWIN ? wm1 : (int)mp[k * MLD]) != 0) {
           Coefs<MASKED, STORED> kk;
-          if (MASKED || STORED) kk.load(L, g + (size_t)k * nx, MASKED ? mp + k * MLD : nullptr, MLD); else kk = kc;
+          if (MWIN) kk.from_window(L, wa0, wa1, wa2, wm0, wm2, wh0, wh1, wh2);
+          else if (STORED) kk.load(L, g + (size_t)k * nx, nullptr, MLD);
+          else kk = kc;
           val = jacobi_val<MASKED, STORED>(L, kk, a0, a1, a2, m0, m1, m2, h0, h1, h2, bget(k));
         }
         out(k, val);
       }
       a0 = m0; a1 = m1; a2 = m2;
       m0 = h0; m1 = h1; m2 = h2;
+      if (MWIN) { wa0 = wm0; wa1 = wm1; wa2 = wm2; wm0 = wh0; wm1 = wh1; wm2 = wh2; }
     }
   }
 }
@@ -451,10 +491,18 @@ __device__ __forceinline__ void resid_strip(const LevelK &L, const Coefs<MASKED,
   double a0 = sp[-RXP - 1], a1 = sp[-RXP], a2 = sp[-RXP + 1];
   double m0 = sp[-1], m1 = sp[0], m2 = sp[1];
   size_t g = (size_t)j * nx + i;
+  constexpr bool MWIN = MASKED && !STORED;   // 3x3 mask window in registers (see jacobi_strip)
+  int wa0 = 0, wa1 = 0, wa2 = 0, wm0 = 0, wm1 = 0, wm2 = 0;
+  if (MWIN) {
+    wa0 = mp[-RXW - 1]; wa1 = mp[-RXW]; wa2 = mp[-RXW + 1];
+    wm0 = mp[-1]; wm1 = mp[0]; wm2 = mp[1];
+  }
 #pragma unroll
   for (int k = 0; k < NR; k++) {
     if (k < nr) {
       double h0 = sp[(k + 1) * RXP - 1], h1 = sp[(k + 1) * RXP], h2 = sp[(k + 1) * RXP + 1];
+      int wh0 = 0, wh1 = 0, wh2 = 0;
+      if (MWIN) { wh0 = mp[(k + 1) * RXW - 1]; wh1 = mp[(k + 1) * RXW]; wh2 = mp[(k + 1) * RXW + 1]; }
       double val = 0.;
       const int jj = j + k;
       if (GUARD && (jj > ny - NH || i > nx - NH)) {
@@ -464,15 +512,18 @@ __device__ __forceinline__ void resid_strip(const LevelK &L, const Coefs<MASKED,
         // there, i.e. the residual of the periodic source cell
         // (on a y-slab the halo row already holds the neighbour's data: evaluate in place)
         val = resid_global<MASKED, STORED>(L, x, b, L.ywrap ? f2d::wrap_src(jj, ny, NH) : jj, f2d::wrap_src(i, nx, NH));
-      } else if (!MASKED || mp[k * RXW] != 0) {
+      } else if (!MASKED || (MWIN ? wm1 : (int)mp[k * RXW]) != 0) {
         Coefs<MASKED, STORED> kk;
-        if (MASKED || STORED) kk.load(L, g + (size_t)k * nx, MASKED ? mp + k * RXW : nullptr, RXW); else kk = kc;
+        if (MWIN) kk.from_window(L, wa0, wa1, wa2, wm0, wm2, wh0, wh1, wh2);
+        else if (STORED) kk.load(L, g + (size_t)k * nx, nullptr, RXW);
+        else kk = kc;
         double cdiag = STORED ? L.A[4 * (size_t)ny * nx + g + (size_t)k * nx] : L.c[4];
         val = resid_val<MASKED, STORED>(L, kk, cdiag, a0, a1, a2, m0, m1, m2, h0, h1, h2, bp[k * RBP]);
       }
       rp[k * RBP] = val;
       a0 = m0; a1 = m1; a2 = m2;
       m0 = h0; m1 = h1; m2 = h2;
+      if (MWIN) { wa0 = wm0; wa1 = wm1; wa2 = wm2; wm0 = wh0; wm1 = wh1; wm2 = wh2; }
     }
   }
 }

@@ -47,6 +47,11 @@ class Euler(object):
             tr = [ix(trac) for trac in param.tracer_list]
             self.tscheme.fields_stage = tr+[ix('u'), ix('v')]
             self.tscheme.fields_final = tr+[ix('psi')]
+            # at the first stage of RK3_SSP the tendency of a tracer is what rhs_adv leaves (the
+            # inversion that follows writes psi, u, v only): the advection kernel writes x + dt*dx0
+            if self.timestepping == 'RK3_SSP':
+                self.tscheme.adv_hook = self.ope
+                self.tscheme.fused_fields = tr
         r = rt()
         self.rt = r
         self.d_xr = r.to_device(self.xr, dtype=np.float64)

@@ -108,6 +108,8 @@ class Operators(Param):
         self._d_rhsp = None
         self._d_psi_island = None
         self.last_solve = (0, 0.)
+        self.fuse = None     # request of the time scheme: stage update fused into the advection kernel
+        self.fused = []
 
     # ------------------------------------------------------------------
     def set_boundary_msk(self):
@@ -180,16 +182,39 @@ class Operators(Param):
 
     # ------------------------------------------------------------------
     def rhs_adv(self, x, t, dxdt):
-        """dxdt[tracer] = -div(u tracer) for every tracer, halo filled (operators.py:214-236)"""
+        """dxdt[tracer] = -div(u tracer) for every tracer, halo filled (operators.py:214-236): one
+        launch for all the tracers of the model (they share the velocity tiles).  When the time
+        scheme has asked for it (self.fuse = (xout, xbase, coef, fields), Timescheme.RK3_SSP), the
+        same kernel also writes the stage state xout[k] = xbase[k] + coef*dxdt[k] of the tracers
+        in `fields`; self.fused says which ones it did."""
         r, lib = self.rt, self.lib
         iu, iv = self.ix('u'), self.ix('v')
         cst = (ctypes.c_double*5)(*self.cst)
-        adv = lib.adv_upwind if self.upwind else lib.adv_centered
         msk = None if self.all_fluid else r.ptr(self.d_msk)
-        for trac in self.tracer_list:
-            ik = self.ix(trac)
-            adv(msk, x.rptr(ik), dxdt.wptr(ik), x.rptr(iu), x.rptr(iv), None, None, cst,
-                self.nh, self.fs_method, self.order, self.nyl, self.nxl, self.fillmode, r.stream)
+        tracers = [self.ix(trac) for trac in self.tracer_list]
+        self.fused = []
+        groups = [(tracers, None)]
+        if self.fuse is not None and self.comm is None:
+            xout, xbase, coef, fields = self.fuse
+            yes = [k for k in tracers if k in fields]
+            no = [k for k in tracers if k not in fields]
+            groups = [(g, f) for g, f in ((yes, (xout, xbase, coef)), (no, None)) if g]
+            self.fused = yes
+        pu, pv = x.rptr(iu), x.rptr(iv)
+        for group, fuse in groups:
+            n = len(group)
+            arr = ctypes.c_void_p*n
+            q = arr(*[x.rptr(k).value for k in group])
+            dq = arr(*[dxdt.wptr(k).value for k in group])
+            xb = xo = None
+            coef = 0.
+            if fuse is not None:
+                xb = arr(*[fuse[1].rptr(k).value for k in group])
+                xo = arr(*[fuse[0].wptr(k).value for k in group])
+                coef = fuse[2]
+            lib.adv_multi(msk, q, dq, n, pu, pv, cst, self.nh, 1 if self.upwind else 0, self.fs_method,
+                          self.order, xb, xo, coef, self.nyl, self.nxl, self.fillmode, r.stream)
+        for ik in tracers:
             self._xch(dxdt.wptr(ik))
 
     def rhs_diffusion(self, x, t, dxdt, coef=1.):

@@ -42,6 +42,11 @@ class Timescheme(object):
         # reads later (see Euler.__init__).
         self.fields_stage = None
         self.fields_final = None
+        # optional: an object with `fuse` / `fused` attributes (the model's Operators) and the
+        # fields whose FIRST-stage update x + dt*dx0 of RK3_SSP its advection kernel may write
+        # itself -- tracers whose tendency is complete once rhs_adv has run at that stage
+        self.adv_hook = None
+        self.fused_fields = []
         self.kstage = 0
         self.kforcing = 0
         self.forward = self._unset
@@ -187,8 +192,21 @@ class Timescheme(object):
         final = self._runs(self.fields_final if self.fields_final is not None else range(nf))
         fs = self.fieldsize
         self.kstage = 0
-        self.rhs(x, t, self.dx0)
-        for k0, c in stage:
+        done = []
+        if self.adv_hook is not None and self.fused_fields:
+            self.adv_hook.fuse = (self.x, x, dt, list(self.fused_fields))
+            try:
+                self.rhs(x, t, self.dx0)
+            finally:
+                done = list(self.adv_hook.fused)
+                self.adv_hook.fuse = None
+                self.adv_hook.fused = []
+            todo = [k for k in (self.fields_stage if self.fields_stage is not None else range(nf)) if k not in done]
+            stage0 = self._runs(todo)
+        else:
+            self.rhs(x, t, self.dx0)
+            stage0 = stage
+        for k0, c in stage0:
             lib.ts_xpay(self._wk(self.x, k0, c), self._rk(x, k0, c), dt, self._rk(self.dx0, k0, c), c*fs, r.stream)
         self.kstage = 1
         self.rhs(self.x, t+dt, self.dx1)

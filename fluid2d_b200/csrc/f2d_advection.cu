@@ -12,7 +12,10 @@
 // The running mask sums of the Fortran (mx5/mx3, my5/my3; :62-70,96-97,132-133) are
 // window sums here -- the same integers.
 #include <cstddef>
+#include <map>
+#include <tuple>
 #include "f2d_common.cuh"
+#include "f2d_tma.cuh"
 
 using namespace f2d;
 
@@ -112,55 +115,121 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
+// Tiles in shared memory.  TMA: dense boxes (128-byte aligned, even widths; the v tile starts
+// one column early because a box must start at an even column: the tile proper sits at column
+// offset 1).  Otherwise (odd nx) the rows are staged by LDGSTS with the same layout.
+constexpr int UW = TX + 2;     // u tile width: faces i0-1 .. i0+TX (the last one unused)
+constexpr int VW = TX + 2;     // v tile width: columns i0-1 .. i0+TX
 struct AdvSmem {
-  double q[SH][SW];       // tracer tile, halo 3
-  double u[TY][TX + 1];   // u on the east faces i0-1 .. i0+TX-1; overwritten by the x fluxes
-  double v[TY + 1][TX];   // v on the north faces of rows j0-1 .. j0+TY-1
-  int8_t m[SH][SW];       // mask tile (MASKED only)
+  alignas(128) double q[SH][SW];     // tracer tile, halo 3
+  alignas(128) double u[TY][UW];     // u on the east faces i0-1 .. ; overwritten by the x fluxes
+  alignas(128) double v[TY + 1][VW]; // v on the north faces of rows j0-1 .. j0+TY-1, column i0+c at [.][c+1]
+  alignas(8) uint64_t bar;
+  int8_t m[SH][SW];                  // mask tile (MASKED only)
 };
 
-// mask-free instantiations: launched without the mask tile (54.8 KB) and compiled for 4 CTAs
-// per SM (<= 64 registers)
-template <bool UPW, int ORDER, bool MASKED>
+// One launch advects up to ADV_MAXT tracers of a model (operators.py:214-236 is a loop over the
+// tracer list): the CTAs of the tracers of one tile are neighbours in the grid (blockIdx.x =
+// tile_x * n + tracer), so the velocity tiles they all read come from L2 after the first one.
+// Optionally the kernel also writes the Runge-Kutta stage state xo = xb + coef * dq
+// (timescheme.py:172-176; product rounded before the sum, as numpy does).
+constexpr int ADV_MAXT = 4;
+struct AdvBatch {
+  const double *q[ADV_MAXT];
+  double *dq[ADV_MAXT];
+  const double *xb[ADV_MAXT];
+  double *xo[ADV_MAXT];
+  double coef;
+  int n;
+};
+struct AdvMaps {
+  CUtensorMap q[ADV_MAXT], u, v;
+};
+
+// mask-free instantiations: launched without the mask tile and compiled for 4 CTAs per SM
+// (<= 64 registers)
+template <bool UPW, int ORDER, bool MASKED, bool TMA>
 __global__ void __launch_bounds__(NT, MASKED ? 3 : 4)
-k_adv(const int8_t *__restrict__ msk, const double *__restrict__ q, double *__restrict__ dq,
-      const double *__restrict__ u, const double *__restrict__ v, double *__restrict__ xflx,
-      double *__restrict__ yflx, AdvC k, int ny, int nx, int fill) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+k_adv(const int8_t *__restrict__ msk, const AdvBatch B, const double *__restrict__ u, const double *__restrict__ v,
+      double *__restrict__ xflx, double *__restrict__ yflx, AdvC k, int ny, int nx, int fill,
+      const __grid_constant__ AdvMaps M) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   AdvSmem &S = *reinterpret_cast<AdvSmem *>(smem_raw);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int i0 = NH + blockIdx.x * TX;  // first output column of the tile
+  const int tr = B.n > 1 ? (int)(blockIdx.x % (unsigned)B.n) : 0;
+  const int bx = B.n > 1 ? (int)(blockIdx.x / (unsigned)B.n) : (int)blockIdx.x;
+  const double *__restrict__ q = B.q[tr];
+  double *__restrict__ dq = B.dq[tr];
+  const double *__restrict__ xb = B.xb[tr];
+  double *__restrict__ xo = B.xo[tr];
+  const int i0 = NH + bx * TX;  // first output column of the tile
   const int j0 = NH + blockIdx.y * TY;
-  // ---- stage q (halo 3), u, v with asynchronous copies: one tile row per warp and pass
-  for (int r = warp; r < SH; r += NT / 32) {
-    int j = j0 - NH + r;
-    const double *row = q + (size_t)j * nx + (i0 - NH);
-#pragma unroll
-    for (int c = lane; c < SW; c += 32) {
-      bool in = j < ny && (i0 - NH + c) < nx;
-      cp_async8(&S.q[r][c], in ? row + c : q, in);
-      if (MASKED) S.m[r][c] = in ? msk[(size_t)j * nx + i0 - NH + c] : (int8_t)0;
+  if (TMA) {
+    // ---- three boxes, one instruction each (zero fill outside the array)
+    if (t == 0) f2d::mbar_init(&S.bar, 1);
+    __syncthreads();
+    if (t == 0) {
+      f2d::mbar_expect_tx(&S.bar, (SH * SW + TY * UW + (TY + 1) * VW) * 8);
+      f2d::tma_load_2d(&S.q[0][0], &M.q[tr], &S.bar, i0 - NH, j0 - NH);
+      f2d::tma_load_2d(&S.u[0][0], &M.u, &S.bar, i0 - 1, j0);
+      f2d::tma_load_2d(&S.v[0][0], &M.v, &S.bar, i0 - 1, j0 - 1);
     }
-  }
-  for (int r = warp; r < TY; r += NT / 32) {
-    int j = j0 + r;
-    const double *row = u + (size_t)j * nx + (i0 - 1);
+    if (MASKED) {
+      // every byte load issued before the first store: one L2 round trip for the mask tile
+      constexpr int NW = NT / 32, NK = (SH + NW - 1) / NW, NCC = (SW + 31) / 32;
+      int8_t mv[NK][NCC];
 #pragma unroll
-    for (int c = lane; c < TX + 1; c += 32) {
-      bool in = j < ny && (i0 - 1 + c) < nx;
-      cp_async8(&S.u[r][c], in ? row + c : u, in);
-    }
-  }
-  for (int r = warp; r < TY + 1; r += NT / 32) {
-    int j = j0 - 1 + r;
-    const double *row = v + (size_t)j * nx + i0;
+      for (int kk = 0; kk < NK; kk++) {
+        const int r = warp + kk * NW, j = j0 - NH + r;
 #pragma unroll
-    for (int c = lane; c < TX; c += 32) {
-      bool in = j < ny && (i0 + c) < nx;
-      cp_async8(&S.v[r][c], in ? row + c : v, in);
+        for (int cc = 0; cc < NCC; cc++) {
+          const int c = lane + cc * 32;
+          mv[kk][cc] = (r < SH && c < SW && j < ny && (i0 - NH + c) < nx) ? msk[(size_t)j * nx + i0 - NH + c] : (int8_t)0;
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < NK; kk++) {
+        const int r = warp + kk * NW;
+#pragma unroll
+        for (int cc = 0; cc < NCC; cc++) {
+          const int c = lane + cc * 32;
+          if (r < SH && c < SW) S.m[r][c] = mv[kk][cc];
+        }
+      }
     }
+    f2d::mbar_wait(&S.bar, 0);
+  } else {
+    // ---- stage q (halo 3), u, v with asynchronous copies: one tile row per warp and pass
+    for (int r = warp; r < SH; r += NT / 32) {
+      int j = j0 - NH + r;
+      const double *row = q + (size_t)j * nx + (i0 - NH);
+#pragma unroll
+      for (int c = lane; c < SW; c += 32) {
+        bool in = j < ny && (i0 - NH + c) < nx;
+        cp_async8(&S.q[r][c], in ? row + c : q, in);
+        if (MASKED) S.m[r][c] = in ? msk[(size_t)j * nx + i0 - NH + c] : (int8_t)0;
+      }
+    }
+    for (int r = warp; r < TY; r += NT / 32) {
+      int j = j0 + r;
+      const double *row = u + (size_t)j * nx + (i0 - 1);
+#pragma unroll
+      for (int c = lane; c < TX + 1; c += 32) {
+        bool in = j < ny && (i0 - 1 + c) < nx;
+        cp_async8(&S.u[r][c], in ? row + c : u, in);
+      }
+    }
+    for (int r = warp; r < TY + 1; r += NT / 32) {
+      int j = j0 - 1 + r;
+      const double *row = v + (size_t)j * nx + i0;
+#pragma unroll
+      for (int c = lane; c < TX; c += 32) {
+        bool in = j < ny && (i0 + c) < nx;
+        cp_async8(&S.v[r][c + 1], in ? row + c : v, in);
+      }
+    }
+    cp_async_wait_all();
   }
-  cp_async_wait_all();
   __syncthreads();
   const int tx = t & (TX - 1), tg = t >> 6;   // column, row group (TX == 64)
   const int r0 = tg * (TY / 4);
@@ -185,66 +254,118 @@ k_adv(const int8_t *__restrict__ msk, const double *__restrict__ q, double *__re
       f = face_flux<UPW, ORDER, MASKED>(k, S.u[t][0], &S.q[t + NH][NH - 1], 1,
                                         MASKED ? &S.m[t + NH][NH - 1] : nullptr, 1);
     S.u[t][0] = f;
-    if (flx && blockIdx.x == 0 && j < ny - NH) xflx[(size_t)j * nx + (i0 - 1)] = f;
+    if (flx && bx == 0 && j < ny - NH) xflx[(size_t)j * nx + (i0 - 1)] = f;
   }
   __syncthreads();
   if (!col_ok) return;
   // ---- north-face fluxes marching up the strip (the Fortran's fym), divergence, stores
   const bool rim = fill && ((j0 < 2 * NH) || (i0 < 2 * NH) || (j0 + TY > ny - 2 * NH) || (i0 + TX > nx - 2 * NH));
   if (j0 + r0 >= ny - NH) return;
-  double fym = face_flux<UPW, ORDER, MASKED>(k, S.v[r0][tx], &S.q[r0 + NH - 1][tx + NH], SW,
-                                             MASKED ? &S.m[r0 + NH - 1][tx + NH] : nullptr, SW);
+  // The 6-point window of the north face marches in registers: the face above row r reads the
+  // rows r-2 .. r+3, five of which the face below already holds (one shared load per face
+  // instead of six; the same for the mask window).
+  const double *qc = &S.q[r0 + NH - 1][tx + NH];        // cell below the first face (row r0-1)
+  double w0 = qc[-2 * SW], w1 = qc[-SW], w2 = qc[0], w3 = qc[SW], w4 = qc[2 * SW], w5 = qc[3 * SW];
+  int n0 = 1, n1 = 1, n2 = 1, n3 = 1, n4 = 1, n5 = 1;
+  const int8_t *mc = &S.m[r0 + NH - 1][tx + NH];
+  if (MASKED) { n0 = mc[-2 * SW]; n1 = mc[-SW]; n2 = mc[0]; n3 = mc[SW]; n4 = mc[2 * SW]; n5 = mc[3 * SW]; }
+  auto north_flux = [&](double vel) {
+    return UPW ? upw_flux<ORDER, MASKED>(k, vel, w0, w1, w2, w3, w4, w5, n0, n1, n2, n3, n4, n5)
+               : cen_flux<ORDER, MASKED>(k, vel, w0, w1, w2, w3, w4, w5, n0, n1, n2, n3, n4, n5);
+  };
+  double fym = north_flux(S.v[r0][tx + 1]);
   if (flx && blockIdx.y == 0 && r0 == 0) yflx[(size_t)(j0 - 1) * nx + i] = fym;
+  const double coef = B.coef;
 #pragma unroll 2
   for (int r = r0; r < r0 + TY / 4; r++) {
     int j = j0 + r;
     if (j >= ny - NH) break;
     size_t c = (size_t)j * nx + i;
-    double fy = face_flux<UPW, ORDER, MASKED>(k, S.v[r + 1][tx], &S.q[r + NH][tx + NH], SW,
-                                              MASKED ? &S.m[r + NH][tx + NH] : nullptr, SW);
+    // the window moves one row north: its new top is row r + 3
+    w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5;
+    w5 = S.q[r + NH + 3][tx + NH];
+    if (MASKED) { n0 = n1; n1 = n2; n2 = n3; n3 = n4; n4 = n5; n5 = S.m[r + NH + 3][tx + NH]; }
+    double fy = north_flux(S.v[r + 1][tx + 1]);
     double fxe = S.u[r][tx + 1], fxw = S.u[r][tx];
     double y = -k.zdx * (fxe - fxw) - k.zdy * (fy - fym);
     dq[c] = y;
+    if (xo) xo[c] = add_rn(xb[c], mul_rn(coef, y));
     if (flx) {
       xflx[c] = fxe;
       yflx[c] = fy;
     }
     if (rim)
-      for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { dq[(size_t)jj * nx + ii] = y; }, fill != 2);
+      for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) {
+        dq[(size_t)jj * nx + ii] = y;
+        // the halo of the stage state is the reference's whole-array sum evaluated THERE: xb's
+        // halo need not hold the images of its interior (masked domains, sponge, user edits)
+        if (xo) xo[(size_t)jj * nx + ii] = add_rn(xb[(size_t)jj * nx + ii], mul_rn(coef, y));
+      }, fill != 2);
     fym = fy;
   }
 }
 
+// tensor maps of the advected fields, cached by (pointer, shape, box)
+bool adv_tmap(const double *base, int ny, int nx, int boxh, int boxw, CUtensorMap *out) {
+  static std::map<std::tuple<const void *, int, int, int, int>, CUtensorMap> cache;
+  if (!base || nx < boxw || ny < boxh) return false;
+  auto key = std::make_tuple((const void *)base, ny, nx, boxh, boxw);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    CUtensorMap tm;
+    if (f2d::make_tmap_2d(&tm, base, ny, nx, boxh, boxw) != 0) return false;
+    if (cache.size() > 256) cache.clear();
+    it = cache.emplace(key, tm).first;
+  }
+  *out = it->second;
+  return true;
+}
+
 template <bool UPW, int ORDER, bool MASKED>
-int launch_adv_m(const int8_t *msk, const double *q, double *dq, const double *u, const double *v,
+int launch_adv_m(const int8_t *msk, const AdvBatch &B, const double *u, const double *v,
                  double *xflx, double *yflx, const AdvC &k, int ny, int nx, int fill, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    F2D_CUDA(cudaFuncSetAttribute(k_adv<UPW, ORDER, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    F2D_CUDA(cudaFuncSetAttribute(k_adv<UPW, ORDER, MASKED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(AdvSmem)));
+    F2D_CUDA(cudaFuncSetAttribute(k_adv<UPW, ORDER, MASKED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sizeof(AdvSmem)));
     attr_set = true;
   }
-  dim3 grid(cdiv(nx - 2 * NH, TX), cdiv(ny - 2 * NH, TY));
+  static AdvMaps M;
+  static const char *notma = getenv("F2D_ADV_TMA");
+  bool tma = !(notma && notma[0] == '0');
+  for (int t = 0; tma && t < B.n; t++) tma = adv_tmap(B.q[t], ny, nx, SH, SW, &M.q[t]);
+  if (tma) tma = adv_tmap(u, ny, nx, TY, UW, &M.u) && adv_tmap(v, ny, nx, TY + 1, VW, &M.v);
+  dim3 grid(cdiv(nx - 2 * NH, TX) * B.n, cdiv(ny - 2 * NH, TY));
   const size_t sm = MASKED ? sizeof(AdvSmem) : offsetof(AdvSmem, m);
-  prof_tag("k_adv<upw%d,order%d,masked%d> %dx%d", (int)UPW, ORDER, (int)MASKED, nx - 2 * NH, ny - 2 * NH);
-  k_adv<UPW, ORDER, MASKED><<<grid, NT, sm, s>>>(msk, q, dq, u, v, xflx, yflx, k, ny, nx, fill);
+  prof_tag("k_adv<upw%d,order%d,masked%d> %dx%d x%d%s", (int)UPW, ORDER, (int)MASKED, nx - 2 * NH, ny - 2 * NH, B.n,
+           B.xo[0] ? " +stage" : "");
+  if (tma) k_adv<UPW, ORDER, MASKED, true><<<grid, NT, sm, s>>>(msk, B, u, v, xflx, yflx, k, ny, nx, fill, M);
+  else k_adv<UPW, ORDER, MASKED, false><<<grid, NT, sm, s>>>(msk, B, u, v, xflx, yflx, k, ny, nx, fill, M);
   F2D_LAUNCHED();
   return F2D_OK;
 }
 
 template <bool UPW, int ORDER>
-int launch_adv(const int8_t *msk, const double *q, double *dq, const double *u, const double *v,
+int launch_adv(const int8_t *msk, const AdvBatch &B, const double *u, const double *v,
                double *xflx, double *yflx, const AdvC &k, int ny, int nx, int fill, bool masked,
                cudaStream_t s) {
-  if (masked) return launch_adv_m<UPW, ORDER, true>(msk, q, dq, u, v, xflx, yflx, k, ny, nx, fill, s);
-  return launch_adv_m<UPW, ORDER, false>(msk, q, dq, u, v, xflx, yflx, k, ny, nx, fill, s);
+  if (masked) return launch_adv_m<UPW, ORDER, true>(msk, B, u, v, xflx, yflx, k, ny, nx, fill, s);
+  return launch_adv_m<UPW, ORDER, false>(msk, B, u, v, xflx, yflx, k, ny, nx, fill, s);
 }
 
-int adv_common(bool upw, const int8_t *msk, const double *q, double *dq, const double *u, const double *v,
+int adv_common(bool upw, const int8_t *msk, const AdvBatch &B, const double *u, const double *v,
                double *xflx, double *yflx, const double *cst, int nh, int method, int order, int ny, int nx,
                int fill, cudaStream_t s) {
   if (nh != NH) return fail(F2D_ERR_NH, "NHALO = 3 is compulsory with UP5");
-  if (!q || !dq || !u || !v || !cst) return fail(F2D_ERR_ARG, "adv: null pointer");
+  if (B.n < 1 || B.n > ADV_MAXT || !u || !v || !cst) return fail(F2D_ERR_ARG, "adv: null pointer");
+  for (int t = 0; t < B.n; t++) {
+    if (!B.q[t] || !B.dq[t]) return fail(F2D_ERR_ARG, "adv: null pointer");
+    if ((B.xo[t] == nullptr) != (B.xb[t] == nullptr) || (B.xo[t] == nullptr) != (B.xo[0] == nullptr))
+      return fail(F2D_ERR_ARG, "adv: the stage output needs xbase and xout for every tracer of the batch");
+  }
+  if (B.n > 1 && xflx) return fail(F2D_ERR_ARG, "adv: flux outputs are for one tracer at a time");
   if ((xflx == nullptr) != (yflx == nullptr)) return fail(F2D_ERR_ARG, "adv: xflx and yflx go together");
   if (ny < 2 * NH + NH || nx < 2 * NH + NH) return fail(F2D_ERR_ARG, "adv: grid too small");
   if (method != 0 && method != 1) return fail(F2D_ERR_ARG, "adv: flux splitting method must be 0 or 1");
@@ -264,28 +385,36 @@ int adv_common(bool upw, const int8_t *msk, const double *q, double *dq, const d
   bool masked = msk != nullptr;
   if (upw) {
     switch (order) {
-      case 1: return launch_adv<true, 1>(msk, q, dq, u, v, xflx, yflx, k, ny, nx, fill, masked, s);
-      case 3: return launch_adv<true, 3>(msk, q, dq, u, v, xflx, yflx, k, ny, nx, fill, masked, s);
-      case 5: return launch_adv<true, 5>(msk, q, dq, u, v, xflx, yflx, k, ny, nx, fill, masked, s);
+      case 1: return launch_adv<true, 1>(msk, B, u, v, xflx, yflx, k, ny, nx, fill, masked, s);
+      case 3: return launch_adv<true, 3>(msk, B, u, v, xflx, yflx, k, ny, nx, fill, masked, s);
+      case 5: return launch_adv<true, 5>(msk, B, u, v, xflx, yflx, k, ny, nx, fill, masked, s);
     }
     return fail(F2D_ERR_ARG, "adv_upwind: order must be 1, 3 or 5");
   }
   switch (order) {
-    case 2: return launch_adv<false, 2>(msk, q, dq, u, v, xflx, yflx, k, ny, nx, fill, masked, s);
-    case 4: return launch_adv<false, 4>(msk, q, dq, u, v, xflx, yflx, k, ny, nx, fill, masked, s);
-    case 6: return launch_adv<false, 6>(msk, q, dq, u, v, xflx, yflx, k, ny, nx, fill, masked, s);
+    case 2: return launch_adv<false, 2>(msk, B, u, v, xflx, yflx, k, ny, nx, fill, masked, s);
+    case 4: return launch_adv<false, 4>(msk, B, u, v, xflx, yflx, k, ny, nx, fill, masked, s);
+    case 6: return launch_adv<false, 6>(msk, B, u, v, xflx, yflx, k, ny, nx, fill, masked, s);
   }
   return fail(F2D_ERR_ARG, "adv_centered: order must be 2, 4 or 6");
 }
 
 }  // namespace
 
+static AdvBatch one_tracer(const double *q, double *dq) {
+  AdvBatch B = {};
+  B.q[0] = q;
+  B.dq[0] = dq;
+  B.n = 1;
+  return B;
+}
+
 // msk == NULL selects the all-fluid specialisation (no mask reads); callers pass NULL
 // only when every cell of msk, halo included, is 1 (geometry 'perio', grid.py:82-84).
 extern "C" int f2d_adv_upwind(const int8_t *msk, const double *q, double *dq, const double *u, const double *v,
                               double *xflx, double *yflx, const double *cst5, int nh, int method, int order,
                               int ny, int nx, int fill_halo, f2d_stream_t s) {
-  return adv_common(true, msk, q, dq, u, v, xflx, yflx, cst5, nh, method, order, ny, nx, fill_halo, S(s));
+  return adv_common(true, msk, one_tracer(q, dq), u, v, xflx, yflx, cst5, nh, method, order, ny, nx, fill_halo, S(s));
 }
 extern "C" int f2d_adv_centered(const int8_t *msk, const double *q, double *dq, const double *u,
                                 const double *v, double *xflx, double *yflx, const double *cst5, int nh,
@@ -294,5 +423,30 @@ extern "C" int f2d_adv_centered(const int8_t *msk, const double *q, double *dq, 
   // core/fortran_fluxes.f90's adv_centered (flux outputs) has no 6th-order branch: order = 6
   // falls through to its `order.ge.2` two-point mean
   if (xflx != nullptr && order == 6) order = 2;
-  return adv_common(false, msk, q, dq, u, v, xflx, yflx, cst5, nh, 0, order, ny, nx, fill_halo, S(s));
+  return adv_common(false, msk, one_tracer(q, dq), u, v, xflx, yflx, cst5, nh, 0, order, ny, nx, fill_halo, S(s));
+}
+// Operators.rhs_adv (operators.py:214-236) in one launch: the tracers of the model share the
+// velocity tiles; xbase / xout (both NULL, or one pointer per tracer): the kernel also writes the
+// Runge-Kutta stage state xout[t] = xbase[t] + coef * dq[t] (timescheme.py:172-176) with its halo
+extern "C" int f2d_adv_multi(const int8_t *msk, const double *const *q, double *const *dq, int ntracers,
+                             const double *u, const double *v, const double *cst5, int nh, int upwind, int method,
+                             int order, const double *const *xbase, double *const *xout, double coef, int ny,
+                             int nx, int fill_halo, f2d_stream_t s) {
+  if (!q || !dq || ntracers < 1) return fail(F2D_ERR_ARG, "adv_multi: null pointer");
+  if ((xbase == nullptr) != (xout == nullptr)) return fail(F2D_ERR_ARG, "adv_multi: xbase and xout go together");
+  for (int t0 = 0; t0 < ntracers; t0 += ADV_MAXT) {
+    AdvBatch B = {};
+    B.n = ntracers - t0 < ADV_MAXT ? ntracers - t0 : ADV_MAXT;
+    B.coef = coef;
+    for (int t = 0; t < B.n; t++) {
+      B.q[t] = q[t0 + t];
+      B.dq[t] = dq[t0 + t];
+      B.xb[t] = xbase ? xbase[t0 + t] : nullptr;
+      B.xo[t] = xout ? xout[t0 + t] : nullptr;
+    }
+    int rc = adv_common(upwind != 0, msk, B, u, v, nullptr, nullptr, cst5, nh, upwind ? method : 0, order, ny, nx,
+                        fill_halo, S(s));
+    if (rc != F2D_OK) return rc;
+  }
+  return F2D_OK;
 }

@@ -91,6 +91,15 @@ int f2d_adv_centered(const int8_t *msk, const double *q, double *dq, const doubl
                      const double *v, double *xflx, double *yflx, const double *cst5,
                      int nh, int method, int order, int ny, int nx, int fill_halo,
                      f2d_stream_t stream);
+/* Operators.rhs_adv (core/operators.py:214-236: the loop over the tracer list) in ONE launch: the
+ * tracers of the model share the velocity tiles.  q, dq (and xbase, xout) are HOST arrays of
+ * ntracers device pointers.  xbase / xout both NULL, or both given: the kernel then also writes
+ * the Runge-Kutta stage state xout[t] = xbase[t] + coef*dq[t], halo included
+ * (core/timescheme.py:172-176; the product is rounded before the sum, as numpy does). */
+int f2d_adv_multi(const int8_t *msk, const double *const *q, double *const *dq, int ntracers,
+                  const double *u, const double *v, const double *cst5, int nh, int upwind, int method,
+                  int order, const double *const *xbase, double *const *xout, double coef, int ny, int nx,
+                  int fill_halo, f2d_stream_t stream);
 
 /* ---- core/fortran_operators.f90 */
 /* :44-64 celltocorner(xr,xp) */

@@ -153,6 +153,16 @@ class EmuLib(object):
     def adv_upwind(self, *a):
         return self._adv(True, *a[:-1])
 
+    def adv_multi(self, msk, q, dq, ntr, u, v, cst5, nh, upwind, method, order, xbase, xout, coef, ny, nx, fill,
+                  stream):
+        for k in range(ntr):
+            rc = self._adv(bool(upwind), msk, q[k], dq[k], u, v, None, None, cst5, nh, method, order, ny, nx, fill)
+            if rc:
+                return rc
+            if xout is not None:
+                f64(xout[k], ny, nx)[...] = f64(xbase[k], ny, nx)+coef*f64(dq[k], ny, nx)
+        return 0
+
     def adv_centered(self, *a):
         return self._adv(False, *a[:-1])
 

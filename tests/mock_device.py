@@ -46,6 +46,8 @@ def _summary(a):
     if isinstance(a, (float, np.floating)):
         return float("%.12g" % float(a))
     if isinstance(a, ctypes.Array):
+        if a._type_ is ctypes.c_void_p:        # host array of device pointers (f2d_adv_multi)
+            return [_pointer(v) if v else "N" for v in a]
         return [float("%.12g" % float(v)) for v in a]
     if isinstance(a, ctypes.c_void_p):
         return _pointer(a.value) if a.value else "N"

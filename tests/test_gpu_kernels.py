@@ -100,6 +100,50 @@ def test_advection(L, shape, mkind, order, method):
                 g.check(g.host(dfy), fyr, strict, what="yflx")
 
 
+@pytest.mark.parametrize("shape", [(38, 70), (70, 134), (150, 134), (134, 262)])
+@pytest.mark.parametrize("mkind", ["none", "random"])
+@pytest.mark.parametrize("ntr", [1, 2, 5])
+def test_advection_multi_and_fused_stage(L, shape, mkind, ntr):
+    """f2d_adv_multi: the tracers of a model in one launch (operators.py:214-236), with and without
+    the fused Runge-Kutta stage output xout = xbase + coef*dq (timescheme.py:172-176): against the
+    oracle's adv_upwind + fillhalo per tracer and numpy's x + c*dx, halo included"""
+    g = _gpu()
+    lib, strict = L
+    ny, nx = shape
+    rng = np.random.default_rng(ny + nx + ntr)
+    msk = rand_mask(rng, ny, nx, "ones" if mkind == "none" else mkind)
+    u = rng.standard_normal(shape) * 0.3
+    v = rng.standard_normal(shape) * 0.3
+    cst = np.array([1. / 64, 1. / 48, 0.05, 0.9, 0.05])
+    cst_c = (ctypes.c_double * 5)(*cst)
+    qs = [rng.standard_normal(shape) for _ in range(ntr)]
+    xbs = [rng.standard_normal(shape) for _ in range(ntr)]   # (its halo need not hold periodic images)
+    refs = []
+    for q in qs:
+        ref = np.zeros(shape)
+        K.fortran_advection.adv_upwind(msk, q, ref, u, v, cst, 3, 1, 5)
+        K.fortran_multigrid.fillhalo(ref, 3)
+        refs.append(ref)
+    coef = 0.37
+    dm = None if mkind == "none" else g.dev(msk)
+    du, dv = g.keep(u), g.keep(v)
+    for fused in (False, True):
+        dqs = [g.dev(np.zeros(shape)) for _ in range(ntr)]
+        xos = [g.dev(np.full(shape, 7.)) for _ in range(ntr)]
+        dq_in = [g.keep(q) for q in qs]
+        dxb = [g.keep(x) for x in xbs]
+        arr = lambda ts: (ctypes.c_void_p * ntr)(*[t.data_ptr() for t in ts])
+        lib.adv_multi(g.ptr(dm), arr(dq_in), arr(dqs), ntr, g.ptr(du), g.ptr(dv), cst_c, 3, 1, 1, 5,
+                      arr(dxb) if fused else None, arr(xos) if fused else None, coef, ny, nx, 1, g.stream())
+        for k in range(ntr):
+            g.check(g.host(dqs[k]), refs[k], strict, what="dq[%d]" % k)
+            if fused:
+                # numpy: x + coef*dx (product rounded, then the sum); both builds must give exactly
+                # that from the dq they computed
+                got_dq = g.host(dqs[k])
+                np.testing.assert_array_equal(g.host(xos[k]), xbs[k] + coef*got_dq)
+
+
 def test_advection_umax_zero_and_bad_nh(L):
     g = _gpu()
     lib, strict = L

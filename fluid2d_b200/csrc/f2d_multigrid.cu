@@ -448,6 +448,68 @@ k_resid_sumsq(fused::LevelK L, const double *__restrict__ x, const double *__res
   acc = block_sum(acc);
   if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = acc;
 }
+// The same operator on 64 x 32 tiles whose x tile (halo 1) arrives by TMA: the nine values of a
+// point come from shared memory (3 loads per point with the marching window), b and the output go
+// straight between registers and HBM.  Used whenever a tensor map of x exists (even nx, level at
+// least one box large); the strip kernel above is the fallback.
+constexpr int QTX = 64, QTY = 32, QW = QTX + 2, QH = QTY + 2;
+struct SumsqSmem {
+  alignas(128) double xs[QH][QW];
+  alignas(8) uint64_t bar;
+};
+template <bool MASKED, bool STORED>
+__global__ void __launch_bounds__(RST, 4)
+k_resid_sumsq_tma(fused::LevelK L, const double *__restrict__ b, double *__restrict__ r, double *__restrict__ partial,
+                  const __grid_constant__ CUtensorMap tmx) {
+  __shared__ SumsqSmem S;
+  const int ny = L.ny, nx = L.nx, t = threadIdx.x;
+  const int i0 = NH + blockIdx.x * QTX, j0 = NH + blockIdx.y * QTY;
+  if (t == 0) f2d::mbar_init(&S.bar, 1);
+  __syncthreads();
+  if (t == 0) {
+    f2d::mbar_expect_tx(&S.bar, QH * QW * 8);
+    f2d::tma_load_2d(&S.xs[0][0], &tmx, &S.bar, i0 - 1, j0 - 1);
+  }
+  const int tx = t & (QTX - 1), tg = t >> 6;
+  const int i = i0 + tx, jf = j0 + tg * 8;
+  const bool col_ok = i <= nx - 1 - NH;
+  double bv[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) bv[k] = (col_ok && jf + k <= ny - 1 - NH) ? b[(size_t)(jf + k) * nx + i] : 0.;
+  fused::Coefs<MASKED, STORED> kc;
+  if (!MASKED && !STORED) kc.load(L, 0, nullptr, 0);
+  f2d::mbar_wait(&S.bar, 0);
+  double acc = 0.;
+  if (col_ok) {
+    const bool rimcol = i < 2 * NH || i >= nx - 2 * NH;
+    const double *sp = &S.xs[tg * 8 + 1][tx + 1];       // centre of the first point
+    double a0 = sp[-QW - 1], a1 = sp[-QW], a2 = sp[-QW + 1];
+    double m0 = sp[-1], m1 = sp[0], m2 = sp[1];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int j = jf + k;
+      if (j <= ny - 1 - NH) {
+        const double h0 = sp[(k + 1) * QW - 1], h1 = sp[(k + 1) * QW], h2 = sp[(k + 1) * QW + 1];
+        const size_t g = (size_t)j * nx + i;
+        double val = 0.;
+        if (!MASKED || L.msk[g] != 0) {
+          fused::Coefs<MASKED, STORED> kk;
+          if (MASKED || STORED) kk.load(L, g, MASKED ? L.msk + g : nullptr, nx); else kk = kc;
+          const double cdiag = STORED ? L.A[4 * (size_t)ny * nx + g] : L.c[4];
+          val = fused::resid_val<MASKED, STORED>(L, kk, cdiag, a0, a1, a2, m0, m1, m2, h0, h1, h2, bv[k]);
+        }
+        r[g] = val;
+        if (rimcol || j < 2 * NH || j >= ny - 2 * NH)
+          for_each_halo_image(j, i, ny, nx, NH, [&](int jj, int ii) { r[(size_t)jj * nx + ii] = val; }, L.ywrap != 0);
+        acc += val * val;
+        a0 = m0; a1 = m1; a2 = m2;
+        m0 = h0; m1 = h1; m2 = h2;
+      }
+    }
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = acc;
+}
 __global__ void __launch_bounds__(RST) k_fold_partials(const double *__restrict__ partial, int n, double *out) {
   double acc = 0.;
   for (int k = threadIdx.x; k < n; k += RST) acc += partial[k];
@@ -609,6 +671,23 @@ int op_residual(f2d_mg *mg, int lev, const double *x, const double *b, double *r
 int op_resid_sumsq_L(f2d_mg *mg, Level &l, const double *x, const double *b, double *r, double *out,
                      cudaStream_t s) {
   fused::LevelK k = level_k(mg, l);
+  CUtensorMap tmx;
+  memset(&tmx, 0, sizeof tmx);
+  if (get_tmap(mg, x, l.ny, l.nx, QH, QW, &tmx)) {
+    dim3 tg(cdiv(l.nx - 2 * NH, QTX), cdiv(l.ny - 2 * NH, QTY));
+    const int ntb = (int)(tg.x * tg.y);
+    if ((size_t)ntb > mg->npartials) return fail(F2D_ERR_ARG, "resid_sumsq: partial-sum buffer too small");
+    prof_tag("k_resid_sumsq<mode%d> %dx%d", l.mode, l.nx - 2 * NH, l.ny - 2 * NH);
+    switch (l.mode) {
+      case 1: k_resid_sumsq_tma<false, false><<<tg, RST, 0, s>>>(k, b, r, mg->partials, tmx); break;
+      case 2: k_resid_sumsq_tma<true, false><<<tg, RST, 0, s>>>(k, b, r, mg->partials, tmx); break;
+      default: k_resid_sumsq_tma<true, true><<<tg, RST, 0, s>>>(k, b, r, mg->partials, tmx); break;
+    }
+    F2D_LAUNCHED();
+    k_fold_partials<<<1, RST, 0, s>>>(mg->partials, ntb, out);
+    F2D_LAUNCHED();
+    return F2D_OK;
+  }
   dim3 grid(cdiv(l.nx - 2 * NH, RST), cdiv(l.ny - 2 * NH, RSR));
   const int nb = (int)(grid.x * grid.y);
   if ((size_t)nb > mg->npartials) return fail(F2D_ERR_ARG, "resid_sumsq: partial-sum buffer too small");
@@ -1237,7 +1316,10 @@ int finish_setup(f2d_mg *mg, double Rd, cudaStream_t s) {
     // per-block partial sums of k_resid_sumsq (finest level of the handle: L[0], or S[0] on slabs)
     size_t nb = 0;
     for (auto *lp : {mg->L.empty() ? nullptr : &mg->L[0], mg->S.empty() ? nullptr : &mg->S[0]})
-      if (lp) nb = std::max(nb, (size_t)cdiv(lp->nx - 2 * NH, RST) * (size_t)cdiv(lp->ny - 2 * NH, RSR));
+      if (lp) {
+        nb = std::max(nb, (size_t)cdiv(lp->nx - 2 * NH, RST) * (size_t)cdiv(lp->ny - 2 * NH, RSR));
+        nb = std::max(nb, (size_t)cdiv(lp->nx - 2 * NH, QTX) * (size_t)cdiv(lp->ny - 2 * NH, QTY));
+      }
     MGC(cudaMalloc(&mg->partials, nb * sizeof(double)));
     mg->npartials = nb;
   }

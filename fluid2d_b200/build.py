@@ -38,6 +38,7 @@ def build(force=False, verbose=False, variants=None):
     os.makedirs(LIBDIR, exist_ok=True)
     newest = _newest_source()
     built = []
+    jobs = []
     for name, extra in VARIANTS.items():
         if variants and name not in variants:
             continue
@@ -52,6 +53,9 @@ def build(force=False, verbose=False, variants=None):
             cmd = [NVCC] + BASE_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
             objs.append(obj)
+        jobs.append((name, out, tag, procs, objs))
+    # every translation unit of every variant compiles at the same time
+    for name, out, tag, procs, objs in jobs:
         log = []
         for src, p in procs:
             o = p.communicate()[0].decode()

@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <utility>
+
 #include "../../include/f2d_b200.h"
 
 struct f2d_comm;
@@ -48,6 +50,35 @@ inline int cuda_fail(cudaError_t e, const char *where) {
   } while (0)
 
 inline cudaStream_t S(f2d_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- programmatic dependent launch (sm_90+) ------------------------------------------------
+// A kernel launched through launch_pdl() may become resident while the kernel in front of it on
+// the stream (or in the captured graph) is still running: its CTAs set up their barriers and
+// indices, then block in pdl_wait() until that kernel has completed and its stores are visible.
+// The launch gap between two small kernels of a multigrid cycle (most of a 256^2 level's cost)
+// is hidden that way.  Rules: a kernel launched by launch_pdl() calls pdl_wait() before its
+// first access to global memory another kernel may have written, and pdl_trigger() as early as
+// it likes (here: at entry).  F2D_PDL=0 turns the attribute off (plain stream order).
+extern int g_pdl;   // -1: not read yet
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

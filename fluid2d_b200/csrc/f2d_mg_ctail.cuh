@@ -346,6 +346,8 @@ __global__ void __launch_bounds__(NT, 1) k_mg_ctail(const __grid_constant__ Para
   C.T = C.B + P.total;
   const Lev &l0 = P.lv[0];
   const Geo G0 = geo(l0, C);
+  f2d::pdl_trigger();
+  f2d::pdl_wait();
   {
     // my band of the rhs (and of the first guess), ghost rows included: the global arrays
     // arrive halo-filled

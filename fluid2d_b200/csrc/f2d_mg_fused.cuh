@@ -275,10 +275,19 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
   const int t = threadIdx.x;
   const int by = PEER ? f2d::peer_tile_row(blockIdx.y, gridDim.y) : blockIdx.y;
   const bool bsouth = PEER && by == 0, bnorth = PEER && by == (int)gridDim.y - 1;
-  if (PEER && (bsouth || bnorth)) f2d::peer_wait(P, bsouth, bnorth);
-  const int i0 = NH + blockIdx.x * TX, j0 = NH + by * TY;
   constexpr bool INTERP = INPUT >= 2;
   constexpr bool HAVE_X = (INPUT == 0 || INPUT == 3);
+  // programmatic dependent launch: barrier and descriptors are set up while the kernel in
+  // front of this one drains; nothing it wrote is touched before pdl_wait()
+  f2d::pdl_trigger();
+  if (use_tma && t == 0) {
+    f2d::mbar_init(&S.bar, 1);
+    if (HAVE_X) f2d::tma_prefetch_desc(&tmx);
+    if (INTERP) f2d::tma_prefetch_desc(&tmc);
+  }
+  f2d::pdl_wait();
+  if (PEER && (bsouth || bnorth)) f2d::peer_wait(P, bsouth, bnorth);
+  const int i0 = NH + blockIdx.x * TX, j0 = NH + by * TY;
   constexpr bool ZERO = INPUT == 1;
   const int cj0 = ((j0 - 2) >> 1) + 1, ci0 = ((i0 - 2) >> 1) + 1;
   // inner tile: every point of the sweep-1 ring and of the output tile is a valid target
@@ -306,7 +315,6 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
   // ---- stage the tiles: TMA boxes (one instruction per tile, zero fill outside the
   // array) or, on levels smaller than a box, per-element asynchronous copies
   if (use_tma) {
-    if (t == 0) f2d::mbar_init(&S.bar, 1);
     __syncthreads();
     if (t == 0) {
       // (PEER) the neighbour's halo rows were observed through the generic proxy
@@ -539,13 +547,19 @@ k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restric
   const int t = threadIdx.x;
   const int by = PEER ? f2d::peer_tile_row(blockIdx.y, gridDim.y) : blockIdx.y;
   const bool bsouth = PEER && by == 0, bnorth = PEER && by == (int)gridDim.y - 1;
+  f2d::pdl_trigger();
+  if (use_tma && t == 0) {
+    f2d::mbar_init(&S.bar, 1);
+    f2d::tma_prefetch_desc(&tmx);
+    f2d::tma_prefetch_desc(&tmb);
+  }
+  f2d::pdl_wait();
   if (PEER && (bsouth || bnorth)) f2d::peer_wait(P, bsouth, bnorth);
   const int ci0 = NH + blockIdx.x * RTX, cj0 = NH + by * RTY;  // first coarse output
   const int fi0 = 2 * ci0 - 3, fj0 = 2 * cj0 - 3;                      // first fine residual point
   // inner tile: the whole residual tile lies strictly inside the fine interior
   const bool inner = (fj0 + RH <= ny - NH) && (fi0 + RW <= nx - NH);
   if (use_tma) {
-    if (t == 0) f2d::mbar_init(&S.bar, 1);
     __syncthreads();
     if (t == 0) {
       if (PEER) asm volatile("fence.proxy.async;" ::: "memory");

@@ -412,6 +412,8 @@ __global__ void __launch_bounds__(NT, 1) k_mg_ptail(const __grid_constant__ Para
   C.T = C.B + total_cells<TOP, NC>();
   constexpr int N0 = G0::N, NX0 = N0 + 2 * NH;
   const int base0 = G0::DIST ? C.rank * G0::R : 0;
+  f2d::pdl_trigger();
+  f2d::pdl_wait();
   {
     // b on own rows +- 1 (loaded +- 2), x (program 1) on own rows +- 2: the global arrays are halo
     // filled, so the rows outside the interior are read at their halo position (global row 3 + j)

@@ -151,6 +151,8 @@ __global__ void k_residual(const int8_t *__restrict__ msk, const double *__restr
 template <bool PEER>
 __global__ void k_restrict(const int8_t *__restrict__ msk2, const double *__restrict__ x1, double *__restrict__ x2,
                            int ny, int nx /*coarse*/, int nx1, int ywrap, f2d::Peer P) {
+  f2d::pdl_trigger();
+  f2d::pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   const size_t c = (size_t)j * nx + i;
@@ -414,6 +416,8 @@ __global__ void __launch_bounds__(RST)
 k_resid_sumsq(fused::LevelK L, const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ r,
               double *__restrict__ partial) {
   const int ny = L.ny, nx = L.nx;
+  f2d::pdl_trigger();
+  f2d::pdl_wait();
   fused::Coefs<MASKED, STORED> kc;
   if (!MASKED && !STORED) kc.load(L, 0, nullptr, 0);
   const int i = NH + blockIdx.x * RST + threadIdx.x;
@@ -464,7 +468,12 @@ k_resid_sumsq_tma(fused::LevelK L, const double *__restrict__ b, double *__restr
   __shared__ SumsqSmem S;
   const int ny = L.ny, nx = L.nx, t = threadIdx.x;
   const int i0 = NH + blockIdx.x * QTX, j0 = NH + blockIdx.y * QTY;
-  if (t == 0) f2d::mbar_init(&S.bar, 1);
+  f2d::pdl_trigger();
+  if (t == 0) {
+    f2d::mbar_init(&S.bar, 1);
+    f2d::tma_prefetch_desc(&tmx);
+  }
+  f2d::pdl_wait();
   __syncthreads();
   if (t == 0) {
     f2d::mbar_expect_tx(&S.bar, QH * QW * 8);
@@ -511,6 +520,8 @@ k_resid_sumsq_tma(fused::LevelK L, const double *__restrict__ b, double *__restr
   if (threadIdx.x == 0) partial[blockIdx.y * gridDim.x + blockIdx.x] = acc;
 }
 __global__ void __launch_bounds__(RST) k_fold_partials(const double *__restrict__ partial, int n, double *out) {
+  f2d::pdl_trigger();
+  f2d::pdl_wait();
   double acc = 0.;
   for (int k = threadIdx.x; k < n; k += RST) acc += partial[k];
   acc = block_sum(acc);
@@ -577,8 +588,8 @@ int launch_smooth2(f2d_mg *mg, Level &l, Level *cl, const double *xin, const dou
   prof_tag("k_smooth2<mode%d,input%d%s> %dx%d", l.mode, INPUT, peer ? ",peer" : "", l.nx - 2 * NH, l.ny - 2 * NH);
 #define F2D_SM2(M, St)                                                                                              \
   do {                                                                                                              \
-    if (peer) fused::k_smooth2<M, St, INPUT, true><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc, acc, P, use_tma, tmx, tmc); \
-    else fused::k_smooth2<M, St, INPUT, false><<<grid, fused::NT, sm, s>>>(k, xin, b, xout, xc, mskc, nxc, nyc, acc, P, use_tma, tmx, tmc);     \
+    if (peer) F2D_CUDA(f2d::launch_pdl(fused::k_smooth2<M, St, INPUT, true>, grid, dim3(fused::NT), sm, s, k, xin, b, xout, xc, mskc, nxc, nyc, acc, P, use_tma, tmx, tmc)); \
+    else F2D_CUDA(f2d::launch_pdl(fused::k_smooth2<M, St, INPUT, false>, grid, dim3(fused::NT), sm, s, k, xin, b, xout, xc, mskc, nxc, nyc, acc, P, use_tma, tmx, tmc));     \
   } while (0)
   switch (l.mode) {
     case 1: F2D_SM2(false, false); break;
@@ -679,12 +690,12 @@ int op_resid_sumsq_L(f2d_mg *mg, Level &l, const double *x, const double *b, dou
     if ((size_t)ntb > mg->npartials) return fail(F2D_ERR_ARG, "resid_sumsq: partial-sum buffer too small");
     prof_tag("k_resid_sumsq<mode%d> %dx%d", l.mode, l.nx - 2 * NH, l.ny - 2 * NH);
     switch (l.mode) {
-      case 1: k_resid_sumsq_tma<false, false><<<tg, RST, 0, s>>>(k, b, r, mg->partials, tmx); break;
-      case 2: k_resid_sumsq_tma<true, false><<<tg, RST, 0, s>>>(k, b, r, mg->partials, tmx); break;
-      default: k_resid_sumsq_tma<true, true><<<tg, RST, 0, s>>>(k, b, r, mg->partials, tmx); break;
+      case 1: F2D_CUDA(f2d::launch_pdl(k_resid_sumsq_tma<false, false>, tg, dim3(RST), 0, s, k, b, r, mg->partials, tmx)); break;
+      case 2: F2D_CUDA(f2d::launch_pdl(k_resid_sumsq_tma<true, false>, tg, dim3(RST), 0, s, k, b, r, mg->partials, tmx)); break;
+      default: F2D_CUDA(f2d::launch_pdl(k_resid_sumsq_tma<true, true>, tg, dim3(RST), 0, s, k, b, r, mg->partials, tmx)); break;
     }
     F2D_LAUNCHED();
-    k_fold_partials<<<1, RST, 0, s>>>(mg->partials, ntb, out);
+    F2D_CUDA(f2d::launch_pdl(k_fold_partials, dim3(1), dim3(RST), 0, s, mg->partials, ntb, out));
     F2D_LAUNCHED();
     return F2D_OK;
   }
@@ -693,12 +704,12 @@ int op_resid_sumsq_L(f2d_mg *mg, Level &l, const double *x, const double *b, dou
   if ((size_t)nb > mg->npartials) return fail(F2D_ERR_ARG, "resid_sumsq: partial-sum buffer too small");
   prof_tag("k_resid_sumsq<mode%d> %dx%d", l.mode, l.nx - 2 * NH, l.ny - 2 * NH);
   switch (l.mode) {
-    case 1: k_resid_sumsq<false, false><<<grid, RST, 0, s>>>(k, x, b, r, mg->partials); break;
-    case 2: k_resid_sumsq<true, false><<<grid, RST, 0, s>>>(k, x, b, r, mg->partials); break;
-    default: k_resid_sumsq<true, true><<<grid, RST, 0, s>>>(k, x, b, r, mg->partials); break;
+    case 1: F2D_CUDA(f2d::launch_pdl(k_resid_sumsq<false, false>, grid, dim3(RST), 0, s, k, x, b, r, mg->partials)); break;
+    case 2: F2D_CUDA(f2d::launch_pdl(k_resid_sumsq<true, false>, grid, dim3(RST), 0, s, k, x, b, r, mg->partials)); break;
+    default: F2D_CUDA(f2d::launch_pdl(k_resid_sumsq<true, true>, grid, dim3(RST), 0, s, k, x, b, r, mg->partials)); break;
   }
   F2D_LAUNCHED();
-  k_fold_partials<<<1, RST, 0, s>>>(mg->partials, nb, out);
+  F2D_CUDA(f2d::launch_pdl(k_fold_partials, dim3(1), dim3(RST), 0, s, mg->partials, nb, out));
   F2D_LAUNCHED();
   return F2D_OK;
 }
@@ -712,8 +723,8 @@ int op_restrict_L(f2d_mg *mg, Level &f, Level &c, const double *xf, double *xc, 
   if (peer && !comm_owns(mg->comm, xc))
     return fail(F2D_ERR_ARG, "restrict: the output of a slab level must live in the symmetric heap");
   prof_tag("k_restrict%s %dx%d", peer ? "<peer>" : "", f.nx - 2 * NH, f.ny - 2 * NH);
-  if (peer) k_restrict<true><<<grid2d(c.ny, c.nx, blk), blk, 0, s>>>(c.msk, xf, xc, c.ny, c.nx, f.nx, c.ywrap, P);
-  else k_restrict<false><<<grid2d(c.ny, c.nx, blk), blk, 0, s>>>(c.msk, xf, xc, c.ny, c.nx, f.nx, c.ywrap, P);
+  if (peer) F2D_CUDA(f2d::launch_pdl(k_restrict<true>, grid2d(c.ny, c.nx, blk), blk, 0, s, c.msk, xf, xc, c.ny, c.nx, f.nx, c.ywrap, P));
+  else F2D_CUDA(f2d::launch_pdl(k_restrict<false>, grid2d(c.ny, c.nx, blk), blk, 0, s, c.msk, xf, xc, c.ny, c.nx, f.nx, c.ywrap, P));
   F2D_LAUNCHED();
   return F2D_OK;
 }
@@ -742,8 +753,8 @@ int op_resid_restrict_L(f2d_mg *mg, Level &l, Level &c, const double *x, const d
   prof_tag("k_resid_restrict<mode%d%s> %dx%d", l.mode, peer ? ",peer" : "", l.nx - 2 * NH, l.ny - 2 * NH);
 #define F2D_RR(M, St)                                                                                         \
   do {                                                                                                        \
-    if (peer) fused::k_resid_restrict<M, St, true><<<grid, fused::NT, sm, s>>>(k, x, b, bc, c.msk, c.ny, c.nx, P, use_tma, tmx, tmb); \
-    else fused::k_resid_restrict<M, St, false><<<grid, fused::NT, sm, s>>>(k, x, b, bc, c.msk, c.ny, c.nx, P, use_tma, tmx, tmb);     \
+    if (peer) F2D_CUDA(f2d::launch_pdl(fused::k_resid_restrict<M, St, true>, grid, dim3(fused::NT), sm, s, k, x, b, bc, c.msk, c.ny, c.nx, P, use_tma, tmx, tmb)); \
+    else F2D_CUDA(f2d::launch_pdl(fused::k_resid_restrict<M, St, false>, grid, dim3(fused::NT), sm, s, k, x, b, bc, c.msk, c.ny, c.nx, P, use_tma, tmx, tmb));     \
   } while (0)
   switch (l.mode) {
     case 1: F2D_RR(false, false); break;
@@ -797,13 +808,15 @@ int ptail_launch_t(const ptail::Params &P, int program, cudaStream_t s, bool pro
   cfg.blockDim = dim3(ptail::NT);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = NC;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (!probe && f2d::pdl_enabled()) ? 2 : 1;
   if (probe) {   // set-up: attributes, and can the device co-schedule such a cluster?
     if (NC > 8 && cudaFuncSetAttribute(ptail::k_mg_ptail<TOP, NC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
       cudaGetLastError();
@@ -869,13 +882,15 @@ int tail_launch(f2d_mg *mg, int program, const double *b_in, const double *x_in,
     cfg.blockDim = dim3(ctail::NT);
     cfg.dynamicSmemBytes = mg->tail_smem;
     cfg.stream = s;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = mg->ctail_nc;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = f2d::pdl_enabled() ? 2 : 1;
     if (mg->tail_const) F2D_CUDA(cudaLaunchKernelEx(&cfg, ctail::k_mg_ctail<false, false>, P, program));
     else F2D_CUDA(cudaLaunchKernelEx(&cfg, ctail::k_mg_ctail<true, true>, P, program));
     F2D_LAUNCHED();
@@ -1035,6 +1050,8 @@ int read_scalars(f2d_mg *mg, int n, cudaStream_t s) {
 // one graph launch and one host read instead of a host round trip per F-cycle.
 __global__ void k_solve_init(const double *dscal, f2d_mg::SolveState *st, cudaGraphConditionalHandle h, double tol,
                              int maxite) {
+  f2d::pdl_trigger();
+  f2d::pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double normb = sqrt(dscal[0]);
   double res0 = 0.;
@@ -1049,6 +1066,8 @@ __global__ void k_solve_init(const double *dscal, f2d_mg::SolveState *st, cudaGr
 }
 __global__ void k_solve_step(const double *dscal, f2d_mg::SolveState *st, cudaGraphConditionalHandle h, double tol,
                              int maxite) {
+  f2d::pdl_trigger();
+  f2d::pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double res = sqrt(dscal[1]) / st->normb;
   const double conv = st->res0 / res;
@@ -1088,7 +1107,8 @@ int build_solve_graph(f2d_mg *mg, double *psi, const double *rhs, double tol, in
   cudaGraphConditionalHandle h;
   e = cudaGraphConditionalHandleCreate(&h, g, 0, cudaGraphCondAssignDefault);
   if (e != cudaSuccess) return abort_capture(cuda_fail(e, "cudaGraphConditionalHandleCreate"));
-  k_solve_init<<<1, 32, 0, s>>>(mg->dscal, mg->dstate, h, tol, maxite);
+  e = f2d::launch_pdl(k_solve_init, dim3(1), dim3(32), 0, s, mg->dscal, mg->dstate, h, tol, maxite);
+  if (e != cudaSuccess) return abort_capture(cuda_fail(e, "k_solve_init"));
   ++g_launches;
   out.pre = g_launches - before;
   e = cudaStreamGetCaptureInfo_v2(s, &status, nullptr, &g, &deps, &ndeps);
@@ -1110,7 +1130,8 @@ int build_solve_graph(f2d_mg *mg, double *psi, const double *rhs, double tol, in
   if (e != cudaSuccess) return abort_capture(cuda_fail(e, "cudaStreamBeginCaptureToGraph"));
   rc = solve_body(mg, psi, rhs, mg->cap2);
   if (rc == F2D_OK) {
-    k_solve_step<<<1, 32, 0, mg->cap2>>>(mg->dscal, mg->dstate, h, tol, maxite);
+    if (f2d::launch_pdl(k_solve_step, dim3(1), dim3(32), 0, mg->cap2, mg->dscal, mg->dstate, h, tol, maxite) != cudaSuccess)
+      rc = F2D_ERR_CUDA;
     ++g_launches;
   }
   e = cudaStreamEndCapture(mg->cap2, nullptr);

@@ -12,6 +12,15 @@ namespace f2d {
 char g_err[512] = "";
 long long g_launches = 0;
 bool g_prof = false;
+int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char *e = getenv("F2D_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  // per-kernel accounting puts an event behind every launch: keep the kernels apart there
+  return g_pdl == 1 && !g_prof;
+}
 namespace {
 cudaStream_t g_prof_stream = nullptr;
 struct ProfMark { std::string name; cudaEvent_t start, end; };   // start == nullptr: the previous mark's end

@@ -32,6 +32,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned phase) {
         : "memory");
   } while (!ok);
 }
+// descriptor fetch ahead of the first copy that uses it (a kernel parameter: legal before
+// griddepcontrol.wait, the tensor map is not written by any kernel)
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)tm) : "memory");
+}
 // box whose first element is (row y, column x) of the 2-D array described by tm -> dst.
 // x * 8 bytes must be a multiple of 16 (x even): an odd innermost coordinate raises
 // "illegal instruction" on sm_100 (measured, tools/tma_probe.cu); y is unconstrained.

@@ -103,6 +103,9 @@ def kernel_bytes_per_cell(name):
     m = re.match(r"k_restrict(<peer>)? (\d+)x(\d+)", name)
     if m:
         return 10., int(m.group(2))*int(m.group(3))
+    m = re.match(r"k_zsmooth_rr<mode1> (\d+)x(\d+)", name)
+    if m:   # b read once; t written; the coarse right-hand side written (a quarter of the cells)
+        return 18., int(m.group(1))*int(m.group(2))
     m = re.match(r"k_adv<upw\d,order\d,masked(\d)> (\d+)x(\d+)", name)
     if m:
         return 32.+float(m.group(1)), int(m.group(2))*int(m.group(3))
@@ -193,6 +196,9 @@ def isolated_times(lib, r, mgh, table, torch, reps=10):
         m = re.match(r"k_restrict(<peer>)? (\d+)x(\d+)", name)
         if m and (int(m.group(2)), int(m.group(3))) in shapes:
             us = timed(5, shapes[(int(m.group(2)), int(m.group(3)))])
+        m = re.match(r"k_zsmooth_rr<mode1> (\d+)x(\d+)", name)
+        if m and (int(m.group(1)), int(m.group(2))) in shapes:
+            us = timed(9, shapes[(int(m.group(1)), int(m.group(2)))])
         if name.startswith("k_resid_sumsq"):
             us = timed(6, 0)
         m = re.match(r"k_mg_[cp]?tail<program(\d)>", name)
@@ -526,7 +532,7 @@ def gpu_main(args):
     table, us_nograph = kernel_table(lib, r, f2d, peak, (rows, n))
     dram = dram_traffic_table()
     for row in table:
-        row["dram_bytes_per_launch"] = dram.get(row["kernel"].replace(",peer", ""))
+        row["dram_bytes_per_launch"] = dram.get(row["kernel"].replace(",peer", "").replace(" +stage", ""))
 
     # ---- the level-0 smoother and the V-cycle timed alone
     if slabs:
@@ -644,9 +650,14 @@ def gpu_main(args):
     # dominant kernel = the largest share of the step in the accounting above, among the
     # bandwidth-bound kernels (the latency-bound tail is listed in the table without a roofline)
     dom = next((row for row in table if row["achieved_gbs"]), None)
+    # DRAM bytes of one whole step as ncu counted them (every kernel of an ungraphed 4096^2 step,
+    # tools/ncu_step_dram.py -> profiles/r02_step_dram_bytes.json); only for the case it was taken on
     step_dram = None
-    if dram and all(row["dram_bytes_per_launch"] is not None for row in table if row["share"] > 0.01):
-        step_dram = sum((row["dram_bytes_per_launch"] or 0.)*row["launches_per_step"] for row in table)
+    if config == "turb" and world == 1 and n == 4096 and T == 1:
+        try:
+            step_dram = json.load(open(os.path.join(REPO, "profiles", "r02_step_dram_bytes.json")))["step_total_bytes"]
+        except Exception:
+            step_dram = None
     line = {
         "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,

@@ -58,7 +58,7 @@ inline cudaStream_t S(f2d_stream_t s) { return reinterpret_cast<cudaStream_t>(s)
 // The launch gap between two small kernels of a multigrid cycle (most of a 256^2 level's cost)
 // is hidden that way.  Rules: a kernel launched by launch_pdl() calls pdl_wait() before its
 // first access to global memory another kernel may have written, and pdl_trigger() as early as
-// it likes (here: at entry).  F2D_PDL=0 turns the attribute off (plain stream order).
+// it likes (here: at entry).  F2D_PDL=1 turns the attribute on (default: plain stream order).
 extern int g_pdl;   // -1: not read yet
 bool pdl_enabled();
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -138,7 +138,7 @@ __device__ __forceinline__ double jacobi_at(const fused::LevelK &L, const fused:
   const int nx = L.nx;
   const int c = jl * nx + i;
   const size_t g = (size_t)(base + jl) * nx + i;
-  if (MASKED && L.msk[g] == 0) return 0.;
+  if (MASKED && __ldg(L.msk + g) == 0) return 0.;
   fused::Coefs<MASKED, STORED> k;
   if (MASKED || STORED) k.load(L, g, MASKED ? L.msk + g : nullptr, nx); else k = kc;
   if (ZERO) return fused::jacobi_val<MASKED, STORED>(L, k, 0., 0., 0., 0., 0., 0., 0., 0., 0., b[c]);
@@ -195,10 +195,10 @@ __device__ void residual(const Params &P, const Ctx &C, int l) {
     const int c = jl * nx + i;
     const size_t g = (size_t)(G.base + jl) * nx + i;
     double val = 0.;
-    if (!MASKED || L.msk[g] != 0) {
+    if (!MASKED || __ldg(L.msk + g) != 0) {
       fused::Coefs<MASKED, STORED> k;
       if (MASKED || STORED) k.load(L, g, MASKED ? L.msk + g : nullptr, nx); else k = kc;
-      const double cdiag = STORED ? L.A[4 * (size_t)L.ny * nx + g] : L.c[4];
+      const double cdiag = STORED ? __ldg(L.A + 4 * (size_t)L.ny * nx + g) : L.c[4];
       const double *q = x + c;
       val = fused::resid_val<MASKED, STORED>(L, k, cdiag, q[-nx - 1], q[-nx], q[-nx + 1], q[-1], q[0], q[1], q[nx - 1],
                                              q[nx], q[nx + 1], b[c]);
@@ -228,7 +228,7 @@ __device__ void restrict_to(const Params &P, const Ctx &C, int l, const double *
     const int t = p >> lc.lgn, i = NH + (p & nm);
     const int jl = NH + jbase + t;                 // coarse row in the coarse array of this CTA
     double val = 0.;
-    if (!MASKED || Lc.msk[(size_t)(gbase + jl) * nxc + i] != 0) {
+    if (!MASKED || __ldg(Lc.msk + (size_t)(gbase + jl) * nxc + i) != 0) {
       // fine centre: local fine row 2*(NH + t) - 2 (band coordinates), column 2*i - 2
       const double *f = xf + (2 * (NH + t) - 2) * nxf + (2 * i - 2);
       val = 0.25 * f[0] + 0.125 * (((f[-1] + f[1]) + f[-nxf]) + f[nxf]) +
@@ -264,7 +264,7 @@ __device__ void interpolate(const Params &P, const Ctx &C, int l, bool add) {
   for (int p = threadIdx.x; p < cnt; p += NT) {
     const int jl = p / nx, i = p - jl * nx;
     double iv = 0.;
-    if (!MASKED || Lf.msk[(size_t)(G.base + jl) * nx + i] > 0) {
+    if (!MASKED || __ldg(Lf.msk + (size_t)(G.base + jl) * nx + i) > 0) {
       const int kl = ((jl >> 1) + 1 + shift) * nxc + (i >> 1) + 1;
       const int pj = jl & 1, pi = i & 1;
       const int8_t *mc = Lc.msk + (size_t)gbc * nxc + kl;   // mask of the same coarse cell (global array)
@@ -272,13 +272,13 @@ __device__ void interpolate(const Params &P, const Ctx &C, int l, bool add) {
       if (!pj && !pi) {
         iv = c0[0];
       } else if (!pj) {
-        const int s = MASKED ? mc[0] + mc[1] : 2;
+        const int s = MASKED ? __ldg(mc) + __ldg(mc + 1) : 2;
         iv = (c0[0] + c0[1]) * fused::interp_w2(s);
       } else if (!pi) {
-        const int s = MASKED ? mc[0] + mc[nxc] : 2;
+        const int s = MASKED ? __ldg(mc) + __ldg(mc + nxc) : 2;
         iv = (c0[0] + c0[nxc]) * fused::interp_w2(s);
       } else {
-        const int s = MASKED ? mc[0] + mc[1] + mc[nxc] + mc[nxc + 1] : 4;
+        const int s = MASKED ? __ldg(mc) + __ldg(mc + 1) + __ldg(mc + nxc) + __ldg(mc + nxc + 1) : 4;
         iv = fused::interp_w4(s) * (((c0[0] + c0[1]) + c0[nxc]) + c0[nxc + 1]);
       }
     }

@@ -43,14 +43,24 @@ template <bool MASKED, bool STORED>
 struct Coefs {
   double sw, s, se, w, e, nw, n, ne, c3;
   // m: pointer to the centre of a mask window with row stride ms (MASKED only)
+  // STORED, in two steps, so that a column strip can issue the loads of ALL its rows before it
+  // waits for the first of them (one round trip to L2 per sweep instead of one per row):
+  // load_raw leaves the diagonal in c3, finish turns it into omega / |diagonal|.
+  // Matrices and masks are written at set-up only: non-coherent loads (LDG.CONSTANT), which
+  // the barriers and fences of the cycle kernels do not throw out of L1.
+  __device__ __forceinline__ void load_raw(const LevelK &L, size_t g) {
+    size_t pl = (size_t)L.ny * L.nx;
+    const double *A1 = L.A, *A2 = L.A + pl, *A3 = L.A + 2 * pl, *A4 = L.A + 3 * pl, *A5 = L.A + 4 * pl;
+    int nx = L.nx;
+    sw = __ldg(A1 + g); s = __ldg(A2 + g); se = __ldg(A3 + g); w = __ldg(A4 + g);
+    e = __ldg(A4 + g + 1); nw = __ldg(A3 + g + nx - 1); n = __ldg(A2 + g + nx); ne = __ldg(A1 + g + nx + 1);
+    c3 = __ldg(A5 + g);
+  }
+  __device__ __forceinline__ void finish(const LevelK &L) { c3 = L.c1 / fabs(c3); }
   __device__ __forceinline__ void load(const LevelK &L, size_t g, const int8_t *m, int ms) {
     if (STORED) {
-      size_t pl = (size_t)L.ny * L.nx;
-      const double *A1 = L.A, *A2 = L.A + pl, *A3 = L.A + 2 * pl, *A4 = L.A + 3 * pl, *A5 = L.A + 4 * pl;
-      int nx = L.nx;
-      sw = A1[g]; s = A2[g]; se = A3[g]; w = A4[g];
-      e = A4[g + 1]; nw = A3[g + nx - 1]; n = A2[g + nx]; ne = A1[g + nx + 1];
-      c3 = L.c1 / fabs(A5[g]);
+      load_raw(L, g);
+      finish(L);
     } else if (MASKED) {
       sw = m[-ms - 1] ? L.c[0] : 0.; s = m[-ms] ? L.c[1] : 0.; se = m[-ms + 1] ? L.c[2] : 0.;
       w = m[-1] ? L.c[3] : 0.;       e = m[1] ? L.c[3] : 0.;
@@ -232,6 +242,17 @@ __device__ __forceinline__ void jacobi_strip(const LevelK &L, const Coefs<MASKED
     wa0 = mp[-MLD - 1]; wa1 = mp[-MLD]; wa2 = mp[-MLD + 1];
     wm0 = mp[-1]; wm1 = mp[0]; wm2 = mp[1];
   }
+  // stored coefficients: every row's loads are issued here, fluid cell or not (the row-by-row
+  // form paid one L2 round trip per row: 13 us per kernel on a 256 x 64 level against 7 us for
+  // the constant-stencil kernel)
+  Coefs<MASKED, STORED> kpre[STORED ? NR : 1];
+  if (STORED) {
+#pragma unroll
+    for (int k = 0; k < NR; k++) {
+      const bool okk = k < nr && (!GUARD || (j + k >= lo && j + k <= ny - 1 - lo && i >= lo && i <= nx - 1 - lo));
+      if (okk) kpre[k].load_raw(L, g + (size_t)k * nx);
+    }
+  }
 #pragma unroll
   for (int k = 0; k < NR; k++) {
     if (k < nr) {
@@ -242,11 +263,13 @@ __device__ __forceinline__ void jacobi_strip(const LevelK &L, const Coefs<MASKED
       const bool ok = !GUARD || (j + k >= lo && j + k <= ny - 1 - lo && i >= lo && i <= nx - 1 - lo);
       if (ok) {
         double val = 0.;
+        // stored coefficients are fetched whether the cell is fluid or not: loads that do not hang
+        // on the mask test can be issued ahead of the rows before them
+        Coefs<MASKED, STORED> kk;
+        if (STORED) { kk = kpre[k]; kk.finish(L); }
         if (!MASKED || (MWIN ? wm1 : (int)mp[k * MLD]) != 0) {
-          Coefs<MASKED, STORED> kk;
           if (MWIN) kk.from_window(L, wa0, wa1, wa2, wm0, wm2, wh0, wh1, wh2);
-          else if (STORED) kk.load(L, g + (size_t)k * nx, nullptr, MLD);
-          else kk = kc;
+          else if (!STORED) kk = kc;
           val = jacobi_val<MASKED, STORED>(L, kk, a0, a1, a2, m0, m1, m2, h0, h1, h2, bget(k));
         }
         out(k, val);
@@ -474,7 +497,7 @@ __device__ __noinline__ double resid_global(const LevelK &L, const double *__res
   if (MASKED && L.msk[g] == 0) return 0.;
   Coefs<MASKED, STORED> k;
   k.load(L, g, MASKED ? L.msk + g : nullptr, nx);
-  double cdiag = STORED ? L.A[4 * (size_t)L.ny * nx + g] : L.c[4];
+  double cdiag = STORED ? __ldg(L.A + 4 * (size_t)L.ny * nx + g) : L.c[4];
   return resid_val<MASKED, STORED>(L, k, cdiag, x[g - nx - 1], x[g - nx], x[g - nx + 1], x[g - 1], x[g], x[g + 1],
                                    x[g + nx - 1], x[g + nx], x[g + nx + 1], b[g]);
 }
@@ -505,6 +528,16 @@ __device__ __forceinline__ void resid_strip(const LevelK &L, const Coefs<MASKED,
     wa0 = mp[-RXW - 1]; wa1 = mp[-RXW]; wa2 = mp[-RXW + 1];
     wm0 = mp[-1]; wm1 = mp[0]; wm2 = mp[1];
   }
+  // stored coefficients: all rows' loads first (see jacobi_strip); rows this strip evaluates in
+  // place, i.e. inside [NH, n-NH) on GUARD tiles
+  Coefs<MASKED, STORED> kpre[STORED ? NR : 1];
+  if (STORED) {
+#pragma unroll
+    for (int k = 0; k < NR; k++) {
+      const bool okk = k < nr && (!GUARD || (j + k < ny - NH && i < nx - NH));
+      if (okk) kpre[k].load_raw(L, g + (size_t)k * nx);
+    }
+  }
 #pragma unroll
   for (int k = 0; k < NR; k++) {
     if (k < nr) {
@@ -523,9 +556,10 @@ __device__ __forceinline__ void resid_strip(const LevelK &L, const Coefs<MASKED,
       } else if (!MASKED || (MWIN ? wm1 : (int)mp[k * RXW]) != 0) {
         Coefs<MASKED, STORED> kk;
         if (MWIN) kk.from_window(L, wa0, wa1, wa2, wm0, wm2, wh0, wh1, wh2);
-        else if (STORED) kk.load(L, g + (size_t)k * nx, nullptr, RXW);
+        else if (STORED) kk = kpre[k];
         else kk = kc;
-        double cdiag = STORED ? L.A[4 * (size_t)ny * nx + g + (size_t)k * nx] : L.c[4];
+        // (the residual uses the diagonal itself, not omega / |diagonal|: kpre holds it raw in c3)
+        double cdiag = STORED ? kk.c3 : L.c[4];
         val = resid_val<MASKED, STORED>(L, kk, cdiag, a0, a1, a2, m0, m1, m2, h0, h1, h2, bp[k * RBP]);
       }
       rp[k * RBP] = val;
@@ -537,7 +571,7 @@ __device__ __forceinline__ void resid_strip(const LevelK &L, const Coefs<MASKED,
 }
 
 template <bool MASKED, bool STORED, bool PEER>
-__global__ void __launch_bounds__(NT, MASKED ? 4 : 5)
+__global__ void __launch_bounds__(NT, STORED ? 1 : (MASKED ? 4 : 5))   // stored: the strip's coefficients live in registers
 k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ bc,
                  const int8_t *__restrict__ mskc, int nyc, int nxc, f2d::Peer P, int use_tma,
                  const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmb) {
@@ -638,6 +672,142 @@ k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restric
     }
   }
   if (PEER && (bsouth || bnorth)) f2d::peer_done(P, gridDim.x * (gridDim.y == 1 ? 1u : 2u));
+}
+
+// ---------------------------------------------------------------------------
+// k_zsmooth_resid_restrict: the whole visit of a level on the way down, below the level a
+// cycle starts from (hierarchy.py:100-107: x = 0; smooth(x, b, npre = 1); residual; restrict)
+//     t  = S2(0, b)          (double sweep from a zero first guess)
+//     bc = R(b - A t)
+// in ONE kernel that reads b once: the first sweep of a zero guess is pointwise
+// (y = 0*c2 + c3*(0 - b) = -(c3*b), exactly), so sweep 2 forms its 3x3 window of y from the b tile
+// on the fly; t stays in shared memory for the residual, the residual replaces b in place, the
+// restriction reads it from there.  Replaces k_smooth2<INPUT = 1> + k_resid_restrict (two
+// launches, t and b read back through TMA) on ALL-FLUID DOUBLY PERIODIC levels, where a halo
+// cell evaluated in place from halo-filled inputs IS the periodic image of its source, bit for
+// bit -- so no tile needs a guard: for every tile the b tile (residual tile + 2 rings) lies
+// inside the array (rows / columns 1 .. n-1).
+// Coarse tile RTX x RTY at (cj0, ci0); fine residual tile RH x RW from (fj0, fi0) = 2*(cj0, ci0) - 3;
+// t tile = + 1 ring, b tile = + 2 rings.
+// ---------------------------------------------------------------------------
+constexpr int ZBH = RH + 4, ZBW = RW + 4, ZBP = ZBW + 1;   // b tile 37 x 69; the TMA box starts one column early (even)
+constexpr int ZTH = RH + 2, ZTW = RW + 2, ZTP = ZTW + 1;   // t tile 35 x 67
+static_assert(ZBP % 2 == 0, "TMA boxes need an even number of doubles per row");
+struct ZrrSmem {
+  alignas(128) double bs[ZBH][ZBP];   // b tile (ring 2): tile column c sits at bs[.][c + 1]; later the residual in place
+  alignas(128) double ts[ZTH][ZTP];   // t tile (ring 1)
+  alignas(8) uint64_t bar;
+};
+// t at t-tile point (rho, c) from the b tile: window of y = -(c3*b) at b-tile rows rho..rho+2,
+// columns c..c+2, right-hand side b-tile (rho+1, c+1)
+__device__ __forceinline__ double zsmooth_point(const LevelK &L, const Coefs<false, false> &kc, const ZrrSmem &S,
+                                                int rho, int c) {
+  const double nc3 = -kc.c3;
+  const double *p = &S.bs[rho][c + 1];
+  return jacobi_val<false, false>(L, kc, nc3 * p[0], nc3 * p[1], nc3 * p[2], nc3 * p[ZBP], nc3 * p[ZBP + 1],
+                                  nc3 * p[ZBP + 2], nc3 * p[2 * ZBP], nc3 * p[2 * ZBP + 1], nc3 * p[2 * ZBP + 2],
+                                  p[ZBP + 1]);
+}
+__global__ void __launch_bounds__(NT, 4)
+k_zsmooth_resid_restrict(LevelK L, double *__restrict__ tout, double *__restrict__ bc, int nyc, int nxc,
+                         const __grid_constant__ CUtensorMap tmb) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ZrrSmem &S = *reinterpret_cast<ZrrSmem *>(smem_raw);
+  const int ny = L.ny, nx = L.nx;
+  const int t = threadIdx.x;
+  const int ci0 = NH + blockIdx.x * RTX, cj0 = NH + blockIdx.y * RTY;
+  const int fi0 = 2 * ci0 - 3, fj0 = 2 * cj0 - 3;
+  f2d::pdl_trigger();
+  if (t == 0) {
+    f2d::mbar_init(&S.bar, 1);
+    f2d::tma_prefetch_desc(&tmb);
+  }
+  f2d::pdl_wait();
+  __syncthreads();
+  if (t == 0) {
+    f2d::mbar_expect_tx(&S.bar, ZBH * ZBP * 8);
+    f2d::tma_load_2d(&S.bs[0][0], &tmb, &S.bar, fi0 - 3, fj0 - 2);
+  }
+  Coefs<false, false> kc;
+  kc.load(L, 0, nullptr, 0);
+  const double nc3 = -kc.c3;
+  const int tx = t & 63, tg = t >> 6;
+  f2d::mbar_wait(&S.bar, 0);
+  // ---- t = S2(0, b) on the t tile (35 x 67): column strips of 9, 9, 9, 8 rows with the 3x3
+  // window of y in registers; columns 64..66 point-wise.  The tile's own 32 x 64 points
+  // (t-tile rows 1..32, columns 1..64) also go to global memory, with their halo images.
+  const bool rimf = (fj0 < 2 * NH) || (fi0 < 2 * NH) || (fj0 + 2 * RTY > ny - 2 * NH) || (fi0 + 2 * RTX > nx - 2 * NH);
+  auto put_t = [&](int rho, int c, double val) {
+    S.ts[rho][c] = val;
+    if (rho >= 1 && rho <= 2 * RTY && c >= 1 && c <= 2 * RTX) {
+      const int j = fj0 - 1 + rho, i = fi0 - 1 + c;
+      tout[(size_t)j * nx + i] = val;
+      if (rimf)
+        f2d::for_each_halo_image(j, i, ny, nx, NH, [&](int j2, int i2) { tout[(size_t)j2 * nx + i2] = val; });
+    }
+  };
+  {
+    const int r0 = tg * 9, nr = tg < 3 ? 9 : 8;
+    const double *p = &S.bs[r0][tx + 1];
+    double a0 = nc3 * p[0], a1 = nc3 * p[1], a2 = nc3 * p[2];
+    double m0 = nc3 * p[ZBP], m1 = nc3 * p[ZBP + 1], m2 = nc3 * p[ZBP + 2];
+    double bm = p[ZBP + 1];   // b at the window centre
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      if (k < nr) {
+        const double *q = p + (k + 2) * ZBP;
+        const double bh = q[1];
+        const double h0 = nc3 * q[0], h1 = nc3 * bh, h2 = nc3 * q[2];
+        put_t(r0 + k, tx, jacobi_val<false, false>(L, kc, a0, a1, a2, m0, m1, m2, h0, h1, h2, bm));
+        a0 = m0; a1 = m1; a2 = m2;
+        m0 = h0; m1 = h1; m2 = h2;
+        bm = bh;
+      }
+    }
+    if (t < 3 * ZTH) {
+      const int rho = t / 3, c = 64 + t % 3;
+      put_t(rho, c, zsmooth_point(L, kc, S, rho, c));
+    }
+  }
+  __syncthreads();
+  // ---- residual on the 33 x 65 tile, in place over b: residual-tile (rho, c) = t-tile centre
+  // (rho+1, c+1) = b-tile (rho+2, c+2)
+  {
+    const int r0 = tg * 8 + (tg < 1 ? 0 : 1), nr = tg < 1 ? 9 : 8;
+    const double cdiag = L.c[4];
+    auto strip = [&](int rho0, int c, int n) {
+      const double *p = &S.ts[rho0][c];
+      double *bp = &S.bs[rho0 + 2][c + 3];
+      double a0 = p[0], a1 = p[1], a2 = p[2];
+      double m0 = p[ZTP], m1 = p[ZTP + 1], m2 = p[ZTP + 2];
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        if (k < n) {
+          const double *q = p + (k + 2) * ZTP;
+          const double h0 = q[0], h1 = q[1], h2 = q[2];
+          bp[k * ZBP] = resid_val<false, false>(L, kc, cdiag, a0, a1, a2, m0, m1, m2, h0, h1, h2, bp[k * ZBP]);
+          a0 = m0; a1 = m1; a2 = m2;
+          m0 = h0; m1 = h1; m2 = h2;
+        }
+      }
+    };
+    strip(r0, tx, nr);
+    if (t < RH) strip(t, RW - 1, 1);
+  }
+  __syncthreads();
+  // ---- full-weighting restriction (as k_resid_restrict), halo images on rim tiles
+  const bool rim = (cj0 < 2 * NH) || (ci0 < 2 * NH) || (cj0 + RTY > nyc - 2 * NH) || (ci0 + RTX > nxc - 2 * NH);
+#pragma unroll
+  for (int pidx = t; pidx < RTY * RTX; pidx += NT) {
+    const int r = pidx / RTX, q = pidx % RTX;
+    const int j = cj0 + r, i = ci0 + q;
+    const double *c = &S.bs[2 * r + 3][2 * q + 4];   // residual-tile (2r+1, 2q+1)
+    const double val = 0.25 * c[0] + 0.125 * (((c[-1] + c[1]) + c[-ZBP]) + c[ZBP]) +
+                       0.0625 * (((c[-ZBP - 1] + c[-ZBP + 1]) + c[ZBP - 1]) + c[ZBP + 1]);
+    bc[(size_t)j * nxc + i] = val;
+    if (rim)
+      f2d::for_each_halo_image(j, i, nyc, nxc, NH, [&](int jj, int ii) { bc[(size_t)jj * nxc + ii] = val; });
+  }
 }
 
 // ---------------------------------------------------------------------------

@@ -438,7 +438,7 @@ k_resid_sumsq(fused::LevelK L, const double *__restrict__ x, const double *__res
       if (!MASKED || L.msk[g] != 0) {
         fused::Coefs<MASKED, STORED> kk;
         if (MASKED || STORED) kk.load(L, g, MASKED ? L.msk + g : nullptr, nx); else kk = kc;
-        const double cdiag = STORED ? L.A[4 * (size_t)ny * nx + g] : L.c[4];
+        const double cdiag = STORED ? __ldg(L.A + 4 * (size_t)ny * nx + g) : L.c[4];
         val = fused::resid_val<MASKED, STORED>(L, kk, cdiag, a0, a1, a2, m0, m1, m2, h0, h1, h2, b[g]);
       }
       r[g] = val;
@@ -504,7 +504,7 @@ k_resid_sumsq_tma(fused::LevelK L, const double *__restrict__ b, double *__restr
         if (!MASKED || L.msk[g] != 0) {
           fused::Coefs<MASKED, STORED> kk;
           if (MASKED || STORED) kk.load(L, g, MASKED ? L.msk + g : nullptr, nx); else kk = kc;
-          const double cdiag = STORED ? L.A[4 * (size_t)ny * nx + g] : L.c[4];
+          const double cdiag = STORED ? __ldg(L.A + 4 * (size_t)ny * nx + g) : L.c[4];
           val = fused::resid_val<MASKED, STORED>(L, kk, cdiag, a0, a1, a2, m0, m1, m2, h0, h1, h2, bv[k]);
         }
         r[g] = val;
@@ -765,6 +765,31 @@ int op_resid_restrict_L(f2d_mg *mg, Level &l, Level &c, const double *x, const d
   F2D_LAUNCHED();
   return F2D_OK;
 }
+// A level's whole visit on the way down from a zero first guess in one kernel
+// (fused::k_zsmooth_resid_restrict): t = S2(0, b), bc = R(b - A t).  All-fluid doubly periodic
+// levels whose coarse grid tiles exactly; F2D_MG_NO_ZRR=1 keeps the two-kernel form.
+bool zrr_ok(f2d_mg *mg, const Level &l, const Level &c) {
+  static int off = -1;
+  if (off < 0) {
+    const char *e = getenv("F2D_MG_NO_ZRR");
+    off = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (off || !mg->tma || mg->relax != 0 || l.mode != 1 || !l.ywrap) return false;
+  if ((c.nx - 2 * NH) % fused::RTX || (c.ny - 2 * NH) % fused::RTY) return false;
+  return l.nx - 2 * NH == 2 * (c.nx - 2 * NH) && l.ny - 2 * NH == 2 * (c.ny - 2 * NH);
+}
+int op_zsmooth_rr_L(f2d_mg *mg, Level &l, Level &c, const double *b, double *t, double *bc, cudaStream_t s) {
+  fused::LevelK k = level_k(mg, l);
+  CUtensorMap tmb;
+  memset(&tmb, 0, sizeof tmb);
+  if (!get_tmap(mg, b, l.ny, l.nx, fused::ZBH, fused::ZBP, &tmb)) return fail(F2D_ERR_ARG, "zsmooth_rr: no tensor map");
+  dim3 grid((c.nx - 2 * NH) / fused::RTX, (c.ny - 2 * NH) / fused::RTY);
+  prof_tag("k_zsmooth_rr<mode1> %dx%d", l.nx - 2 * NH, l.ny - 2 * NH);
+  F2D_CUDA(f2d::launch_pdl(fused::k_zsmooth_resid_restrict, grid, dim3(fused::NT), sizeof(fused::ZrrSmem), s, k, t, bc,
+                           c.ny, c.nx, tmb));
+  F2D_LAUNCHED();
+  return F2D_OK;
+}
 int op_interpolate(f2d_mg *mg, int lev, const double *xc, double *xf, int add, cudaStream_t s) {
   Level &f = mg->L[lev];
   dim3 blk(32, 8);
@@ -962,6 +987,10 @@ int vcycle_enqueue(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s,
   for (int lev = lev1; lev < bottom; lev++) {
     Level &l = mg->L[lev];
     int input = lev > lev1 ? 1 : first_input;
+    if (input == 1 && zrr_ok(mg, l, mg->L[lev + 1])) {
+      TRY(op_zsmooth_rr_L(mg, l, mg->L[lev + 1], B(lev), l.t, B(lev + 1), s));
+      continue;
+    }
     TRY(smooth2(mg, lev, input, X(lev), B(lev), l.t, input == 2 ? X(lev + 1) : nullptr, s));
     TRY(op_resid_restrict(mg, lev, l.t, B(lev), B(lev + 1), s));
   }
@@ -1857,7 +1886,11 @@ extern "C" int f2d_mg_bench_op(f2d_mg_t *mg, int kind, int lev, int reps, f2d_st
         if (lev != mg->tail0) return fail(F2D_ERR_ARG, "mg_bench_op: not the first level of the tail");
         TRY(tail_launch(mg, 2, l.b, nullptr, l.x, s));
         break;
-      default: return fail(F2D_ERR_ARG, "mg_bench_op: kind 0..8");
+      case 9:
+        if (!has_coarse || !zrr_ok(mg, l, mg->L[lev + 1])) return fail(F2D_ERR_ARG, "mg_bench_op: no fused descent on this level");
+        TRY(op_zsmooth_rr_L(mg, l, mg->L[lev + 1], l.b, l.t, mg->L[lev + 1].b, s));
+        break;
+      default: return fail(F2D_ERR_ARG, "mg_bench_op: kind 0..9");
     }
   }
   return F2D_OK;

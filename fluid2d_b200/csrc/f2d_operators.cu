@@ -16,7 +16,7 @@ int g_pdl = -1;
 bool pdl_enabled() {
   if (g_pdl < 0) {
     const char *e = getenv("F2D_PDL");
-    g_pdl = (e && e[0] == '0') ? 0 : 1;
+    g_pdl = (e && e[0] == '1') ? 1 : 0;   // off by default: measured neutral inside the graphs
   }
   // per-kernel accounting puts an event behind every launch: keep the kernels apart there
   return g_pdl == 1 && !g_prof;

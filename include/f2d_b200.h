@@ -57,7 +57,8 @@ int f2d_mg_bench_op(f2d_mg_t *mg, int kind, int level, int reps, f2d_stream_t st
 /* ^ measurement aid (bench.py): `reps` back-to-back launches of ONE operator of the cycles on the
  * level's own arrays.  kind: 0 Grid.smooth, 1 Grid.smooth from x = 0, 2 x = I(xc) + smooth,
  * 3 x += I(xc) + smooth, 4 residual + restriction, 5 restriction, 6 residual + norm (level 0),
- * 7 / 8 the coarse-tail kernel's V-cycle / F-cycle (first tail level, f2d_mg_tail_level). */
+ * 7 / 8 the coarse-tail kernel's V-cycle / F-cycle (first tail level, f2d_mg_tail_level),
+ * 9 the fused descent of a level (smooth from x = 0 + residual + restriction in one kernel). */
 int f2d_mg_tail_level(const f2d_mg_t *mg);
 int f2d_prof_begin(f2d_stream_t stream);
 int f2d_prof_report(char *buf, size_t cap);

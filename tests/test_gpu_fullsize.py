@@ -207,8 +207,13 @@ def test_two_vcycle_shift_equivariance(L, ny, nx):
         moved = torch.roll(outs[0], (sh, 2*sh % nx), (0, 1))
         if strict:
             assert torch.equal(moved, outs[1])
-        else:   # rim and inner tiles are different instantiations: FMA contraction may differ
-            assert float(torch.linalg.norm(moved-outs[1])/torch.linalg.norm(outs[1])) <= 1e-13
+        else:
+            # rim and inner tiles are different instantiations: FMA contraction may differ; what it
+            # leaves in the constant (the null space of the periodic operator, which no sweep damps
+            # and the model removes, reference core/operators.py:474-478) is not compared
+            a, b = moved-moved.mean(), outs[1]-outs[1].mean()
+            assert float(torch.linalg.norm(a-b)/torch.linalg.norm(b)) <= 1e-13, \
+                (float(torch.linalg.norm(moved-outs[1])/torch.linalg.norm(outs[1])), float(moved.mean()-outs[1].mean()))
         # full solve: iteration count within the reference's bound, residual recomputed independently
         r = with_halo(rhs)
         psi = torch.zeros_like(r)

@@ -52,10 +52,14 @@ def tag_of(name, grid):
         masked, stored = int(v[0]), int(v[1])
         mode = 1 if not masked else (0 if stored else 2)
         return "k_resid_restrict<mode%d> %dx%d" % (mode, g[0]*64, g[1]*32)
+    if "k_zsmooth_resid_restrict" in name:   # grid = coarse tiles of 32 x 16
+        return "k_zsmooth_rr<mode1> %dx%d" % (g[0]*64, g[1]*32)
+    if "k_resid_sumsq_tma" in name:          # tiles of 64 x 32
+        return "k_resid_sumsq<mode1> %dx%d" % (g[0]*64, g[1]*32)
     if "k_resid_sumsq" in name:
         return "k_resid_sumsq<mode1> 4096x4096"
     if "k_adv<" in name:
-        return "k_adv<upw1,order5,masked0> %dx%d" % (g[0]*64, g[1]*32)
+        return "k_adv<upw1,order5,masked0> %dx%d x1" % (g[0]*64, g[1]*32)
     return None
 
 

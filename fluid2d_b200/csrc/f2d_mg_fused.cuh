@@ -26,7 +26,8 @@ namespace fused {
 
 constexpr int NH = 3;
 constexpr int TX = 64;   // outputs per tile in x
-constexpr int TY = 32;   // outputs per tile in y
+constexpr int TY = 32;   // outputs per tile in y (levels with fewer tiles than the device has SMs: TYS)
+constexpr int TYS = 8;   // small-level tile height: four times as many CTAs, a quarter of the rows per thread
 constexpr int NT = 256;  // threads per CTA
 
 struct LevelK {
@@ -135,7 +136,9 @@ constexpr int XP = XW + 2, CP = CW + 2;
 // goes from global memory straight into the registers of the column strip (one coalesced load
 // per strip row, shared by both sweeps) instead of through a shared-memory tile -- 18 KB less
 // shared memory per CTA and two shared loads less per point.
-struct Smooth2Smem {
+template <int TYP>
+struct Smooth2SmemT {
+  static constexpr int XH = TYP + 4, YH = TYP + 2, CH = XH / 2 + 2;
   alignas(128) double xs[XH][XP];   // TMA destinations: 128-byte aligned, dense boxes
   // the coarse tile is dead once the interpolation pass has folded it into xs (a block
   // barrier later sweep 1 starts writing y1): the two share their storage
@@ -150,7 +153,14 @@ struct Smooth2Smem {
   int8_t cm[CH][CW];
 };
 static_assert(sizeof(double[CH][CP]) <= sizeof(double[YH][YW]), "coarse tile must fit in the y1 tile");
-constexpr size_t SMOOTH2_SMEM_NOMASK = offsetof(Smooth2Smem, ms);
+static_assert(sizeof(double[TYS / 2 + 4][CP]) <= sizeof(double[TYS + 2][YW]), "coarse tile must fit in the y1 tile");
+using Smooth2Smem = Smooth2SmemT<TY>;
+template <int TYP>
+constexpr size_t smooth2_smem_nomask() { return offsetof(Smooth2SmemT<TYP>, ms); }
+template <int TYP>
+constexpr int smooth2_xh() { return TYP + 4; }
+template <int TYP>
+constexpr int smooth2_ch() { return (TYP + 4) / 2 + 2; }
 static_assert(XP % 2 == 0 && YW % 2 == 0 && CP % 2 == 0, "TMA boxes need an even number of doubles per row");
 
 // ---- asynchronous tile loader -----------------------------------------------------
@@ -245,8 +255,11 @@ __device__ __forceinline__ void jacobi_strip(const LevelK &L, const Coefs<MASKED
   // stored coefficients: every row's loads are issued here, fluid cell or not (the row-by-row
   // form paid one L2 round trip per row: 13 us per kernel on a 256 x 64 level against 7 us for
   // the constant-stencil kernel)
-  Coefs<MASKED, STORED> kpre[STORED ? NR : 1];
-  if (STORED) {
+  // (short strips only -- the small-level tiles: nine rows of coefficients in registers leave
+  // one CTA per SM, which costs the large stored levels more than the round trips)
+  constexpr bool PRE = STORED && NR <= 4;
+  Coefs<MASKED, STORED> kpre[PRE ? NR : 1];
+  if (PRE) {
 #pragma unroll
     for (int k = 0; k < NR; k++) {
       const bool okk = k < nr && (!GUARD || (j + k >= lo && j + k <= ny - 1 - lo && i >= lo && i <= nx - 1 - lo));
@@ -266,7 +279,8 @@ __device__ __forceinline__ void jacobi_strip(const LevelK &L, const Coefs<MASKED
         // stored coefficients are fetched whether the cell is fluid or not: loads that do not hang
         // on the mask test can be issued ahead of the rows before them
         Coefs<MASKED, STORED> kk;
-        if (STORED) { kk = kpre[k]; kk.finish(L); }
+        if (PRE) { kk = kpre[k]; kk.finish(L); }
+        else if (STORED) kk.load(L, g + (size_t)k * nx, nullptr, MLD);
         if (!MASKED || (MWIN ? wm1 : (int)mp[k * MLD]) != 0) {
           if (MWIN) kk.from_window(L, wa0, wa1, wa2, wm0, wm2, wh0, wh1, wh2);
           else if (!STORED) kk = kc;
@@ -287,13 +301,17 @@ __device__ __forceinline__ void jacobi_strip(const LevelK &L, const Coefs<MASKED
 // neighbour's halo rows as well (peer stores), and the last of them publishes the epoch --
 // the halo exchange of the reference (halo.fill after every smooth) without a kernel of
 // its own, overlapped with the interior tiles.
-template <bool MASKED, bool STORED, int INPUT, bool PEER>
+template <bool MASKED, bool STORED, int INPUT, bool PEER, int TYP>
 __global__ void __launch_bounds__(NT)
 k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b, double *__restrict__ xout,
           const double *__restrict__ xc, const int8_t *__restrict__ mskc, int nxc, int nyc, double *acc,
           f2d::Peer P, int use_tma, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smooth2Smem &S = *reinterpret_cast<Smooth2Smem *>(smem_raw);
+  // tile height TYP (these shadow the namespace constants of the standard tile); a thread
+  // group owns RG rows of the tile
+  constexpr int TY = TYP, XH = TY + 4, YH = TY + 2, CH = XH / 2 + 2, RG = TY / 4;
+  static_assert(TY % 4 == 0 && TY >= 4 && 2 * YH <= NT, "tile height");
+  Smooth2SmemT<TYP> &S = *reinterpret_cast<Smooth2SmemT<TYP> *>(smem_raw);
   const int ny = L.ny, nx = L.nx;
   const int t = threadIdx.x;
   const int by = PEER ? f2d::peer_tile_row(blockIdx.y, gridDim.y) : blockIdx.y;
@@ -320,13 +338,13 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
   // among them -- so the b of its points is loaded once, into registers, for both sweeps.
   // The two ring columns i0-1 and i0+TX of sweep 1 are done point-wise by the first 68 threads.
   const int tx = t & (TX - 1), tg = t >> 6;  // TX == 64
-  const int r1 = tg * 8 + (tg > 0 ? 1 : 0);  // first sweep-1 row (y1 tile coordinates): 0, 9, 17, 25
-  const int n1 = (tg == 0 || tg == 3) ? 9 : 8;
-  double bv[9], bx = 0.;
+  const int r1 = tg * RG + (tg > 0 ? 1 : 0);  // first sweep-1 row (y1 tile coordinates): 0, 9, 17, 25 (RG = 8)
+  const int n1 = (tg == 0 || tg == 3) ? RG + 1 : RG;
+  double bv[RG + 1], bx = 0.;
   auto load_b = [&]() {
     const int i = i0 + tx;
 #pragma unroll
-    for (int k = 0; k < 9; k++) {
+    for (int k = 0; k < RG + 1; k++) {
       const int j = j0 - 1 + r1 + k;
       bv[k] = (k < n1 && (inner || (j < ny && i < nx))) ? b[(size_t)j * nx + i] : 0.;
     }
@@ -418,9 +436,9 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
     auto out = [&](int k, double val) { yp[k * YW] = val; };
     auto bget = [&](int k) { return bv[k]; };
     if (inner)
-      jacobi_strip<MASKED, STORED, ZERO, false, 9, XP, XW>(L, kc, sp, bget, mp, n1, j, i, 2, out);
+      jacobi_strip<MASKED, STORED, ZERO, false, RG + 1, XP, XW>(L, kc, sp, bget, mp, n1, j, i, 2, out);
     else
-      jacobi_strip<MASKED, STORED, ZERO, true, 9, XP, XW>(L, kc, sp, bget, mp, n1, j, i, 2, out);
+      jacobi_strip<MASKED, STORED, ZERO, true, RG + 1, XP, XW>(L, kc, sp, bget, mp, n1, j, i, 2, out);
     if (t < YH * 2) {   // ring columns 0 and YW-1 of the y1 tile
       const int r = t >> 1, q = (t & 1) ? YW - 1 : 0;
       double *y = &S.y1[r][q];
@@ -434,7 +452,7 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
   // ---- sweep 2 on the tile interior; tiles that touch the rim also store halo images
   {
     const bool rim = (j0 < 2 * NH) || (i0 < 2 * NH) || (j0 + TY > ny - 2 * NH) || (i0 + TX > nx - 2 * NH);
-    const int r0 = tg * 8;
+    const int r0 = tg * RG;
     const int j = j0 + r0, i = i0 + tx;
     double *base = acc ? acc : xout;
     double *dst = base + (size_t)j * nx + i;
@@ -473,9 +491,9 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
     // the ring), row k of the others'
     auto bget = [&](int k) { return tg == 0 ? bv[k + 1] : bv[k]; };
     if (inner)
-      jacobi_strip<MASKED, STORED, false, false, 8, YW, XW>(L, kc, sp, bget, mp, 8, j, i, NH, out);
+      jacobi_strip<MASKED, STORED, false, false, RG, YW, XW>(L, kc, sp, bget, mp, RG, j, i, NH, out);
     else
-      jacobi_strip<MASKED, STORED, false, true, 8, YW, XW>(L, kc, sp, bget, mp, 8, j, i, NH, out);
+      jacobi_strip<MASKED, STORED, false, true, RG, YW, XW>(L, kc, sp, bget, mp, RG, j, i, NH, out);
   }
   if (PEER && (bsouth || bnorth)) f2d::peer_done(P, gridDim.x * (gridDim.y == 1 ? 1u : 2u));
 }
@@ -484,6 +502,7 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
 // k_resid_restrict: coarse tile RTX x RTY, fine residual tile (2RTX+1) x (2RTY+1)
 // ---------------------------------------------------------------------------
 constexpr int RTX = 32, RTY = 16;
+constexpr int RTYS = TYS / 2;   // small-level tiles
 constexpr int RW = 2 * RTX + 1, RH = 2 * RTY + 1;  // residual tile
 constexpr int RXW = RW + 2, RXH = RH + 2;          // x tile
 
@@ -503,7 +522,9 @@ __device__ __noinline__ double resid_global(const LevelK &L, const double *__res
 }
 
 constexpr int RXP = RXW + 1, RBP = RW + 1;         // row pitches of the x / b tiles (even: TMA boxes)
-struct ResidSmem {
+template <int RTYP>
+struct ResidSmemT {
+  static constexpr int RH = 2 * RTYP + 1, RXH = RH + 2;
   alignas(128) double xs[RXH][RXP];
   // b tile, overwritten IN PLACE by the residual: the thread that computes r(j,i) is the only
   // reader of b(j,i), so r(r,q) takes the place of b at bs[r][q + 1] (row pitch RBP)
@@ -511,7 +532,9 @@ struct ResidSmem {
   alignas(8) uint64_t bar;
   int8_t ms[RXH][RXW];     // last: not allocated for the mask-free instantiations
 };
-constexpr size_t RESID_SMEM_NOMASK = offsetof(ResidSmem, ms);
+using ResidSmem = ResidSmemT<RTY>;
+template <int RTYP>
+constexpr size_t resid_smem_nomask() { return offsetof(ResidSmemT<RTYP>, ms); }
 
 // column strip of the residual tile (same register-window scheme as jacobi_strip)
 template <bool MASKED, bool STORED, bool GUARD, int NR>
@@ -530,8 +553,9 @@ __device__ __forceinline__ void resid_strip(const LevelK &L, const Coefs<MASKED,
   }
   // stored coefficients: all rows' loads first (see jacobi_strip); rows this strip evaluates in
   // place, i.e. inside [NH, n-NH) on GUARD tiles
-  Coefs<MASKED, STORED> kpre[STORED ? NR : 1];
-  if (STORED) {
+  constexpr bool PRE = STORED && NR <= 4;
+  Coefs<MASKED, STORED> kpre[PRE ? NR : 1];
+  if (PRE) {
 #pragma unroll
     for (int k = 0; k < NR; k++) {
       const bool okk = k < nr && (!GUARD || (j + k < ny - NH && i < nx - NH));
@@ -556,9 +580,10 @@ __device__ __forceinline__ void resid_strip(const LevelK &L, const Coefs<MASKED,
       } else if (!MASKED || (MWIN ? wm1 : (int)mp[k * RXW]) != 0) {
         Coefs<MASKED, STORED> kk;
         if (MWIN) kk.from_window(L, wa0, wa1, wa2, wm0, wm2, wh0, wh1, wh2);
-        else if (STORED) kk = kpre[k];
+        else if (PRE) kk = kpre[k];
+        else if (STORED) kk.load_raw(L, g + (size_t)k * nx);
         else kk = kc;
-        // (the residual uses the diagonal itself, not omega / |diagonal|: kpre holds it raw in c3)
+        // (the residual uses the diagonal itself, not omega / |diagonal|: load_raw leaves it in c3)
         double cdiag = STORED ? kk.c3 : L.c[4];
         val = resid_val<MASKED, STORED>(L, kk, cdiag, a0, a1, a2, m0, m1, m2, h0, h1, h2, bp[k * RBP]);
       }
@@ -570,13 +595,16 @@ __device__ __forceinline__ void resid_strip(const LevelK &L, const Coefs<MASKED,
   }
 }
 
-template <bool MASKED, bool STORED, bool PEER>
-__global__ void __launch_bounds__(NT, STORED ? 1 : (MASKED ? 4 : 5))   // stored: the strip's coefficients live in registers
+template <bool MASKED, bool STORED, bool PEER, int RTYP>
+__global__ void __launch_bounds__(NT, (STORED && RTYP <= 4) ? 2 : (MASKED ? 4 : 5))   // short stored strips: coefficients in registers
 k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ bc,
                  const int8_t *__restrict__ mskc, int nyc, int nxc, f2d::Peer P, int use_tma,
                  const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ResidSmem &S = *reinterpret_cast<ResidSmem *>(smem_raw);
+  // coarse tile height RTYP (shadowing the constants of the standard tile); RG rows per thread group
+  constexpr int RTY = RTYP, RH = 2 * RTY + 1, RXH = RH + 2, RG = RTY / 2;
+  static_assert(RTY % 2 == 0 && RH <= NT, "tile height");
+  ResidSmemT<RTYP> &S = *reinterpret_cast<ResidSmemT<RTYP> *>(smem_raw);
   const int ny = L.ny, nx = L.nx;
   const int t = threadIdx.x;
   const int by = PEER ? f2d::peer_tile_row(blockIdx.y, gridDim.y) : blockIdx.y;
@@ -625,13 +653,13 @@ k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restric
   if (!MASKED && !STORED) kc.load(L, 0, nullptr, 0);
   {
     const int tx = t & 63, tg = t >> 6;
-    const int r0 = tg * 8 + (tg < 1 ? 0 : 1), nr = tg < 1 ? 9 : 8;
+    const int r0 = tg * RG + (tg < 1 ? 0 : 1), nr = tg < 1 ? RG + 1 : RG;
     if (inner)
-      resid_strip<MASKED, STORED, false, 9>(L, kc, &S.xs[r0 + 1][tx + 1], &S.bs[r0][tx + 1], &S.ms[r0 + 1][tx + 1],
-                                            &S.bs[r0][tx + 1], nr, fj0 + r0, fi0 + tx, x, b);
+      resid_strip<MASKED, STORED, false, RG + 1>(L, kc, &S.xs[r0 + 1][tx + 1], &S.bs[r0][tx + 1], &S.ms[r0 + 1][tx + 1],
+                                                 &S.bs[r0][tx + 1], nr, fj0 + r0, fi0 + tx, x, b);
     else
-      resid_strip<MASKED, STORED, true, 9>(L, kc, &S.xs[r0 + 1][tx + 1], &S.bs[r0][tx + 1], &S.ms[r0 + 1][tx + 1],
-                                           &S.bs[r0][tx + 1], nr, fj0 + r0, fi0 + tx, x, b);
+      resid_strip<MASKED, STORED, true, RG + 1>(L, kc, &S.xs[r0 + 1][tx + 1], &S.bs[r0][tx + 1], &S.ms[r0 + 1][tx + 1],
+                                                &S.bs[r0][tx + 1], nr, fj0 + r0, fi0 + tx, x, b);
     if (t < RH) {
       const int r = t, q = RW - 1;
       resid_strip<MASKED, STORED, true, 1>(L, kc, &S.xs[r + 1][q + 1], &S.bs[r][q + 1], &S.ms[r + 1][q + 1], &S.bs[r][q + 1], 1,
@@ -690,29 +718,38 @@ k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restric
 // Coarse tile RTX x RTY at (cj0, ci0); fine residual tile RH x RW from (fj0, fi0) = 2*(cj0, ci0) - 3;
 // t tile = + 1 ring, b tile = + 2 rings.
 // ---------------------------------------------------------------------------
-constexpr int ZBH = RH + 4, ZBW = RW + 4, ZBP = ZBW + 1;   // b tile 37 x 69; the TMA box starts one column early (even)
-constexpr int ZTH = RH + 2, ZTW = RW + 2, ZTP = ZTW + 1;   // t tile 35 x 67
+constexpr int ZBW = RW + 4, ZBP = ZBW + 1;   // b tile 37 x 69 (standard tile); the TMA box starts one column early (even)
+constexpr int ZTW = RW + 2, ZTP = ZTW + 1;   // t tile 35 x 67
 static_assert(ZBP % 2 == 0, "TMA boxes need an even number of doubles per row");
-struct ZrrSmem {
+template <int RTYP>
+struct ZrrSmemT {
+  static constexpr int RH = 2 * RTYP + 1, ZBH = RH + 4, ZTH = RH + 2;
   alignas(128) double bs[ZBH][ZBP];   // b tile (ring 2): tile column c sits at bs[.][c + 1]; later the residual in place
   alignas(128) double ts[ZTH][ZTP];   // t tile (ring 1)
   alignas(8) uint64_t bar;
 };
+template <int RTYP>
+constexpr int zrr_bh() { return 2 * RTYP + 5; }
 // t at t-tile point (rho, c) from the b tile: window of y = -(c3*b) at b-tile rows rho..rho+2,
 // columns c..c+2, right-hand side b-tile (rho+1, c+1)
-__device__ __forceinline__ double zsmooth_point(const LevelK &L, const Coefs<false, false> &kc, const ZrrSmem &S,
+__device__ __forceinline__ double zsmooth_point(const LevelK &L, const Coefs<false, false> &kc, const double (*bs)[ZBP],
                                                 int rho, int c) {
   const double nc3 = -kc.c3;
-  const double *p = &S.bs[rho][c + 1];
+  const double *p = &bs[rho][c + 1];
   return jacobi_val<false, false>(L, kc, nc3 * p[0], nc3 * p[1], nc3 * p[2], nc3 * p[ZBP], nc3 * p[ZBP + 1],
                                   nc3 * p[ZBP + 2], nc3 * p[2 * ZBP], nc3 * p[2 * ZBP + 1], nc3 * p[2 * ZBP + 2],
                                   p[ZBP + 1]);
 }
+template <int RTYP>
 __global__ void __launch_bounds__(NT, 4)
 k_zsmooth_resid_restrict(LevelK L, double *__restrict__ tout, double *__restrict__ bc, int nyc, int nxc,
                          const __grid_constant__ CUtensorMap tmb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ZrrSmem &S = *reinterpret_cast<ZrrSmem *>(smem_raw);
+  constexpr int RTY = RTYP, RH = 2 * RTY + 1, ZBH = RH + 4, ZTH = RH + 2;
+  constexpr int TG = (ZTH + 3) / 4;    // t-tile rows per thread group (9, 9, 9, 8 of 35)
+  constexpr int RG = RTY / 2;          // residual rows per thread group (9, 8, 8, 8 of 33)
+  static_assert(3 * ZTH <= NT && RH <= NT, "tile height");
+  ZrrSmemT<RTYP> &S = *reinterpret_cast<ZrrSmemT<RTYP> *>(smem_raw);
   const int ny = L.ny, nx = L.nx;
   const int t = threadIdx.x;
   const int ci0 = NH + blockIdx.x * RTX, cj0 = NH + blockIdx.y * RTY;
@@ -747,13 +784,13 @@ k_zsmooth_resid_restrict(LevelK L, double *__restrict__ tout, double *__restrict
     }
   };
   {
-    const int r0 = tg * 9, nr = tg < 3 ? 9 : 8;
+    const int r0 = tg * TG, nr = (ZTH - r0 < TG) ? ZTH - r0 : TG;
     const double *p = &S.bs[r0][tx + 1];
     double a0 = nc3 * p[0], a1 = nc3 * p[1], a2 = nc3 * p[2];
     double m0 = nc3 * p[ZBP], m1 = nc3 * p[ZBP + 1], m2 = nc3 * p[ZBP + 2];
     double bm = p[ZBP + 1];   // b at the window centre
 #pragma unroll
-    for (int k = 0; k < 9; k++) {
+    for (int k = 0; k < TG; k++) {
       if (k < nr) {
         const double *q = p + (k + 2) * ZBP;
         const double bh = q[1];
@@ -766,14 +803,14 @@ k_zsmooth_resid_restrict(LevelK L, double *__restrict__ tout, double *__restrict
     }
     if (t < 3 * ZTH) {
       const int rho = t / 3, c = 64 + t % 3;
-      put_t(rho, c, zsmooth_point(L, kc, S, rho, c));
+      put_t(rho, c, zsmooth_point(L, kc, S.bs, rho, c));
     }
   }
   __syncthreads();
   // ---- residual on the 33 x 65 tile, in place over b: residual-tile (rho, c) = t-tile centre
   // (rho+1, c+1) = b-tile (rho+2, c+2)
   {
-    const int r0 = tg * 8 + (tg < 1 ? 0 : 1), nr = tg < 1 ? 9 : 8;
+    const int r0 = tg * RG + (tg < 1 ? 0 : 1), nr = tg < 1 ? RG + 1 : RG;
     const double cdiag = L.c[4];
     auto strip = [&](int rho0, int c, int n) {
       const double *p = &S.ts[rho0][c];
@@ -781,7 +818,7 @@ k_zsmooth_resid_restrict(LevelK L, double *__restrict__ tout, double *__restrict
       double a0 = p[0], a1 = p[1], a2 = p[2];
       double m0 = p[ZTP], m1 = p[ZTP + 1], m2 = p[ZTP + 2];
 #pragma unroll
-      for (int k = 0; k < 9; k++) {
+      for (int k = 0; k < RG + 1; k++) {
         if (k < n) {
           const double *q = p + (k + 2) * ZTP;
           const double h0 = q[0], h1 = q[1], h2 = q[2];

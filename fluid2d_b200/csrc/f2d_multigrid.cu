@@ -562,13 +562,31 @@ bool get_tmap(f2d_mg *mg, const double *base, int ny, int nx, int boxh, int boxw
   return true;
 }
 
+// Levels that give the standard 64 x 32 tiles fewer CTAs than the device has SMs run on 64 x 8
+// tiles: four times as many CTAs, a quarter of the rows per thread (the kernels of such levels
+// are bound by the instruction latency of one CTA, with most SMs idle).
+// F2D_SMALL_TILE_MAXCTAS: largest standard-tile CTA count that still switches (0: never).
+// Measured on a B200 (profiles/r02_vcycle_by_level_4096_v7.txt, r02_bench_*_v7): 256^2 (32 standard
+// CTAs) 12.3 -> 8.1 us per level visit, 512^2 (128 CTAs) 8.2 -> 9.0 us (slower: stays standard);
+// stored-coefficient levels gain up to 128 CTAs (256 x 64: 13 -> 7 us per kernel, 1024 x 256: 14.3 -> 13.2).
+bool small_tiles(const Level &l) {
+  static long long maxctas = -1;
+  if (maxctas < 0) {
+    maxctas = 96;
+    if (const char *e = getenv("F2D_SMALL_TILE_MAXCTAS")) maxctas = atoll(e);
+  }
+  const long long ctas = (long long)cdiv(l.nx - 2 * NH, fused::TX) * cdiv(l.ny - 2 * NH, fused::TY);
+  const long long lim = (l.mode == 0 && maxctas > 0) ? (maxctas * 3) / 2 : maxctas;   // stored: the short strips also prefetch their coefficients
+  return ctas <= lim && l.ny - 2 * NH >= fused::TYS;
+}
+
 // fused double sweep: xout = S2(input), input = xin | 0 | I(xc) | xin + I(xc)
-template <int INPUT>
+template <int INPUT, int TYP>
 int launch_smooth2(f2d_mg *mg, Level &l, Level *cl, const double *xin, const double *b, double *xout,
                    const double *xc, cudaStream_t s, double *acc) {
   fused::LevelK k = level_k(mg, l);
-  dim3 grid(cdiv(l.nx - 2 * NH, fused::TX), cdiv(l.ny - 2 * NH, fused::TY));
-  const size_t sm = l.mode == 1 ? fused::SMOOTH2_SMEM_NOMASK : sizeof(fused::Smooth2Smem);
+  dim3 grid(cdiv(l.nx - 2 * NH, fused::TX), cdiv(l.ny - 2 * NH, TYP));
+  const size_t sm = l.mode == 1 ? fused::smooth2_smem_nomask<TYP>() : sizeof(fused::Smooth2SmemT<TYP>);
   const int8_t *mskc = nullptr;
   int nxc = 0, nyc = 0;
   if (INPUT >= 2) {
@@ -583,13 +601,13 @@ int launch_smooth2(f2d_mg *mg, Level &l, Level *cl, const double *xin, const dou
   CUtensorMap tmx, tmc;
   memset(&tmx, 0, sizeof tmx); memset(&tmc, 0, sizeof tmc);
   int use_tma = mg->tma ? 1 : 0;   // (INPUT == 1 stages nothing but the masks: either path does)
-  if (use_tma && (INPUT == 0 || INPUT == 3)) use_tma = get_tmap(mg, xin, l.ny, l.nx, fused::XH, fused::XP, &tmx);
-  if (use_tma && INPUT >= 2) use_tma = get_tmap(mg, xc, nyc, nxc, fused::CH, fused::CP, &tmc);
+  if (use_tma && (INPUT == 0 || INPUT == 3)) use_tma = get_tmap(mg, xin, l.ny, l.nx, fused::smooth2_xh<TYP>(), fused::XP, &tmx);
+  if (use_tma && INPUT >= 2) use_tma = get_tmap(mg, xc, nyc, nxc, fused::smooth2_ch<TYP>(), fused::CP, &tmc);
   prof_tag("k_smooth2<mode%d,input%d%s> %dx%d", l.mode, INPUT, peer ? ",peer" : "", l.nx - 2 * NH, l.ny - 2 * NH);
 #define F2D_SM2(M, St)                                                                                              \
   do {                                                                                                              \
-    if (peer) F2D_CUDA(f2d::launch_pdl(fused::k_smooth2<M, St, INPUT, true>, grid, dim3(fused::NT), sm, s, k, xin, b, xout, xc, mskc, nxc, nyc, acc, P, use_tma, tmx, tmc)); \
-    else F2D_CUDA(f2d::launch_pdl(fused::k_smooth2<M, St, INPUT, false>, grid, dim3(fused::NT), sm, s, k, xin, b, xout, xc, mskc, nxc, nyc, acc, P, use_tma, tmx, tmc));     \
+    if (peer) F2D_CUDA(f2d::launch_pdl(fused::k_smooth2<M, St, INPUT, true, TYP>, grid, dim3(fused::NT), sm, s, k, xin, b, xout, xc, mskc, nxc, nyc, acc, P, use_tma, tmx, tmc)); \
+    else F2D_CUDA(f2d::launch_pdl(fused::k_smooth2<M, St, INPUT, false, TYP>, grid, dim3(fused::NT), sm, s, k, xin, b, xout, xc, mskc, nxc, nyc, acc, P, use_tma, tmx, tmc));     \
   } while (0)
   switch (l.mode) {
     case 1: F2D_SM2(false, false); break;
@@ -602,11 +620,19 @@ int launch_smooth2(f2d_mg *mg, Level &l, Level *cl, const double *xin, const dou
 }
 int smooth2_L(f2d_mg *mg, Level &l, Level *cl, int input, const double *xin, const double *b, double *xout,
               const double *xc, cudaStream_t s, double *acc = nullptr) {
+  if (small_tiles(l)) {
+    switch (input) {
+      case 0: return launch_smooth2<0, fused::TYS>(mg, l, cl, xin, b, xout, xc, s, acc);
+      case 1: return launch_smooth2<1, fused::TYS>(mg, l, cl, xin, b, xout, xc, s, acc);
+      case 2: return launch_smooth2<2, fused::TYS>(mg, l, cl, xin, b, xout, xc, s, acc);
+      default: return launch_smooth2<3, fused::TYS>(mg, l, cl, xin, b, xout, xc, s, acc);
+    }
+  }
   switch (input) {
-    case 0: return launch_smooth2<0>(mg, l, cl, xin, b, xout, xc, s, acc);
-    case 1: return launch_smooth2<1>(mg, l, cl, xin, b, xout, xc, s, acc);
-    case 2: return launch_smooth2<2>(mg, l, cl, xin, b, xout, xc, s, acc);
-    default: return launch_smooth2<3>(mg, l, cl, xin, b, xout, xc, s, acc);
+    case 0: return launch_smooth2<0, fused::TY>(mg, l, cl, xin, b, xout, xc, s, acc);
+    case 1: return launch_smooth2<1, fused::TY>(mg, l, cl, xin, b, xout, xc, s, acc);
+    case 2: return launch_smooth2<2, fused::TY>(mg, l, cl, xin, b, xout, xc, s, acc);
+    default: return launch_smooth2<3, fused::TY>(mg, l, cl, xin, b, xout, xc, s, acc);
   }
 }
 int smooth2(f2d_mg *mg, int lev, int input, const double *xin, const double *b, double *xout, const double *xc,
@@ -616,12 +642,15 @@ int smooth2(f2d_mg *mg, int lev, int input, const double *xin, const double *b, 
 }
 template <bool M, bool St, int I>
 cudaError_t set_smem_one() {
-  cudaError_t e = cudaFuncSetAttribute(fused::k_smooth2<M, St, I, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(fused::k_smooth2<M, St, I, false, fused::TY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(fused::Smooth2Smem));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(fused::k_smooth2<M, St, I, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  return cudaFuncSetAttribute(fused::k_smooth2<M, St, I, true, fused::TY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)sizeof(fused::Smooth2Smem));
+  // (the small-tile instantiations stay under the 48 KB that need no opt-in)
 }
+static_assert(sizeof(fused::Smooth2SmemT<fused::TYS>) <= 48 * 1024 && sizeof(fused::ResidSmemT<fused::RTYS>) <= 48 * 1024,
+              "small tiles: dynamic shared memory without opt-in");
 template <int I>
 cudaError_t set_smem_input() {
   cudaError_t e = set_smem_one<false, false, I>();
@@ -631,10 +660,10 @@ cudaError_t set_smem_input() {
 }
 template <bool M, bool St>
 cudaError_t set_smem_resid() {
-  cudaError_t e = cudaFuncSetAttribute(fused::k_resid_restrict<M, St, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(fused::k_resid_restrict<M, St, false, fused::RTY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(fused::ResidSmem));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(fused::k_resid_restrict<M, St, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  return cudaFuncSetAttribute(fused::k_resid_restrict<M, St, true, fused::RTY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)sizeof(fused::ResidSmem));
 }
 cudaError_t set_smem_all() {
@@ -737,24 +766,31 @@ int op_resid_restrict_L(f2d_mg *mg, Level &l, Level &c, const double *x, const d
 int op_resid_restrict(f2d_mg *mg, int lev, const double *x, const double *b, double *bc, cudaStream_t s) {
   return op_resid_restrict_L(mg, mg->L[lev], mg->L[lev + 1], x, b, bc, s);
 }
+template <int RTYP>
+int launch_resid_restrict(f2d_mg *mg, Level &l, Level &c, const double *x, const double *b, double *bc, cudaStream_t s);
 int op_resid_restrict_L(f2d_mg *mg, Level &l, Level &c, const double *x, const double *b, double *bc,
                         cudaStream_t s) {
+  if (small_tiles(l)) return launch_resid_restrict<fused::RTYS>(mg, l, c, x, b, bc, s);
+  return launch_resid_restrict<fused::RTY>(mg, l, c, x, b, bc, s);
+}
+template <int RTYP>
+int launch_resid_restrict(f2d_mg *mg, Level &l, Level &c, const double *x, const double *b, double *bc, cudaStream_t s) {
   fused::LevelK k = level_k(mg, l);
-  dim3 grid(cdiv(c.nx - 2 * NH, fused::RTX), cdiv(c.ny - 2 * NH, fused::RTY));
-  const size_t sm = l.mode == 1 ? fused::RESID_SMEM_NOMASK : sizeof(fused::ResidSmem);
+  dim3 grid(cdiv(c.nx - 2 * NH, fused::RTX), cdiv(c.ny - 2 * NH, RTYP));
+  const size_t sm = l.mode == 1 ? fused::resid_smem_nomask<RTYP>() : sizeof(fused::ResidSmemT<RTYP>);
   const bool peer = mg->comm != nullptr && l.ywrap == 0;
   f2d::Peer P = comm_peer(peer ? mg->comm : nullptr);
   if (peer && !comm_owns(mg->comm, bc))
     return fail(F2D_ERR_ARG, "restrict: the output of a slab level must live in the symmetric heap");
   CUtensorMap tmx, tmb;
   memset(&tmx, 0, sizeof tmx); memset(&tmb, 0, sizeof tmb);
-  int use_tma = get_tmap(mg, x, l.ny, l.nx, fused::RXH, fused::RXP, &tmx);
-  if (use_tma) use_tma = get_tmap(mg, b, l.ny, l.nx, fused::RH, fused::RBP, &tmb);
+  int use_tma = get_tmap(mg, x, l.ny, l.nx, 2 * RTYP + 3, fused::RXP, &tmx);
+  if (use_tma) use_tma = get_tmap(mg, b, l.ny, l.nx, 2 * RTYP + 1, fused::RBP, &tmb);
   prof_tag("k_resid_restrict<mode%d%s> %dx%d", l.mode, peer ? ",peer" : "", l.nx - 2 * NH, l.ny - 2 * NH);
 #define F2D_RR(M, St)                                                                                         \
   do {                                                                                                        \
-    if (peer) F2D_CUDA(f2d::launch_pdl(fused::k_resid_restrict<M, St, true>, grid, dim3(fused::NT), sm, s, k, x, b, bc, c.msk, c.ny, c.nx, P, use_tma, tmx, tmb)); \
-    else F2D_CUDA(f2d::launch_pdl(fused::k_resid_restrict<M, St, false>, grid, dim3(fused::NT), sm, s, k, x, b, bc, c.msk, c.ny, c.nx, P, use_tma, tmx, tmb));     \
+    if (peer) F2D_CUDA(f2d::launch_pdl(fused::k_resid_restrict<M, St, true, RTYP>, grid, dim3(fused::NT), sm, s, k, x, b, bc, c.msk, c.ny, c.nx, P, use_tma, tmx, tmb)); \
+    else F2D_CUDA(f2d::launch_pdl(fused::k_resid_restrict<M, St, false, RTYP>, grid, dim3(fused::NT), sm, s, k, x, b, bc, c.msk, c.ny, c.nx, P, use_tma, tmx, tmb));     \
   } while (0)
   switch (l.mode) {
     case 1: F2D_RR(false, false); break;
@@ -775,20 +811,26 @@ bool zrr_ok(f2d_mg *mg, const Level &l, const Level &c) {
     off = (e && e[0] == '1') ? 1 : 0;
   }
   if (off || !mg->tma || mg->relax != 0 || l.mode != 1 || !l.ywrap) return false;
-  if ((c.nx - 2 * NH) % fused::RTX || (c.ny - 2 * NH) % fused::RTY) return false;
+  const int rty = small_tiles(l) ? fused::RTYS : fused::RTY;
+  if ((c.nx - 2 * NH) % fused::RTX || (c.ny - 2 * NH) % rty) return false;
   return l.nx - 2 * NH == 2 * (c.nx - 2 * NH) && l.ny - 2 * NH == 2 * (c.ny - 2 * NH);
 }
-int op_zsmooth_rr_L(f2d_mg *mg, Level &l, Level &c, const double *b, double *t, double *bc, cudaStream_t s) {
+template <int RTYP>
+int launch_zsmooth_rr(f2d_mg *mg, Level &l, Level &c, const double *b, double *t, double *bc, cudaStream_t s) {
   fused::LevelK k = level_k(mg, l);
   CUtensorMap tmb;
   memset(&tmb, 0, sizeof tmb);
-  if (!get_tmap(mg, b, l.ny, l.nx, fused::ZBH, fused::ZBP, &tmb)) return fail(F2D_ERR_ARG, "zsmooth_rr: no tensor map");
-  dim3 grid((c.nx - 2 * NH) / fused::RTX, (c.ny - 2 * NH) / fused::RTY);
+  if (!get_tmap(mg, b, l.ny, l.nx, fused::zrr_bh<RTYP>(), fused::ZBP, &tmb)) return fail(F2D_ERR_ARG, "zsmooth_rr: no tensor map");
+  dim3 grid((c.nx - 2 * NH) / fused::RTX, (c.ny - 2 * NH) / RTYP);
   prof_tag("k_zsmooth_rr<mode1> %dx%d", l.nx - 2 * NH, l.ny - 2 * NH);
-  F2D_CUDA(f2d::launch_pdl(fused::k_zsmooth_resid_restrict, grid, dim3(fused::NT), sizeof(fused::ZrrSmem), s, k, t, bc,
-                           c.ny, c.nx, tmb));
+  F2D_CUDA(f2d::launch_pdl(fused::k_zsmooth_resid_restrict<RTYP>, grid, dim3(fused::NT), sizeof(fused::ZrrSmemT<RTYP>), s,
+                           k, t, bc, c.ny, c.nx, tmb));
   F2D_LAUNCHED();
   return F2D_OK;
+}
+int op_zsmooth_rr_L(f2d_mg *mg, Level &l, Level &c, const double *b, double *t, double *bc, cudaStream_t s) {
+  if (small_tiles(l)) return launch_zsmooth_rr<fused::RTYS>(mg, l, c, b, t, bc, s);
+  return launch_zsmooth_rr<fused::RTY>(mg, l, c, b, t, bc, s);
 }
 int op_interpolate(f2d_mg *mg, int lev, const double *xc, double *xf, int add, cudaStream_t s) {
   Level &f = mg->L[lev];

@@ -740,10 +740,15 @@ __device__ __forceinline__ double zsmooth_point(const LevelK &L, const Coefs<fal
                                   nc3 * p[ZBP + 2], nc3 * p[2 * ZBP], nc3 * p[2 * ZBP + 1], nc3 * p[2 * ZBP + 2],
                                   p[ZBP + 1]);
 }
-template <int RTYP>
+// PEER (y-slab levels): the y halo rows of b hold the neighbouring ranks' rows (pushed by the
+// kernel that produced b), so the halo cells the tile evaluates in place are the neighbour's
+// values bit for bit; the tiles of the first / last tile row wait for the neighbours' epoch
+// first, push the 3 outermost rows of t and of bc into the neighbours' halo rows and publish
+// the epoch -- ONE synchronisation point where the two-kernel form has two.
+template <int RTYP, bool PEER>
 __global__ void __launch_bounds__(NT, 4)
 k_zsmooth_resid_restrict(LevelK L, double *__restrict__ tout, double *__restrict__ bc, int nyc, int nxc,
-                         const __grid_constant__ CUtensorMap tmb) {
+                         f2d::Peer P, const __grid_constant__ CUtensorMap tmb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int RTY = RTYP, RH = 2 * RTY + 1, ZBH = RH + 4, ZTH = RH + 2;
   constexpr int TG = (ZTH + 3) / 4;    // t-tile rows per thread group (9, 9, 9, 8 of 35)
@@ -752,7 +757,9 @@ k_zsmooth_resid_restrict(LevelK L, double *__restrict__ tout, double *__restrict
   ZrrSmemT<RTYP> &S = *reinterpret_cast<ZrrSmemT<RTYP> *>(smem_raw);
   const int ny = L.ny, nx = L.nx;
   const int t = threadIdx.x;
-  const int ci0 = NH + blockIdx.x * RTX, cj0 = NH + blockIdx.y * RTY;
+  const int by = PEER ? f2d::peer_tile_row(blockIdx.y, gridDim.y) : blockIdx.y;
+  const bool bsouth = PEER && by == 0, bnorth = PEER && by == (int)gridDim.y - 1;
+  const int ci0 = NH + blockIdx.x * RTX, cj0 = NH + by * RTY;
   const int fi0 = 2 * ci0 - 3, fj0 = 2 * cj0 - 3;
   f2d::pdl_trigger();
   if (t == 0) {
@@ -760,8 +767,10 @@ k_zsmooth_resid_restrict(LevelK L, double *__restrict__ tout, double *__restrict
     f2d::tma_prefetch_desc(&tmb);
   }
   f2d::pdl_wait();
+  if (PEER && (bsouth || bnorth)) f2d::peer_wait(P, bsouth, bnorth);
   __syncthreads();
   if (t == 0) {
+    if (PEER) asm volatile("fence.proxy.async;" ::: "memory");   // the neighbours' rows were observed through the generic proxy
     f2d::mbar_expect_tx(&S.bar, ZBH * ZBP * 8);
     f2d::tma_load_2d(&S.bs[0][0], &tmb, &S.bar, fi0 - 3, fj0 - 2);
   }
@@ -774,13 +783,26 @@ k_zsmooth_resid_restrict(LevelK L, double *__restrict__ tout, double *__restrict
   // window of y in registers; columns 64..66 point-wise.  The tile's own 32 x 64 points
   // (t-tile rows 1..32, columns 1..64) also go to global memory, with their halo images.
   const bool rimf = (fj0 < 2 * NH) || (fi0 < 2 * NH) || (fj0 + 2 * RTY > ny - 2 * NH) || (fi0 + 2 * RTX > nx - 2 * NH);
+  double *tsouth = PEER ? f2d::peer_addr(tout, P.south_off) : nullptr;
+  double *tnorth = PEER ? f2d::peer_addr(tout, P.north_off) : nullptr;
+  const int mrows = ny - 2 * NH;   // interior rows of the slab
   auto put_t = [&](int rho, int c, double val) {
     S.ts[rho][c] = val;
     if (rho >= 1 && rho <= 2 * RTY && c >= 1 && c <= 2 * RTX) {
       const int j = fj0 - 1 + rho, i = fi0 - 1 + c;
       tout[(size_t)j * nx + i] = val;
       if (rimf)
-        f2d::for_each_halo_image(j, i, ny, nx, NH, [&](int j2, int i2) { tout[(size_t)j2 * nx + i2] = val; });
+        f2d::for_each_halo_image(j, i, ny, nx, NH, [&](int j2, int i2) { tout[(size_t)j2 * nx + i2] = val; }, L.ywrap != 0);
+      if (PEER) {
+        if (bsouth && j < 2 * NH) {
+          tsouth[(size_t)(j + mrows) * nx + i] = val;
+          f2d::for_each_halo_image(j + mrows, i, ny, nx, NH, [&](int j2, int i2) { tsouth[(size_t)j2 * nx + i2] = val; }, false);
+        }
+        if (bnorth && j >= mrows) {
+          tnorth[(size_t)(j - mrows) * nx + i] = val;
+          f2d::for_each_halo_image(j - mrows, i, ny, nx, NH, [&](int j2, int i2) { tnorth[(size_t)j2 * nx + i2] = val; }, false);
+        }
+      }
     }
   };
   {
@@ -843,10 +865,24 @@ k_zsmooth_resid_restrict(LevelK L, double *__restrict__ tout, double *__restrict
                        0.0625 * (((c[-ZBP - 1] + c[-ZBP + 1]) + c[ZBP - 1]) + c[ZBP + 1]);
     bc[(size_t)j * nxc + i] = val;
     if (rim)
-      f2d::for_each_halo_image(j, i, nyc, nxc, NH, [&](int jj, int ii) { bc[(size_t)jj * nxc + ii] = val; });
+      f2d::for_each_halo_image(j, i, nyc, nxc, NH, [&](int jj, int ii) { bc[(size_t)jj * nxc + ii] = val; },
+                               L.ywrap != 0);
+    if (PEER) {
+      const int m2c = nyc - 2 * NH;
+      if (bsouth && j < 2 * NH) {
+        double *q2 = f2d::peer_addr(bc, P.south_off);
+        q2[(size_t)(j + m2c) * nxc + i] = val;
+        f2d::for_each_halo_image(j + m2c, i, nyc, nxc, NH, [&](int jj, int ii) { q2[(size_t)jj * nxc + ii] = val; }, false);
+      }
+      if (bnorth && j >= m2c) {
+        double *q2 = f2d::peer_addr(bc, P.north_off);
+        q2[(size_t)(j - m2c) * nxc + i] = val;
+        f2d::for_each_halo_image(j - m2c, i, nyc, nxc, NH, [&](int jj, int ii) { q2[(size_t)jj * nxc + ii] = val; }, false);
+      }
+    }
   }
+  if (PEER && (bsouth || bnorth)) f2d::peer_done(P, gridDim.x * (gridDim.y == 1 ? 1u : 2u));
 }
-
 // ---------------------------------------------------------------------------
 // k_check_const: does "constant stencil x mask products" reproduce the stored matrix
 // on every entry the kernels read (cells [2, n-3] compute; they read coefficients and

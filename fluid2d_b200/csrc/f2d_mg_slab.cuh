@@ -33,6 +33,14 @@ int gather_to_full(f2d_mg *mg, const double *slab, double *full, cudaStream_t s)
   TRY(comm_gather(mg->comm, slab, full, v.ny, v.nx, NH, s, mg->lg == 0));
   return f2d_fill_halo(full, NH, f.ny, f.nx, (f2d_stream_t)s);
 }
+// this rank's rows of the replicated level-lg array, halo rows included, as a slab array: the
+// full array is halo filled, so rows [row0, row0 + ny_loc) ARE the slab with its y halo -- the
+// consumers of x at level lg (interpolation fused into the smoother above it) read it in place
+// instead of through a copy (Subdomains.split, subdomains.py:118-124)
+double *full_as_slab(f2d_mg *mg, double *full) {
+  Level &v = mg->S[mg->lg];
+  return full + (size_t)comm_rank(mg->comm) * (v.ny - 2 * NH) * v.nx;
+}
 int scatter_from_full(f2d_mg *mg, const double *full, double *slab, cudaStream_t s) {
   Level &v = mg->S[mg->lg];
   int row0 = comm_rank(mg->comm) * (v.ny - 2 * NH);
@@ -46,13 +54,17 @@ int scatter_from_full(f2d_mg *mg, const double *full, double *slab, cudaStream_t
 int slab_vcycle(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s, int first_input = 0,
                 double *acc = nullptr) {
   const int lg = mg->lg;
-  auto X = [&](int g) { return g == lev1 ? x0 : mg->S[g].x; };
+  auto X = [&](int g) { return g == lev1 ? x0 : (g == lg ? full_as_slab(mg, mg->L[0].x) : mg->S[g].x); };
   auto B = [&](int g) { return g == lev1 ? b0 : mg->S[g].b; };
   for (int g = lev1; g < lg; g++) {
     Level &l = mg->S[g], &c = mg->S[g + 1];
     int input = g > lev1 ? 1 : first_input;
     // the smoother and the residual/restriction kernels fill the neighbours' halo rows of
     // their outputs themselves (fused::k_smooth2<..., PEER>): no exchange kernels here
+    if (input == 1 && zrr_ok(mg, l, c)) {   // smooth from zero + residual + restriction: one kernel, one epoch
+      TRY(op_zsmooth_rr_L(mg, l, c, B(g), l.t, B(g + 1), s));
+      continue;
+    }
     TRY(smooth2_L(mg, l, &c, input, X(g), B(g), l.t, input == 2 ? X(g + 1) : nullptr, s));
     TRY(op_resid_restrict_L(mg, l, c, l.t, B(g), B(g + 1), s));
   }
@@ -67,7 +79,7 @@ int slab_vcycle(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s, in
   } else {
     TRY(vcycle_enqueue(mg, 0, f.x, f.b, s, 1));
   }
-  TRY(scatter_from_full(mg, f.x, X(lg), s));
+  if (lev1 == lg) TRY(scatter_from_full(mg, f.x, X(lg), s));   // (levels above read f.x in place)
   for (int g = lg - 1; g >= lev1; g--) {
     Level &l = mg->S[g], &c = mg->S[g + 1];
     TRY(smooth2_L(mg, l, &c, 3, l.t, B(g), X(g), X(g + 1), s, g == lev1 ? acc : nullptr));
@@ -78,7 +90,7 @@ int slab_vcycle(f2d_mg *mg, int lev1, double *x0, double *b0, cudaStream_t s, in
 // F-cycle from slab level 0 (hierarchy.py:131-151)
 int slab_fcycle(f2d_mg *mg, double *x0, double *b0, cudaStream_t s, double *acc = nullptr) {
   const int lg = mg->lg;
-  auto X = [&](int g) { return g == 0 ? x0 : mg->S[g].x; };
+  auto X = [&](int g) { return g == 0 ? x0 : (g == lg ? full_as_slab(mg, mg->L[0].x) : mg->S[g].x); };
   auto B = [&](int g) { return g == 0 ? b0 : mg->S[g].b; };
   for (int g = 0; g < lg; g++) {
     TRY(op_restrict_L(mg, mg->S[g], mg->S[g + 1], B(g), B(g + 1), s));   // fills the neighbours' halo rows itself
@@ -86,7 +98,7 @@ int slab_fcycle(f2d_mg *mg, double *x0, double *b0, cudaStream_t s, double *acc 
   Level &f = mg->L[0];
   TRY(gather_to_full(mg, B(lg), f.b, s));
   TRY(fcycle_enqueue(mg, 0, f.x, f.b, s));
-  TRY(scatter_from_full(mg, f.x, X(lg), s));
+  if (lg == 0) TRY(scatter_from_full(mg, f.x, X(lg), s));   // (levels above read f.x in place)
   for (int g = lg - 1; g >= 0; g--)
     for (int k = 0; k < mg->nvcyc; k++)
       TRY(slab_vcycle(mg, g, X(g), B(g), s, k == 0 ? 2 : 0, (g == 0 && k == mg->nvcyc - 1) ? acc : nullptr));

@@ -810,7 +810,8 @@ bool zrr_ok(f2d_mg *mg, const Level &l, const Level &c) {
     const char *e = getenv("F2D_MG_NO_ZRR");
     off = (e && e[0] == '1') ? 1 : 0;
   }
-  if (off || !mg->tma || mg->relax != 0 || l.mode != 1 || !l.ywrap) return false;
+  // (y-slab levels: the halo cells evaluated in place hold the neighbouring rank's data)
+  if (off || !mg->tma || mg->relax != 0 || l.mode != 1 || (!l.ywrap && !mg->comm)) return false;
   const int rty = small_tiles(l) ? fused::RTYS : fused::RTY;
   if ((c.nx - 2 * NH) % fused::RTX || (c.ny - 2 * NH) % rty) return false;
   return l.nx - 2 * NH == 2 * (c.nx - 2 * NH) && l.ny - 2 * NH == 2 * (c.ny - 2 * NH);
@@ -822,9 +823,17 @@ int launch_zsmooth_rr(f2d_mg *mg, Level &l, Level &c, const double *b, double *t
   memset(&tmb, 0, sizeof tmb);
   if (!get_tmap(mg, b, l.ny, l.nx, fused::zrr_bh<RTYP>(), fused::ZBP, &tmb)) return fail(F2D_ERR_ARG, "zsmooth_rr: no tensor map");
   dim3 grid((c.nx - 2 * NH) / fused::RTX, (c.ny - 2 * NH) / RTYP);
-  prof_tag("k_zsmooth_rr<mode1> %dx%d", l.nx - 2 * NH, l.ny - 2 * NH);
-  F2D_CUDA(f2d::launch_pdl(fused::k_zsmooth_resid_restrict<RTYP>, grid, dim3(fused::NT), sizeof(fused::ZrrSmemT<RTYP>), s,
-                           k, t, bc, c.ny, c.nx, tmb));
+  const bool peer = mg->comm != nullptr && l.ywrap == 0;
+  f2d::Peer P = comm_peer(peer ? mg->comm : nullptr);
+  if (peer && (!comm_owns(mg->comm, t) || !comm_owns(mg->comm, bc)))
+    return fail(F2D_ERR_ARG, "zsmooth_rr: the outputs of a slab level must live in the symmetric heap");
+  prof_tag("k_zsmooth_rr<mode1%s> %dx%d", peer ? ",peer" : "", l.nx - 2 * NH, l.ny - 2 * NH);
+  if (peer)
+    F2D_CUDA(f2d::launch_pdl(fused::k_zsmooth_resid_restrict<RTYP, true>, grid, dim3(fused::NT),
+                             sizeof(fused::ZrrSmemT<RTYP>), s, k, t, bc, c.ny, c.nx, P, tmb));
+  else
+    F2D_CUDA(f2d::launch_pdl(fused::k_zsmooth_resid_restrict<RTYP, false>, grid, dim3(fused::NT),
+                             sizeof(fused::ZrrSmemT<RTYP>), s, k, t, bc, c.ny, c.nx, P, tmb));
   F2D_LAUNCHED();
   return F2D_OK;
 }

@@ -54,7 +54,10 @@ def ngpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("nx,ny,min_cells", [(64, 128, "1500"), (64, 128, "100000000"), (128, 256, "3000")])
+# the last case is large enough for the slab levels to run the standard 64 x 32 tiles AND the
+# small-level 64 x 8 tiles, each with the one-kernel level descent (k_zsmooth_resid_restrict<PEER>)
+@pytest.mark.parametrize("nx,ny,min_cells", [(64, 128, "1500"), (64, 128, "100000000"), (128, 256, "3000"),
+                                             (1024, 2048, "100000")])
 def test_two_slabs_match_single_gpu(nx, ny, min_cells):
     if ngpus() < 2:
         pytest.skip("needs 2 GPUs")

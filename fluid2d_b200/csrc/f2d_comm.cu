@@ -139,7 +139,7 @@ __global__ void k_allreduce(double *vals, int n, unsigned maxmask, Ctrl *me, Ctr
 // full-height array (rows offset by my slab position), then all-rank barrier
 __global__ void k_gather_push(const double *slab, int ny_loc, int nx, int nh, size_t full_off /*bytes from arena base*/,
                               int row0 /*first global interior row of my slab*/, char *const *arena, Ctrl *me,
-                              Ctrl *const *peers, int rank, int nranks) {
+                              Ctrl *const *peers, int rank, int nranks, int yimages) {
   // no rank may still be reading the previous contents of `full`: every rank must have
   // completed the synchronising kernels this rank has (see comm_gather)
   if (threadIdx.x == 0) {
@@ -150,12 +150,26 @@ __global__ void k_gather_push(const double *slab, int ny_loc, int nx, int nh, si
   }
   __syncthreads();
   const int nrows = ny_loc - 2 * nh;
+  const int M = nranks * nrows;   // interior rows of the replicated array
   const size_t total = (size_t)nrows * nx;
   for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
     int r = (int)(p / nx), c = (int)(p % nx);
     double v = slab[(size_t)(nh + r) * nx + c];
-    size_t dst = (size_t)(nh + row0 + r) * nx + c;
+    const int gi = row0 + r;      // global interior row
+    size_t dst = (size_t)(nh + gi) * nx + c;
     for (int k = 0; k < nranks; k++) reinterpret_cast<double *>(arena[k] + full_off)[dst] = v;
+    // yimages: the periodic y halo rows of the replicated array (the x halo columns travel with
+    // the rows), so that no halo-fill kernel has to follow the gather
+    if (yimages) {
+      if (gi < nh) {
+        const size_t d2 = (size_t)(nh + M + gi) * nx + c;
+        for (int k = 0; k < nranks; k++) reinterpret_cast<double *>(arena[k] + full_off)[d2] = v;
+      }
+      if (gi >= M - nh) {
+        const size_t d2 = (size_t)(gi - M + nh) * nx + c;
+        for (int k = 0; k < nranks; k++) reinterpret_cast<double *>(arena[k] + full_off)[d2] = v;
+      }
+    }
   }
   __syncthreads();   // the block's stores happen-before thread 0's system fence (cumulativity)
   if (threadIdx.x == 0) {
@@ -251,7 +265,7 @@ int comm_barrier(f2d_comm *c, int all, cudaStream_t s) {
 }
 // slab (interior rows) -> the same rows of every rank's replicated array `full` (symmetric address)
 int comm_gather(f2d_comm *c, const double *slab, double *full, int ny_loc, int nx, int nh, cudaStream_t s,
-                bool barrier_first) {
+                bool barrier_first, bool yimages) {
   // The replicated levels run without any synchronisation, so a fast rank could push the
   // next cycle's data into `full` while a slow rank still reads the previous contents.
   // The push kernel first waits until every rank has completed the synchronising kernels
@@ -269,7 +283,7 @@ int comm_gather(f2d_comm *c, const double *slab, double *full, int ny_loc, int n
   int blocks = cdiv(total, 256);
   if (blocks > 128) blocks = 128;
   k_gather_push<<<blocks, 256, 0, s>>>(slab, ny_loc, nx, nh, off, row0, d_arena, c->ctrl[c->rank], c->d_ctrl, c->rank,
-                                       c->nranks);
+                                       c->nranks, yimages ? 1 : 0);
   F2D_LAUNCHED();
   return F2D_OK;
 }

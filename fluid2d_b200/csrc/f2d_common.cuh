@@ -220,7 +220,7 @@ int comm_exchange(f2d_comm *c, double *const *arrs, int narr, int nh, int ny, in
 int comm_allreduce(f2d_comm *c, double *vals, int n, unsigned maxmask, cudaStream_t s);
 int comm_barrier(f2d_comm *c, int all, cudaStream_t s);
 int comm_gather(f2d_comm *c, const double *slab, double *full, int ny_loc, int nx, int nh, cudaStream_t s,
-                bool barrier_first = true);
+                bool barrier_first = true, bool yimages = false);
 int comm_gather_i8(f2d_comm *c, const int8_t *slab, int8_t *full, int ny_loc, int nx, int nh, cudaStream_t s);
 
 }  // namespace f2d

@@ -30,7 +30,11 @@ int gather_to_full(f2d_mg *mg, const double *slab, double *full, cudaStream_t s)
   Level &v = mg->S[mg->lg];
   Level &f = mg->L[0];
   // lg == 0: nothing but gathers between two uses of `full` -> explicit barrier first
-  TRY(comm_gather(mg->comm, slab, full, v.ny, v.nx, NH, s, mg->lg == 0));
+  // lg >= 1: the slab array comes from a kernel that wrote its x halo columns; the gather also
+  // pushes the rows that are the periodic y halo of the replicated array -- no fill kernel
+  const bool yimages = mg->lg >= 1;
+  TRY(comm_gather(mg->comm, slab, full, v.ny, v.nx, NH, s, mg->lg == 0, yimages));
+  if (yimages) return F2D_OK;
   return f2d_fill_halo(full, NH, f.ny, f.nx, (f2d_stream_t)s);
 }
 // this rank's rows of the replicated level-lg array, halo rows included, as a slab array: the

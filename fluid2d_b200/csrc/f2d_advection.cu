@@ -2,7 +2,11 @@
 // :169-284) and the flux-storing variants of core/fortran_fluxes.f90.
 //
 // One CTA computes a TX x TY tile of dq = -div(U q).  The q tile (halo 3) and the u, v
-// tiles are staged in shared memory with asynchronous copies (LDGSTS); every east-face
+// tiles arrive in shared memory as three TMA boxes (one instruction each; per-element
+// asynchronous copies, LDGSTS, on arrays too small for a box or with F2D_ADV_TMA=0).  All
+// tracers of a model go through ONE launch (f2d_adv_multi: Operators.rhs_adv's loop over the
+// tracer list, operators.py:214-236), and the same kernel can write the Runge-Kutta stage
+// state x + coef*dq (timescheme.py:172-176) while the tendency is in registers.  Every east-face
 // flux of the tile is computed once (in place over the u tile) and shared through
 // shared memory, the north-face flux is carried in a register while a thread marches
 // up its strip of rows (the Fortran's fym).  The periodic halo fill

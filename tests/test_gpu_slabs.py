@@ -59,8 +59,20 @@ def ngpus():
 @pytest.mark.parametrize("nx,ny,min_cells", [(64, 128, "1500"), (64, 128, "100000000"), (128, 256, "3000"),
                                              (1024, 2048, "100000")])
 def test_two_slabs_match_single_gpu(nx, ny, min_cells):
-    if ngpus() < 2:
-        pytest.skip("needs 2 GPUs")
+    slabs_match_single_gpu(2, nx, ny, min_cells)
+
+
+@pytest.mark.parametrize("nranks,nx,ny,min_cells", [(4, 128, 512, "3000"), (4, 512, 2048, "100000"),
+                                                    (8, 128, 1024, "3000")])
+def test_more_slabs_match_single_gpu(nranks, nx, ny, min_cells):
+    """the same invariance on 4 and 8 ranks (every rank has two distinct neighbours; the gather
+    assembles 4 / 8 slabs); skipped on boxes with fewer GPUs"""
+    slabs_match_single_gpu(nranks, nx, ny, min_cells)
+
+
+def slabs_match_single_gpu(nranks, nx, ny, min_cells):
+    if ngpus() < nranks:
+        pytest.skip("needs %d GPUs" % nranks)
     import fluid2d_b200
     api = fluid2d_b200.api()
     nsteps = 3
@@ -77,7 +89,7 @@ def test_two_slabs_match_single_gpu(nx, ny, min_cells):
     np.savez(refpath, **ref)
     out = os.path.join(d, "out.json")
     env = dict(os.environ, F2D_SLAB_MIN_CELLS=min_cells)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks),
            "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
            os.path.join(REPO, "tests", "slab_worker.py"), refpath, out, str(nx), str(ny), str(nsteps)]
     p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)

@@ -261,6 +261,16 @@ class DeviceState(object):
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._upload_evt = None    # CUDA event behind the last asynchronous upload from the mirror
+        # Uploads run on a copy stream of their own: the first stale field a kernel asks for starts
+        # the upload of EVERY stale field (the one asked for first), one event per field, and the
+        # compute stream waits for a field's event only when a kernel is about to touch that
+        # field -- so the fields a step needs later cross PCIe while its first kernels run.
+        # The order of a batch is the order in which the kernels asked for the fields after the
+        # previous batch (a time step asks for them in the same order every step).
+        self._copy_stream = None
+        self._pending = [None]*nvar    # per field: event of an upload still (possibly) in flight
+        self._asked = []               # fields in the order they were asked for since the last batch
+        self._asked_before = []        # ... and between the two batches before that
 
     def _wait_upload(self):
         """an upload from the pinned mirror is asynchronous: the host must not write the mirror
@@ -291,6 +301,7 @@ class DeviceState(object):
         for f in todo:
             if not self.dev_fresh[f]:
                 raise RuntimeError('DeviceState: field %d stale on both sides' % f)
+            self._await_field(f)
             self._host_t[f].copy_(self.dev[f], non_blocking=True)
             self.host_fresh[f] = True
             self.d2h_bytes += self.fieldbytes
@@ -333,17 +344,47 @@ class DeviceState(object):
             v[k] = value
 
     # -- device side ---------------------------------------------------------
+    def _await_field(self, f):
+        """the compute stream waits for the upload of field f, if one may still be in flight"""
+        e = self._pending[f]
+        if e is not None:
+            torch.cuda.current_stream().wait_event(e)
+            self._pending[f] = None
+
     def to_device(self, k=None):
-        moved = False
-        for f in self._fields(k):
-            if not self.dev_fresh[f]:
-                self.dev[f].copy_(self._host_t[f], non_blocking=True)
-                self.dev_fresh[f] = True
-                self.h2d_bytes += self.fieldbytes
-                moved = True
-        if moved and self.device.type == 'cuda':
-            self._upload_evt = torch.cuda.Event()
-            self._upload_evt.record()
+        want = list(self._fields(k))
+        if k is not None and k not in self._asked:
+            self._asked.append(k)
+        if self.device.type != 'cuda':
+            for f in want:
+                if not self.dev_fresh[f]:
+                    self.dev[f].copy_(self._host_t[f])
+                    self.dev_fresh[f] = True
+                    self.h2d_bytes += self.fieldbytes
+            return
+        if any(not self.dev_fresh[f] for f in want):
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            cs = self._copy_stream
+            # kernels already enqueued may still read what the copies overwrite
+            cs.wait_stream(torch.cuda.current_stream())
+            if len(self._asked) > 1 or not self._asked_before:
+                self._asked_before = list(self._asked)
+            self._asked = [k] if k is not None else []
+            stale = [f for f in want if not self.dev_fresh[f]]
+            stale += [f for f in self._asked_before if not self.dev_fresh[f] and f not in stale]
+            stale += [f for f in range(self.nvar) if not self.dev_fresh[f] and f not in stale]
+            with torch.cuda.stream(cs):
+                for f in stale:
+                    self.dev[f].copy_(self._host_t[f], non_blocking=True)
+                    self.dev_fresh[f] = True
+                    self.h2d_bytes += self.fieldbytes
+                    e = torch.cuda.Event()
+                    e.record(cs)
+                    self._pending[f] = e
+                self._upload_evt = self._pending[stale[-1]]
+        for f in want:
+            self._await_field(f)
 
     def rptr(self, k):
         """device address of field k for reading"""
@@ -368,6 +409,8 @@ class DeviceState(object):
         return self.nvar*self.ny*self.nx
 
     def zero_(self):
+        for f in range(self.nvar):
+            self._await_field(f)
         self.dev.zero_()
         self.dev_fresh = [True]*self.nvar
         self.host_fresh = [False]*self.nvar if self._host is not None else [True]*self.nvar

@@ -358,8 +358,11 @@ k_smooth2(LevelK L, const double *__restrict__ xin, const double *__restrict__ b
   if (use_tma) {
     __syncthreads();
     if (t == 0) {
-      // (PEER) the neighbour's halo rows were observed through the generic proxy
-      if (PEER) asm volatile("fence.proxy.async;" ::: "memory");
+      // (PEER, boundary tiles: the only ones that read rows a neighbour stored) the neighbour's
+      // halo rows were observed through the generic proxy.  Interior tiles skip the fence
+      // (measured on 2 B200s, 16384 x 8192 per rank: 943 -> 901 us per launch in the ungraphed
+      // step, k_resid_restrict 627 -> 564 us)
+      if (PEER && (bsouth || bnorth)) asm volatile("fence.proxy.async;" ::: "memory");
       constexpr unsigned bytes = (HAVE_X ? XH * XP * 8 : 0) + (INTERP ? CH * CP * 8 : 0);
       if (bytes) f2d::mbar_expect_tx(&S.bar, bytes);
       if (HAVE_X) f2d::tma_load_2d(&S.xs[0][0], &tmx, &S.bar, i0 - 3, j0 - 2);
@@ -624,7 +627,7 @@ k_resid_restrict(LevelK L, const double *__restrict__ x, const double *__restric
   if (use_tma) {
     __syncthreads();
     if (t == 0) {
-      if (PEER) asm volatile("fence.proxy.async;" ::: "memory");
+      if (PEER && (bsouth || bnorth)) asm volatile("fence.proxy.async;" ::: "memory");
       f2d::mbar_expect_tx(&S.bar, (RXH * RXP + RH * RBP) * 8);
       f2d::tma_load_2d(&S.xs[0][0], &tmx, &S.bar, fi0 - 1, fj0 - 1);
       f2d::tma_load_2d(&S.bs[0][0], &tmb, &S.bar, fi0 - 1, fj0);   // even column: the tile sits at column offset 1
@@ -770,7 +773,7 @@ k_zsmooth_resid_restrict(LevelK L, double *__restrict__ tout, double *__restrict
   if (PEER && (bsouth || bnorth)) f2d::peer_wait(P, bsouth, bnorth);
   __syncthreads();
   if (t == 0) {
-    if (PEER) asm volatile("fence.proxy.async;" ::: "memory");   // the neighbours' rows were observed through the generic proxy
+    if (PEER && (bsouth || bnorth)) asm volatile("fence.proxy.async;" ::: "memory");   // the neighbours' rows were observed through the generic proxy
     f2d::mbar_expect_tx(&S.bar, ZBH * ZBP * 8);
     f2d::tma_load_2d(&S.bs[0][0], &tmb, &S.bar, fi0 - 3, fj0 - 2);
   }

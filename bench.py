@@ -118,7 +118,9 @@ def kernel_bytes_per_cell(name):
     m = re.match(r"k_reduce1<nout(\d+)> (\d+)x(\d+)", name)
     if m:
         nout = int(m.group(1))
-        return (40. if nout == 8 else 8.), int(m.group(2))*int(m.group(3))
+        # the fused Euler diagnostics read u, v, vorticity, psi, source, xr, yr and the mask once
+        # each (f2d_diag_euler; ncu: 960 MB per launch at 4096^2); the single sums one field + mask
+        return (57. if nout == 8 else 9.), int(m.group(2))*int(m.group(3))
     return None, None
 
 

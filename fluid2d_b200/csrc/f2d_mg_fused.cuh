@@ -7,6 +7,14 @@
 //                      :415-498 and the `x += r` of hierarchy.py:123-126 fused in).
 //   k_resid_restrict : computeresidualwithA (:320-362) + restrict (:501-546) + halo
 //                      fills; the fine residual never goes to HBM.
+//   k_zsmooth_resid_restrict : both of the above for a level visited on the way down from a
+//                      zero first guess (hierarchy.py:100-107), in one kernel that reads b once
+//                      (all-fluid levels; see the comment in front of it).
+//
+// Tiles: 64 x 32 outputs per CTA of 256 threads (a thread marches a column strip with the 3x3
+// window in registers); levels that would get fewer such tiles than the device has SMs use
+// 64 x 8 tiles (template parameter TYP / RTYP), where a thread owns 2-3 rows and the stored
+// coefficients of all of them are loaded before the first is used.
 //
 // Coefficient classes (template parameters MASKED, STORED):
 //   !MASKED,!STORED  the level is all fluid and its matrix is one constant 9-point
@@ -147,8 +155,8 @@ struct Smooth2SmemT {
     double cs[CH][CP];
   };
   alignas(8) uint64_t bar;          // mbarrier of the TMA loads
-  // mask tiles last: the mask-free instantiations are launched with SMOOTH2_SMEM_NOMASK
-  // bytes only (56 KB -> 4 CTAs per SM instead of 3)
+  // mask tiles last: the mask-free instantiations are launched with smooth2_smem_nomask<TYP>()
+  // bytes only (38 KB at TYP = 32: the register file, not shared memory, then sets 4 CTAs per SM)
   int8_t ms[XH][XW];
   int8_t cm[CH][CW];
 };

@@ -41,7 +41,7 @@ constexpr int NT = 256;  // threads per CTA
 struct LevelK {
   int ny, nx;
   const int8_t *msk;
-  const double *A;   // 5 planes (STORED)
+  const double *A;   // 5 planes SW,S,SE,W,C (STORED) + a 6th written at set-up: omega / |C|
   double c[5];       // SW,S,SE,W,C (constant classes)
   double c1, c2, c3; // omega, 1-omega, omega/|C|
   int ywrap;         // 1: y halo rows are local periodic images; 0: they belong to the neighbouring slabs
@@ -52,24 +52,23 @@ template <bool MASKED, bool STORED>
 struct Coefs {
   double sw, s, se, w, e, nw, n, ne, c3;
   // m: pointer to the centre of a mask window with row stride ms (MASKED only)
-  // STORED, in two steps, so that a column strip can issue the loads of ALL its rows before it
-  // waits for the first of them (one round trip to L2 per sweep instead of one per row):
-  // load_raw leaves the diagonal in c3, finish turns it into omega / |diagonal|.
-  // Matrices and masks are written at set-up only: non-coherent loads (LDG.CONSTANT), which
-  // the barriers and fences of the cycle kernels do not throw out of L1.
-  __device__ __forceinline__ void load_raw(const LevelK &L, size_t g) {
+  // STORED: the eight off-diagonal coefficients of cell g and, in c3, what the caller applies
+  // with them: omega / |diagonal| for a sweep -- the 6th plane, divided once at set-up
+  // (k_inverse_diagonal: the same IEEE division the sweep used to do per point, 25 dependent
+  // instructions on a latency-bound path) -- or the diagonal itself for a residual (RESID).
+  // Matrices and masks are written at set-up only: non-coherent loads (LDG.CONSTANT).
+  template <bool RESID>
+  __device__ __forceinline__ void load_stored(const LevelK &L, size_t g) {
     size_t pl = (size_t)L.ny * L.nx;
-    const double *A1 = L.A, *A2 = L.A + pl, *A3 = L.A + 2 * pl, *A4 = L.A + 3 * pl, *A5 = L.A + 4 * pl;
+    const double *A1 = L.A, *A2 = L.A + pl, *A3 = L.A + 2 * pl, *A4 = L.A + 3 * pl;
     int nx = L.nx;
     sw = __ldg(A1 + g); s = __ldg(A2 + g); se = __ldg(A3 + g); w = __ldg(A4 + g);
     e = __ldg(A4 + g + 1); nw = __ldg(A3 + g + nx - 1); n = __ldg(A2 + g + nx); ne = __ldg(A1 + g + nx + 1);
-    c3 = __ldg(A5 + g);
+    c3 = __ldg(L.A + (RESID ? 4 : 5) * pl + g);
   }
-  __device__ __forceinline__ void finish(const LevelK &L) { c3 = L.c1 / fabs(c3); }
   __device__ __forceinline__ void load(const LevelK &L, size_t g, const int8_t *m, int ms) {
     if (STORED) {
-      load_raw(L, g);
-      finish(L);
+      load_stored<false>(L, g);
     } else if (MASKED) {
       sw = m[-ms - 1] ? L.c[0] : 0.; s = m[-ms] ? L.c[1] : 0.; se = m[-ms + 1] ? L.c[2] : 0.;
       w = m[-1] ? L.c[3] : 0.;       e = m[1] ? L.c[3] : 0.;
@@ -271,7 +270,7 @@ __device__ __forceinline__ void jacobi_strip(const LevelK &L, const Coefs<MASKED
 #pragma unroll
     for (int k = 0; k < NR; k++) {
       const bool okk = k < nr && (!GUARD || (j + k >= lo && j + k <= ny - 1 - lo && i >= lo && i <= nx - 1 - lo));
-      if (okk) kpre[k].load_raw(L, g + (size_t)k * nx);
+      if (okk) kpre[k].template load_stored<false>(L, g + (size_t)k * nx);
     }
   }
 #pragma unroll
@@ -287,7 +286,7 @@ __device__ __forceinline__ void jacobi_strip(const LevelK &L, const Coefs<MASKED
         // stored coefficients are fetched whether the cell is fluid or not: loads that do not hang
         // on the mask test can be issued ahead of the rows before them
         Coefs<MASKED, STORED> kk;
-        if (PRE) { kk = kpre[k]; kk.finish(L); }
+        if (PRE) kk = kpre[k];
         else if (STORED) kk.load(L, g + (size_t)k * nx, nullptr, MLD);
         if (!MASKED || (MWIN ? wm1 : (int)mp[k * MLD]) != 0) {
           if (MWIN) kk.from_window(L, wa0, wa1, wa2, wm0, wm2, wh0, wh1, wh2);
@@ -570,7 +569,7 @@ __device__ __forceinline__ void resid_strip(const LevelK &L, const Coefs<MASKED,
 #pragma unroll
     for (int k = 0; k < NR; k++) {
       const bool okk = k < nr && (!GUARD || (j + k < ny - NH && i < nx - NH));
-      if (okk) kpre[k].load_raw(L, g + (size_t)k * nx);
+      if (okk) kpre[k].template load_stored<true>(L, g + (size_t)k * nx);
     }
   }
 #pragma unroll
@@ -592,9 +591,9 @@ __device__ __forceinline__ void resid_strip(const LevelK &L, const Coefs<MASKED,
         Coefs<MASKED, STORED> kk;
         if (MWIN) kk.from_window(L, wa0, wa1, wa2, wm0, wm2, wh0, wh1, wh2);
         else if (PRE) kk = kpre[k];
-        else if (STORED) kk.load_raw(L, g + (size_t)k * nx);
+        else if (STORED) kk.template load_stored<true>(L, g + (size_t)k * nx);
         else kk = kc;
-        // (the residual uses the diagonal itself, not omega / |diagonal|: load_raw leaves it in c3)
+        // (the residual uses the diagonal itself, not omega / |diagonal|: load_stored<true> leaves it in c3)
         double cdiag = STORED ? kk.c3 : L.c[4];
         val = resid_val<MASKED, STORED>(L, kk, cdiag, a0, a1, a2, m0, m1, m2, h0, h1, h2, bp[k * RBP]);
       }

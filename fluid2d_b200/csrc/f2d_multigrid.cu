@@ -384,6 +384,12 @@ __global__ void k_helmholtz(double *__restrict__ A5, double shift, size_t n) {
   for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
     if (A5[k] != 0.) A5[k] = A5[k] - shift;
 }
+// 6th matrix plane: omega / |centre coefficient|, the factor of the damped-Jacobi update
+// (fortran_multigrid.f90:2-127 divides at every point of every sweep; the quotient is the same)
+__global__ void k_inverse_diagonal(const double *__restrict__ A5, double *__restrict__ A6, double omega, size_t n) {
+  size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (k < n) A6[k] = omega / fabs(A5[k]);
+}
 __global__ void k_add_inplace(double *__restrict__ y, const double *__restrict__ a, size_t n) {
   for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
     y[k] = y[k] + a[k];
@@ -1290,7 +1296,7 @@ Stencil9 finest_stencil(double dx, double dy, double hydroepsilon) {
 int alloc_level(f2d_mg *mg, Level &l, bool arena, cudaStream_t s) {
   size_t nb = l.n() * sizeof(double);
   MGC(cudaMalloc(&l.msk, l.n()));
-  MGC(cudaMalloc(&l.A, 5 * nb));
+  MGC(cudaMalloc(&l.A, 6 * nb));   // 5 diagonals + omega / |centre| (finish_setup)
   MGC(cudaMalloc(&l.r, nb));
   l.arena = arena;
   if (arena) {
@@ -1412,6 +1418,11 @@ int finish_setup(f2d_mg *mg, double Rd, cudaStream_t s) {
         ++g_launches;
       }
   }
+  for (auto *vec : {&mg->S, &mg->L})
+    for (auto &l : *vec) {
+      k_inverse_diagonal<<<cdiv(l.n(), 256), 256, 0, s>>>(l.A + 4 * l.n(), l.A + 5 * l.n(), mg->omega, l.n());
+      ++g_launches;
+    }
   MGC(set_smem_all());
   {
     // per-block partial sums of k_resid_sumsq (finest level of the handle: L[0], or S[0] on slabs)

@@ -109,6 +109,9 @@ def kernel_bytes_per_cell(name):
     m = re.match(r"k_adv<upw\d,order\d,masked(\d)> (\d+)x(\d+)", name)
     if m:
         return 32.+float(m.group(1)), int(m.group(2))*int(m.group(3))
+    m = re.match(r"f2d_mask_orthogradient_stage<(\d) extra>", name)
+    if m:   # psi read and written masked, u, v written; base (and extra tendency) of u, v read, stage u, v written
+        return 32.+32.+16.*int(m.group(1)), None
     m = re.match(r"k_map_vec<(\d) in> (\d+) doubles", name)
     if m:
         return 8.*(int(m.group(1))+1), int(m.group(2))
@@ -150,6 +153,8 @@ def kernel_table(lib, r, f2d, peak, shape, nsteps=2):
         # f2d_* entry points without a tag work on the whole local grid
         if bpc is None and name in ("f2d_mask_orthogradient", "f2d_celltocorner"):
             bpc, cells = (32., ny*nx) if name == "f2d_mask_orthogradient" else (16., ny*nx)
+        if bpc is not None and cells is None:
+            cells = ny*nx
         avg = us/cnt
         gbs = bpc*cells/(avg*1e-6)/1e9 if bpc else None
         out.append({"kernel": name, "launches_per_step": cnt/float(nsteps), "share": us/total, "avg_us": avg,

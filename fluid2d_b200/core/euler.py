@@ -52,6 +52,10 @@ class Euler(object):
             if self.timestepping == 'RK3_SSP':
                 self.tscheme.adv_hook = self.ope
                 self.tscheme.fused_fields = tr
+                # ... and at the first two stages the tendencies of u, v are what the inversion
+                # that ends dynamics() derives: its orthogradient kernel writes the stage velocities
+                self.tscheme.uv_hook = self.ope
+                self.tscheme.uv_fields = (ix('u'), ix('v'))
         r = rt()
         self.rt = r
         self.d_xr = r.to_device(self.xr, dtype=np.float64)

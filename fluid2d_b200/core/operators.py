@@ -110,6 +110,8 @@ class Operators(Param):
         self.last_solve = (0, 0.)
         self.fuse = None     # request of the time scheme: stage update fused into the advection kernel
         self.fused = []
+        self.fuse_uv = None  # request of the time scheme: stage velocities written by the next inversion
+        self.fused_uv = False
 
     # ------------------------------------------------------------------
     def set_boundary_msk(self):
@@ -324,6 +326,17 @@ class Operators(Param):
             print('-'*50)
         # all-fluid domain without island: the mask-free orthogradient (no mask traffic)
         nomask = self.all_fluid and not island and self.nxl % 2 == 0
+        fu = getattr(self, 'fuse_uv', None)
+        if fu is not None and x is fu[0] and self.comm is None:
+            # Timescheme.RK3_SSP asked for the stage velocities: this inversion's orthogradient
+            # kernel writes out[u] = base[u] + coef*([extra[u] +] x[u]) (v alike) as well
+            _, base, extra, out, coef = fu
+            lib.mg_set_uv_stage(self.gmg.h, base.rptr(iu), base.rptr(iv),
+                                extra.rptr(iu) if extra is not None else None,
+                                extra.rptr(iv) if extra is not None else None,
+                                out.wptr(iu), out.wptr(iv), coef)
+            self.fused_uv = True
+            self.fuse_uv = None
         lib.invert_vorticity(self.gmg.h, None if nomask else r.ptr(self.d_msk),
                              None if nomask else r.ptr(self.d_mskp), x.rptr(iw), x.wptr(ip),
                              x.wptr(iu), x.wptr(iv), r.ptr(self.work), rhsp, psi_island, full,

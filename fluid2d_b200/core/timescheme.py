@@ -47,6 +47,12 @@ class Timescheme(object):
         # itself -- tracers whose tendency is complete once rhs_adv has run at that stage
         self.adv_hook = None
         self.fused_fields = []
+        # optional: the model's Operators and the indices (u, v): at the first two stages of
+        # RK3_SSP the inversion that ends rhs() derives the velocity tendencies, and its
+        # orthogradient kernel may write the stage velocities x[u] + c*(...) itself
+        # (f2d_mg_set_uv_stage); only for models whose u, v tendencies are complete at that point
+        self.uv_hook = None
+        self.uv_fields = None
         self.kstage = 0
         self.kforcing = 0
         self.forward = self._unset
@@ -191,25 +197,48 @@ class Timescheme(object):
         stage = self._runs(self.fields_stage if self.fields_stage is not None else range(nf))
         final = self._runs(self.fields_final if self.fields_final is not None else range(nf))
         fs = self.fieldsize
+        stage_fields = list(self.fields_stage if self.fields_stage is not None else range(nf))
         self.kstage = 0
         done = []
-        if self.adv_hook is not None and self.fused_fields:
-            self.adv_hook.fuse = (self.x, x, dt, list(self.fused_fields))
-            try:
+        uv = self.uv_hook if (self.uv_hook is not None and self.uv_fields is not None
+                              and all(k in stage_fields for k in self.uv_fields)) else None
+        if uv is not None:
+            # (tendency buffer the inversion works on, base state, extra tendency, stage state, coefficient)
+            uv.fuse_uv = (self.dx0, x, None, self.x, dt)
+            uv.fused_uv = False
+        try:
+            if self.adv_hook is not None and self.fused_fields:
+                self.adv_hook.fuse = (self.x, x, dt, list(self.fused_fields))
+                try:
+                    self.rhs(x, t, self.dx0)
+                finally:
+                    done = list(self.adv_hook.fused)
+                    self.adv_hook.fuse = None
+                    self.adv_hook.fused = []
+            else:
                 self.rhs(x, t, self.dx0)
-            finally:
-                done = list(self.adv_hook.fused)
-                self.adv_hook.fuse = None
-                self.adv_hook.fused = []
-            todo = [k for k in (self.fields_stage if self.fields_stage is not None else range(nf)) if k not in done]
-            stage0 = self._runs(todo)
-        else:
-            self.rhs(x, t, self.dx0)
-            stage0 = stage
+        finally:
+            if uv is not None:
+                if uv.fused_uv:
+                    done += list(self.uv_fields)
+                uv.fuse_uv = None
+        stage0 = self._runs([k for k in stage_fields if k not in done]) if done else stage
         for k0, c in stage0:
             lib.ts_xpay(self._wk(self.x, k0, c), self._rk(x, k0, c), dt, self._rk(self.dx0, k0, c), c*fs, r.stream)
         self.kstage = 1
-        self.rhs(self.x, t+dt, self.dx1)
+        done1 = []
+        if uv is not None:
+            uv.fuse_uv = (self.dx1, x, self.dx0, self.x, 0.25*dt)
+            uv.fused_uv = False
+        try:
+            self.rhs(self.x, t+dt, self.dx1)
+        finally:
+            if uv is not None:
+                if uv.fused_uv:
+                    done1 = list(self.uv_fields)
+                uv.fuse_uv = None
+        if done1:
+            stage = self._runs([k for k in stage_fields if k not in done1])
         for k0, c in stage:
             lib.ts_xpay2(self._wk(self.x, k0, c), self._rk(x, k0, c), 0.25*dt, self._rk(self.dx0, k0, c),
                          self._rk(self.dx1, k0, c), c*fs, r.stream)

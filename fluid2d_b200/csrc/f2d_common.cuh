@@ -209,6 +209,10 @@ __device__ __forceinline__ T *peer_addr(T *p, long long off) {
   return reinterpret_cast<T *>(reinterpret_cast<char *>(p) + off);
 }
 
+// Runge-Kutta stage update of the velocities by f2d_ts_xpay / f2d_ts_xpay2 (f2d_operators.cu)
+int uv_stage(const double *u, const double *v, const double *ub, const double *vb, const double *ue,
+             const double *ve, double *uo, double *vo, double c, size_t n, f2d_stream_t s);
+
 // ---- multi-GPU plumbing (f2d_comm.cu) ------------------------------------------------
 Peer comm_peer(const f2d_comm *c);
 int comm_drain(f2d_comm *c, cudaStream_t s);

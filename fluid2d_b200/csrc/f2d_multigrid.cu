@@ -55,6 +55,8 @@ struct f2d_mg {
   int tail0 = -1;             // first level of the shared-memory tail (-1: no tail kernel)
   bool tail_const = false;    // every tail level is in the constant-stencil class
   size_t tail_smem = 0;
+  // one-shot Runge-Kutta stage update of the velocities for the next f2d_invert_vorticity
+  struct UVStage { bool on = false; const double *ub, *vb, *ue, *ve; double *uo, *vo; double c; } uvs;
   int tail_nt = tail::NT;     // threads of the one-CTA tail kernel (F2D_TAIL_NT)
   bool ctail = false;         // the tail runs on a thread-block cluster (f2d_mg_ctail.cuh), from 256^2 / 128^2 down
   int ctail_nc = 1;           // CTAs of that cluster (1 when no level of the tail is distributed)
@@ -1972,6 +1974,16 @@ extern "C" int f2d_mg_set_trace(f2d_mg_t *mg, long long *buf, int cap) {
   return F2D_OK;
 }
 
+extern "C" int f2d_mg_set_uv_stage(f2d_mg_t *mg, const double *ub, const double *vb, const double *ue,
+                                   const double *ve, double *uo, double *vo, double c) {
+  if (!mg || !ub || !vb || !uo || !vo) return fail(F2D_ERR_ARG, "mg_set_uv_stage: null");
+  if ((ue == nullptr) != (ve == nullptr)) return fail(F2D_ERR_ARG, "mg_set_uv_stage: ue and ve go together");
+  mg->uvs.on = true;
+  mg->uvs.ub = ub; mg->uvs.vb = vb; mg->uvs.ue = ue; mg->uvs.ve = ve;
+  mg->uvs.uo = uo; mg->uvs.vo = vo; mg->uvs.c = c;
+  return F2D_OK;
+}
+
 extern "C" int f2d_invert_vorticity(f2d_mg_t *mg, const int8_t *msk, const int8_t *mskp, const double *w,
                                     double *psi, double *u, double *v, double *work, const double *rhsp,
                                     const double *psi_island, int full, int perio, double area, double dx,
@@ -1997,6 +2009,17 @@ extern "C" int f2d_invert_vorticity(f2d_mg_t *mg, const int8_t *msk, const int8_
     TRY(f2d_mg_two_vcycle(mg, psi, work, stream));
     if (nite) *nite = 1;
     if (res) *res = 0.;
+  }
+  if (mg->uvs.on) {
+    const f2d_mg::UVStage R = mg->uvs;
+    mg->uvs.on = false;
+    if (!psi_island)
+      return f2d_mask_orthogradient_stage(msk, mskp, psi, dx, dy, nh, u, v, R.ub, R.vb, R.ue, R.ve, R.uo, R.vo, R.c,
+                                          l.ny, l.nx, stream);
+    TRY(f2d_mul_mask(psi, mskp, n, stream));
+    TRY(f2d_add_scaled(psi, 1., psi_island, n, stream));
+    TRY(f2d_orthogradient(msk, psi, dx, dy, nh, u, v, l.ny, l.nx, stream));
+    return f2d::uv_stage(u, v, R.ub, R.vb, R.ue, R.ve, R.uo, R.vo, R.c, n, stream);
   }
   if (!psi_island) return f2d_mask_orthogradient(msk, mskp, psi, dx, dy, nh, u, v, l.ny, l.nx, stream);
   TRY(f2d_mul_mask(psi, mskp, n, stream));

@@ -296,11 +296,22 @@ __global__ void k_mask_orthogradient(const int8_t *__restrict__ msk, const int8_
 // from the lane to the left.  ALLFLUID (msk == NULL): the cell mask is 1 everywhere and the
 // corner mask is 1 except on the last row and column, so no mask byte is read at all.
 constexpr int OG_ROWS = 16;
-template <bool ALLFLUID>
+// RK (Timescheme.RK3_SSP, timescheme.py:172-180): the velocities (u, v) this kernel derives are the
+// tendencies du, dv of a stage, and the stage state uo = ub + c*du (ue == NULL) or
+// ub + c*(ue + du) -- v alike -- is written while they are in registers, for every cell of the
+// array (the outermost ring, which computeorthogradient leaves alone, combines the stored du),
+// with numpy's rounding sequence: what f2d_ts_xpay / f2d_ts_xpay2 would compute from the stored
+// fields, without reading them back.
+struct UVStage {
+  const double *ub, *vb, *ue, *ve;
+  double *uo, *vo;
+  double c;
+};
+template <bool ALLFLUID, bool RK>
 __global__ void __launch_bounds__(128) k_mask_orthogradient_strip(const int8_t *__restrict__ msk,
                                                                   const int8_t *__restrict__ mskp, double *psi,
                                                                   double zdx, double zdy, double *__restrict__ u,
-                                                                  double *__restrict__ v, int ny, int nx) {
+                                                                  double *__restrict__ v, int ny, int nx, UVStage R) {
   const int i = (blockIdx.x * 128 + threadIdx.x) * 2;
   const int j0 = blockIdx.y * OG_ROWS;
   const bool active = i < nx;
@@ -335,7 +346,14 @@ __global__ void __launch_bounds__(128) k_mask_orthogradient_strip(const int8_t *
     if (active) {
       const size_t c = (size_t)j * nx + i;
       *reinterpret_cast<double2 *>(psi + c) = p;
-      if (j >= 1 && j <= ny - 2) {
+      const bool wr = j >= 1 && j <= ny - 2;
+      double2 du = make_double2(0., 0.), dv = make_double2(0., 0.);
+      if (RK) {
+        // cells this kernel does not write keep their stored tendency
+        if (!wr || i < 1) { du.x = u[c]; dv.x = v[c]; }
+        if (!wr || i + 1 > nx - 2) { du.y = u[c + 1]; dv.y = v[c + 1]; }
+      }
+      if (wr) {
         if (lane == 0) pw = i > 0 ? masked1(j, i - 1) : 0.;
         bool ue0 = true, ue1 = true, vn0 = true, vn1 = true;
         if (!ALLFLUID) {
@@ -359,6 +377,22 @@ __global__ void __launch_bounds__(128) k_mask_orthogradient_strip(const int8_t *
           if (i >= 1) { u[c] = uu.x; v[c] = vv.x; }
           if (i + 1 <= nx - 2) { u[c + 1] = uu.y; v[c + 1] = vv.y; }
         }
+        if (RK) {
+          if (i >= 1) { du.x = uu.x; dv.x = vv.x; }
+          if (i + 1 <= nx - 2) { du.y = uu.y; dv.y = vv.y; }
+        }
+      }
+      if (RK) {
+        const double2 ub = *reinterpret_cast<const double2 *>(R.ub + c);
+        const double2 vb = *reinterpret_cast<const double2 *>(R.vb + c);
+        if (R.ue) {
+          const double2 ue = *reinterpret_cast<const double2 *>(R.ue + c);
+          const double2 ve = *reinterpret_cast<const double2 *>(R.ve + c);
+          du.x = add_rn(ue.x, du.x); du.y = add_rn(ue.y, du.y);
+          dv.x = add_rn(ve.x, dv.x); dv.y = add_rn(ve.y, dv.y);
+        }
+        *reinterpret_cast<double2 *>(R.uo + c) = make_double2(add_rn(ub.x, mul_rn(R.c, du.x)), add_rn(ub.y, mul_rn(R.c, du.y)));
+        *reinterpret_cast<double2 *>(R.vo + c) = make_double2(add_rn(vb.x, mul_rn(R.c, dv.x)), add_rn(vb.y, mul_rn(R.c, dv.y)));
       }
     }
     ps = p;
@@ -376,8 +410,9 @@ extern "C" int f2d_mask_orthogradient(const int8_t *msk, const int8_t *mskp, dou
                       (!msk || ((reinterpret_cast<uintptr_t>(msk) | reinterpret_cast<uintptr_t>(mskp)) & 1) == 0);
   if (vec_ok) {
     dim3 g(cdiv(nx, 256), cdiv(ny, OG_ROWS));
-    if (msk) k_mask_orthogradient_strip<false><<<g, 128, 0, S(s)>>>(msk, mskp, psi, 1. / dx, 1. / dy, u, v, ny, nx);
-    else k_mask_orthogradient_strip<true><<<g, 128, 0, S(s)>>>(msk, mskp, psi, 1. / dx, 1. / dy, u, v, ny, nx);
+    UVStage R = {};
+    if (msk) k_mask_orthogradient_strip<false, false><<<g, 128, 0, S(s)>>>(msk, mskp, psi, 1. / dx, 1. / dy, u, v, ny, nx, R);
+    else k_mask_orthogradient_strip<true, false><<<g, 128, 0, S(s)>>>(msk, mskp, psi, 1. / dx, 1. / dy, u, v, ny, nx, R);
     F2D_LAUNCHED();
     return F2D_OK;
   }
@@ -386,6 +421,55 @@ extern "C" int f2d_mask_orthogradient(const int8_t *msk, const int8_t *mskp, dou
   k_mask_orthogradient<<<grid2d(ny, nx, b), b, 0, S(s)>>>(msk, mskp, psi, 1. / dx, 1. / dy, u, v, ny, nx);
   F2D_LAUNCHED();
   return F2D_OK;
+}
+
+namespace f2d {
+// the stage update of the velocities as kernels of its own (f2d_ts_xpay / f2d_ts_xpay2 on u and v)
+int uv_stage(const double *u, const double *v, const double *ub, const double *vb, const double *ue,
+             const double *ve, double *uo, double *vo, double c, size_t n, f2d_stream_t s) {
+  int rc;
+  if (ue) {
+    rc = f2d_ts_xpay2(uo, ub, c, ue, u, n, s);
+    if (rc == F2D_OK) rc = f2d_ts_xpay2(vo, vb, c, ve, v, n, s);
+  } else {
+    rc = f2d_ts_xpay(uo, ub, c, u, n, s);
+    if (rc == F2D_OK) rc = f2d_ts_xpay(vo, vb, c, v, n, s);
+  }
+  return rc;
+}
+}  // namespace f2d
+
+/* f2d_mask_orthogradient followed by the Runge-Kutta stage update of the velocities,
+ * uo = ub + c*(u) or ub + c*(ue + u) (ue, ve both NULL or both given), v alike, over the whole
+ * arrays: one kernel when the strip kernel applies (even nx, 16-byte aligned fields), otherwise the
+ * orthogradient followed by f2d_ts_xpay / f2d_ts_xpay2 -- the same numbers either way. */
+extern "C" int f2d_mask_orthogradient_stage(const int8_t *msk, const int8_t *mskp, double *psi, double dx, double dy,
+                                            int nh, double *u, double *v, const double *ub, const double *vb,
+                                            const double *ue, const double *ve, double *uo, double *vo, double c,
+                                            int ny, int nx, f2d_stream_t s) {
+  if (!psi || !u || !v || !ub || !vb || !uo || !vo || ny < 3 || nx < 3)
+    return fail(F2D_ERR_ARG, "mask_orthogradient_stage: bad args");
+  if ((msk == nullptr) != (mskp == nullptr)) return fail(F2D_ERR_ARG, "mask_orthogradient_stage: msk and mskp go together");
+  if ((ue == nullptr) != (ve == nullptr)) return fail(F2D_ERR_ARG, "mask_orthogradient_stage: ue and ve go together");
+  uintptr_t al = reinterpret_cast<uintptr_t>(psi) | reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(v) |
+                 reinterpret_cast<uintptr_t>(ub) | reinterpret_cast<uintptr_t>(vb) | reinterpret_cast<uintptr_t>(uo) |
+                 reinterpret_cast<uintptr_t>(vo) | reinterpret_cast<uintptr_t>(ue) | reinterpret_cast<uintptr_t>(ve);
+  const bool vec_ok = nx % 2 == 0 && (al & 15) == 0 &&
+                      (!msk || ((reinterpret_cast<uintptr_t>(msk) | reinterpret_cast<uintptr_t>(mskp)) & 1) == 0);
+  // the stage state must not be one of the arrays the kernel still reads at other cells
+  const bool distinct = uo != u && uo != v && vo != u && vo != v && (void *)uo != (void *)psi && (void *)vo != (void *)psi;
+  if (vec_ok && distinct) {
+    dim3 g(cdiv(nx, 256), cdiv(ny, OG_ROWS));
+    UVStage R = {ub, vb, ue, ve, uo, vo, c};
+    prof_tag("f2d_mask_orthogradient_stage<%d extra>", ue ? 1 : 0);
+    if (msk) k_mask_orthogradient_strip<false, true><<<g, 128, 0, S(s)>>>(msk, mskp, psi, 1. / dx, 1. / dy, u, v, ny, nx, R);
+    else k_mask_orthogradient_strip<true, true><<<g, 128, 0, S(s)>>>(msk, mskp, psi, 1. / dx, 1. / dy, u, v, ny, nx, R);
+    F2D_LAUNCHED();
+    return F2D_OK;
+  }
+  int rc = f2d_mask_orthogradient(msk, mskp, psi, dx, dy, nh, u, v, ny, nx, s);
+  if (rc != F2D_OK) return rc;
+  return f2d::uv_stage(u, v, ub, vb, ue, ve, uo, vo, c, (size_t)ny * nx, s);
 }
 
 // add_diffusion: fortran_operators.f90:125-156, rows/cols 2..m-1 where msk==1

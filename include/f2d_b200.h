@@ -116,6 +116,15 @@ int f2d_orthogradient(const int8_t *msk, const double *psi, double dx, double dy
 int f2d_mask_orthogradient(const int8_t *msk, const int8_t *mskp, double *psi, double dx,
                            double dy, int nh, double *u, double *v, int ny, int nx,
                            f2d_stream_t stream);
+/* the same, followed by the Runge-Kutta stage update of the velocities it has just derived
+ * (Timescheme.RK3_SSP, timescheme.py:172-180: self.x[u] = x[u] + dt*dx0[u], then
+ * x[u] + dt/4*(dx0[u] + dx1[u]); v alike): uo = ub + c*u (ue == ve == NULL) or ub + c*(ue + u),
+ * over the whole arrays, with numpy's rounding sequence -- in the same kernel while u, v are in
+ * registers (even nx, 16-byte aligned fields), or by f2d_ts_xpay / f2d_ts_xpay2 behind it. */
+int f2d_mask_orthogradient_stage(const int8_t *msk, const int8_t *mskp, double *psi, double dx,
+                                 double dy, int nh, double *u, double *v, const double *ub,
+                                 const double *vb, const double *ue, const double *ve, double *uo,
+                                 double *vo, double c, int ny, int nx, f2d_stream_t stream);
 /* :125-156 add_diffusion(msk,trac,dx,nh,Kdiff,dtrac) (+ optional halo fill,
  * operators.py:300) */
 int f2d_add_diffusion(const int8_t *msk, const double *trac, double dx, int nh,
@@ -334,6 +343,11 @@ int f2d_invert_vorticity(f2d_mg_t *mg, const int8_t *msk, const int8_t *mskp,
                          const double *rhsp, const double *psi_island, int full, int perio,
                          double area, double dx, double dy, int nh, int *nite, double *res,
                          double *scratch, f2d_stream_t stream);
+/* One shot: the NEXT f2d_invert_vorticity on this handle also writes the Runge-Kutta stage state
+ * of the velocities, uo = ub + c*u (ue == ve == NULL) or ub + c*(ue + u), v alike (see
+ * f2d_mask_orthogradient_stage; with an island the update runs as kernels of its own). */
+int f2d_mg_set_uv_stage(f2d_mg_t *mg, const double *ub, const double *vb, const double *ue,
+                        const double *ve, double *uo, double *vo, double c);
 
 /* ---- multi-GPU: y-slab decomposition (npx = 1, npy = nranks), one process per GPU.
  * Replaces the mpi4py layer: gmg/halo.py (8 persistent Send/Recv per fill),

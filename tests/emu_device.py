@@ -539,10 +539,25 @@ class EmuLib(object):
             if res is not None:
                 res._obj.value = 0.
         if not _addr(psi_island):
-            return self.mask_orthogradient(msk, mskp, psi, dx, dy, nh, u, v, ny, nx, stream)
-        self.mul_mask(psi, mskp, n, stream)
-        self.add_scaled(psi, 1., psi_island, n, stream)
-        return self.orthogradient(msk, psi, dx, dy, nh, u, v, ny, nx, stream)
+            rc = self.mask_orthogradient(msk, mskp, psi, dx, dy, nh, u, v, ny, nx, stream)
+        else:
+            self.mul_mask(psi, mskp, n, stream)
+            self.add_scaled(psi, 1., psi_island, n, stream)
+            rc = self.orthogradient(msk, psi, dx, dy, nh, u, v, ny, nx, stream)
+        stage = getattr(self, '_uv_stage', {}).pop(_addr(h), None)
+        if stage is not None and not rc:
+            # f2d_mg_set_uv_stage: out = base + c*([extra +] tendency), numpy's rounding sequence
+            ub, vb, ue, ve, uo, vo, c = stage
+            for d, b, e, o in ((u, ub, ue, uo), (v, vb, ve, vo)):
+                D = f64(d, ny, nx)
+                f64(o, ny, nx)[...] = f64(b, ny, nx)+c*((f64(e, ny, nx)+D) if _addr(e) else D)
+        return rc
+
+    def mg_set_uv_stage(self, h, ub, vb, ue, ve, uo, vo, c):
+        if not hasattr(self, '_uv_stage'):
+            self._uv_stage = {}
+        self._uv_stage[_addr(h)] = (ub, vb, ue, ve, uo, vo, c)
+        return 0
 
     # ---- y-slab decomposition (npx = 1, npy = ranks): the communicator entry points over a
     # gloo process group (one CPU process per rank); the slab multigrid is emulated by

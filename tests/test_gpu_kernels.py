@@ -199,6 +199,47 @@ def test_mask_orthogradient(L, shape):
             g.check(g.host(dv), vr, strict, what="v")
 
 
+@pytest.mark.parametrize("shape", SHAPES + [(35, 601), (70, 262)])
+def test_mask_orthogradient_with_stage_update(L, shape):
+    """f2d_mask_orthogradient_stage: the orthogradient and, from the velocities it has just derived,
+    the Runge-Kutta stage state of u, v over the WHOLE arrays (timescheme.py:172-180) -- one kernel
+    on even nx, the orthogradient followed by f2d_ts_xpay(2) otherwise: either way exactly
+    numpy's  ub + c*du  and  ub + c*(ue + du)  of the du, dv the call itself leaves"""
+    g = _gpu()
+    lib, strict = L
+    ny, nx = shape
+    rng = np.random.default_rng(17 + ny + nx)
+    s = g.stream()
+    c = 0.3712
+    for mkind in ("ones", "random"):
+        msk = rand_mask(rng, ny, nx, mkind)
+        mskp = np.zeros(shape, dtype=np.int8)
+        mskp[:-1, :-1] = msk[:-1, :-1] & msk[:-1, 1:] & msk[1:, :-1] & msk[1:, 1:]
+        psi = rng.standard_normal(shape)
+        u0, v0 = rng.standard_normal(shape), rng.standard_normal(shape)   # the ring keeps these
+        ub, vb, ue, ve = (rng.standard_normal(shape) for _ in range(4))
+        forms = [(g.ptr(g.keep(msk)), g.ptr(g.keep(mskp)))]
+        if mkind == "ones" and nx % 2 == 0:
+            forms.append((None, None))
+        for pm, pmp in forms:
+            # plain call: the reference result of this build for psi, u, v
+            dp, du, dv = g.dev(psi), g.dev(u0), g.dev(v0)
+            lib.mask_orthogradient(pm, pmp, g.ptr(dp), 0.01, 0.02, 3, g.ptr(du), g.ptr(dv), ny, nx, s)
+            pr, ur, vr = g.host(dp), g.host(du), g.host(dv)
+            for extra in (False, True):
+                dp, du, dv = g.dev(psi), g.dev(u0), g.dev(v0)
+                uo, vo = g.dev(np.full(shape, 7.)), g.dev(np.full(shape, 7.))
+                lib.mask_orthogradient_stage(pm, pmp, g.ptr(dp), 0.01, 0.02, 3, g.ptr(du), g.ptr(dv),
+                                             g.ptr(g.keep(ub)), g.ptr(g.keep(vb)),
+                                             g.ptr(g.keep(ue)) if extra else None, g.ptr(g.keep(ve)) if extra else None,
+                                             g.ptr(uo), g.ptr(vo), c, ny, nx, s)
+                np.testing.assert_array_equal(g.host(dp), pr)
+                np.testing.assert_array_equal(g.host(du), ur)
+                np.testing.assert_array_equal(g.host(dv), vr)
+                np.testing.assert_array_equal(g.host(uo), ub + c*((ue + ur) if extra else ur))
+                np.testing.assert_array_equal(g.host(vo), vb + c*((ve + vr) if extra else vr))
+
+
 @pytest.mark.parametrize("shape", SHAPES + [(23, 37), (35, 601)])
 def test_stencil_operators(L, shape):
     g = _gpu()

@@ -327,9 +327,11 @@ class Operators(Param):
         # all-fluid domain without island: the mask-free orthogradient (no mask traffic)
         nomask = self.all_fluid and not island and self.nxl % 2 == 0
         fu = getattr(self, 'fuse_uv', None)
-        if fu is not None and x is fu[0] and self.comm is None:
+        if fu is not None and x is fu[0]:
             # Timescheme.RK3_SSP asked for the stage velocities: this inversion's orthogradient
-            # kernel writes out[u] = base[u] + coef*([extra[u] +] x[u]) (v alike) as well
+            # kernel writes out[u] = base[u] + coef*([extra[u] +] x[u]) (v alike) as well.  (On
+            # slabs too: no exchange separates the orthogradient from the combination it replaces,
+            # and the kernel writes every cell of the local array exactly as f2d_ts_xpay would.)
             _, base, extra, out, coef = fu
             lib.mg_set_uv_stage(self.gmg.h, base.rptr(iu), base.rptr(iv),
                                 extra.rptr(iu) if extra is not None else None,
